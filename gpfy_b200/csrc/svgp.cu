@@ -1,0 +1,817 @@
+// Host orchestration + C-ABI of the gpfy_b200 hot path.  Stream-ordered, no allocation, no sync.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "gemm.cuh"
+#include "svgp_kernels.cuh"
+
+namespace gpfy {
+
+// ------------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int make_shape(const GpfyDesc* desc, Shape* s) {
+  if (!desc) { set_error("descriptor is NULL"); return GPFY_EINVAL; }
+  if (desc->struct_size != sizeof(GpfyDesc) || desc->abi_version != GPFY_ABI_VERSION) {
+    set_error("descriptor size/version mismatch (got %u/%u, want %zu/%d)", desc->struct_size, desc->abi_version,
+              sizeof(GpfyDesc), GPFY_ABI_VERSION);
+    return GPFY_EINVAL;
+  }
+  if (desc->input_dim < 1 || desc->num_degrees < 1 || desc->num_degrees > GPFY_MAX_DEGREES || desc->num_outputs < 1) {
+    set_error("bad input_dim/num_degrees/num_outputs (%d/%d/%d)", desc->input_dim, desc->num_degrees, desc->num_outputs);
+    return GPFY_EINVAL;
+  }
+  s->d = desc->input_dim;
+  s->dim = s->d + 1;
+  s->dimp = round_up(s->dim, 4);
+  s->F = desc->num_degrees;
+  s->P = desc->num_outputs;
+  s->M = 0;
+  s->lsize = 0;
+  s->mmax = 0;
+  for (int l = 0; l < s->F; ++l) {
+    if (desc->m[l] < 1) { set_error("m[%d] = %d must be >= 1", l, desc->m[l]); return GPFY_EINVAL; }
+    s->off[l] = s->M;
+    s->loff[l] = s->lsize;
+    s->M += desc->m[l];
+    s->lsize += (int64_t)desc->m[l] * desc->m[l];
+    s->mmax = std::max(s->mmax, desc->m[l]);
+  }
+  s->off[s->F] = s->M;
+  s->loff[s->F] = s->lsize;
+  s->Mp = round_up(s->M, 32);
+  if (s->dimp > 36) { set_error("input_dim %d > 35 is not built (ambient dim padded to %d > 36)", s->d, s->dimp); return GPFY_EUNSUPPORTED; }
+  if (s->P > 8) { set_error("num_outputs %d > 8 is not built", s->P); return GPFY_EUNSUPPORTED; }
+  if (desc->kernel_order < 0 || desc->kernel_order > 8) { set_error("kernel_order %d out of range", desc->kernel_order); return GPFY_EINVAL; }
+  if (desc->likelihood != GPFY_LIK_GAUSSIAN && desc->likelihood != GPFY_LIK_BERNOULLI) { set_error("unknown likelihood %d", desc->likelihood); return GPFY_EINVAL; }
+  if (desc->q_kind != GPFY_Q_TRIL && desc->q_kind != GPFY_Q_FULLCOV) { set_error("unknown q_kind %d", desc->q_kind); return GPFY_EINVAL; }
+  if (desc->weight_mode != GPFY_W_ARD && desc->weight_mode != GPFY_W_SCALAR) { set_error("unknown weight_mode %d", desc->weight_mode); return GPFY_EINVAL; }
+  if (s->mmax > 1024) { set_error("m_l = %d > 1024 is not built", s->mmax); return GPFY_EUNSUPPORTED; }
+  return GPFY_OK;
+}
+
+static int device_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small parameter-algebra kernels (O(M^2) / O(M^3) per step, N-independent)
+// ------------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const double *w, *b, *v, *eig, *vhat;
+  double *sw, *sb, *dvec, *vhat_p;
+  int d, dim, dimp, M, Mp, scalar_w;
+  DegreeTable deg;
+};
+
+__global__ void prep_kernel(PrepArgs a) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int j = tid; j < a.d; j += nth) a.sw[j] = sqrt(a.w[a.scalar_w ? 0 : j]);
+  if (tid == 0) a.sb[0] = sqrt(a.b[0]);
+  if (a.dvec) {
+    for (int i = tid; i < a.Mp; i += nth) {
+      double val = 0.0;
+      if (i < a.M) {
+        int l = 0, o = 0;
+        while (i >= o + a.deg.m[l]) { o += a.deg.m[l]; ++l; }
+        val = sqrt(a.eig[l] * a.v[0]);  // sqrt(1 / Kuu) * sqrt(variance): spherical_harmonics.py:362,385
+      }
+      a.dvec[i] = val;
+    }
+  }
+  for (int e = tid; e < a.Mp * a.dimp; e += nth) {
+    int i = e / a.dimp, c = e % a.dimp;
+    a.vhat_p[e] = (i < a.M && c < a.dim) ? a.vhat[i * a.dim + c] : 0.0;
+  }
+}
+
+// Linv (dense [Mp, Mp], block diagonal): column j of block l by forward substitution with L_l.
+// One block per degree, one thread per column (strided).  Optionally scaled: out = rs[i] * Linv.
+__global__ void linv_kernel(const double* lcat, double* Linv, int Mp, DegreeTable deg) {
+  const int l = blockIdx.x;
+  int off = 0;
+  int64_t loff = 0;
+  for (int k = 0; k < l; ++k) { off += deg.m[k]; loff += (int64_t)deg.m[k] * deg.m[k]; }
+  const int m = deg.m[l];
+  const double* L = lcat + loff;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    for (int i = j; i < m; ++i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int k = j; k < i; ++k) s -= L[i * m + k] * Linv[(int64_t)(off + k) * Mp + off + j];
+      Linv[(int64_t)(off + i) * Mp + off + j] = s / L[i * m + i];
+    }
+  }
+}
+
+// out[i][j] = rs ? rs[i] * in[i][j] : in[i][j];  outT[j][i] = same      (square Mp x Mp)
+__global__ void scale_rows_transpose_kernel(const double* in, const double* rs, double* out, double* outT, int Mp) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = by + r, j = bx + threadIdx.x;
+    double val = in[(int64_t)i * Mp + j];
+    if (rs) val *= rs[i];
+    if (out) out[(int64_t)i * Mp + j] = val;
+    tile[r][threadIdx.x] = val;
+  }
+  __syncthreads();
+  if (outT)
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) outT[(int64_t)(bx + r) * Mp + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// pad [M, M] -> [Mp, Mp] (zeros outside), optionally subtracting the identity on i < M
+__global__ void pad_square_kernel(const double* in, double* out, int M, int Mp, int sub_identity) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int i = (int)(e / Mp), j = (int)(e % Mp);
+  double val = (i < M && j < M) ? in[(int64_t)i * M + j] : 0.0;
+  if (sub_identity && i == j && i < M) val -= 1.0;
+  out[e] = val;
+}
+
+__global__ void sub_identity_kernel(double* A, int M, int Mp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) A[(int64_t)i * Mp + i] -= 1.0;
+}
+
+// unpad [Mp, Mp] -> [M, M] with a scale
+__global__ void unpad_square_kernel(const double* in, double* out, int M, int Mp, double scale) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)M * M) return;
+  const int i = (int)(e / M), j = (int)(e % M);
+  out[e] = scale * in[(int64_t)i * Mp + j];
+}
+
+// y[i] = sum_j op(A)[i][j] x[j * xs]   (A [Mp, Mp]; trans: use A^T), one warp per row
+__global__ void gemv_kernel(const double* A, int Mp, int trans, const double* x, int xs, int xn, double* y, int ys, int yn) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= yn) return;
+  double s = 0.0;
+  for (int j = lane; j < xn; j += 32) s += (trans ? A[(int64_t)j * Mp + row] : A[(int64_t)row * Mp + j]) * x[(int64_t)j * xs];
+  s = warp_sum(s);
+  if (lane == 0) y[(int64_t)row * ys] = s;
+}
+
+// Gz [Mp, Mp] (full symmetric) = sum_ks Gpart blocks;  bz [Mp] = sum_ks bzpart
+__global__ void reduce_g_kernel(const double* Gpart, const double* bzpart, double* Gz, double* bz, int Mp, int nb, int nblk,
+                                int KS) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (int64_t)Mp * Mp) {
+    const int i = (int)(e / Mp), j = (int)(e % Mp);
+    int bi = i / SYRK_B, bj = j / SYRK_B, ri = i % SYRK_B, rj = j % SYRK_B;
+    if (bi < bj) { int t = bi; bi = bj; bj = t; t = ri; ri = rj; rj = t; }
+    const int blk = bi * (bi + 1) / 2 + bj;
+    double s = 0.0;
+    for (int ks = 0; ks < KS; ++ks) s += Gpart[((int64_t)ks * nblk + blk) * (SYRK_B * SYRK_B) + ri * SYRK_B + rj];
+    Gz[e] = s;
+  }
+  if (e < Mp) {
+    double s = 0.0;
+    for (int ks = 0; ks < KS; ++ks) s += bzpart[(int64_t)ks * (nb * SYRK_B) + e];
+    bz[e] = s;
+  }
+}
+
+// dVhat[i][c] = sum_ks dVpart[ks][i][c]  -> packed [M, dim]
+__global__ void reduce_dv_kernel(const double* dVpart, double* out, int M, int Mp, int dim, int dimp, int KS) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * dim) return;
+  const int i = e / dim, c = e % dim;
+  double s = 0.0;
+  for (int ks = 0; ks < KS; ++ks) s += dVpart[((int64_t)ks * Mp + i) * dimp + c];
+  out[e] = s;
+}
+
+// dd[i] = sum_j (dE[i][j] + sum_p mu[i][p] bz[p][j]) * Linv[i][j]      (one warp per row, i < M)
+__global__ void dd_kernel(const double* dE, const double* mu, const double* bz, const double* Linv, double* dd, int M, int Mp,
+                          int P) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  double s = 0.0;
+  for (int j = lane; j < M; j += 32) {
+    double val = dE[(int64_t)row * Mp + j];
+    for (int p = 0; p < P; ++p) val += mu[row * P + p] * bz[p * Mp + j];
+    s += val * Linv[(int64_t)row * Mp + j];
+  }
+  s = warp_sum(s);
+  if (lane == 0) dd[row] = s;
+}
+
+// per-degree:  B = tril(dvec_i (dE + mu bz^T))_ll ;  X = Linv_l^T B  (stored in tmp)
+__global__ void dl_step1_kernel(const double* dE, const double* mu, const double* bz, const double* dvec, const double* Linv,
+                                double* tmp, int Mp, int P, DegreeTable deg) {
+  const int l = blockIdx.x;
+  int off = 0;
+  for (int k = 0; k < l; ++k) off += deg.m[k];
+  const int m = deg.m[l];
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e % m;
+    // X[i][j] = sum_{k >= max(i, j)} Linv[k][i] * B[k][j],  B[k][j] = dvec_k * dEfull[k][j] for j <= k
+    double s = 0.0;
+    for (int k = (i > j ? i : j); k < m; ++k) {
+      const int gk = off + k, gj = off + j;
+      double b = dE[(int64_t)gk * Mp + gj];
+      for (int p = 0; p < P; ++p) b += mu[gk * P + p] * bz[p * Mp + gj];
+      s += Linv[(int64_t)gk * Mp + off + i] * dvec[gk] * b;
+    }
+    tmp[(int64_t)(off + i) * Mp + off + j] = s;
+  }
+}
+// dL_l = -(X Linv_l^T): dL[i][j] = -sum_{k <= j} X[i][k] Linv[j][k]
+__global__ void dl_step2_kernel(const double* tmp, const double* Linv, double* dlcat, int Mp, DegreeTable deg) {
+  const int l = blockIdx.x;
+  int off = 0;
+  int64_t loff = 0;
+  for (int k = 0; k < l; ++k) { off += deg.m[k]; loff += (int64_t)deg.m[k] * deg.m[k]; }
+  const int m = deg.m[l];
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e % m;
+    double s = 0.0;
+    for (int k = 0; k <= j; ++k) s += tmp[(int64_t)(off + i) * Mp + off + k] * Linv[(int64_t)(off + j) * Mp + off + k];
+    dlcat[loff + e] = (j <= i) ? -s : 0.0;
+  }
+}
+
+struct FinalArgs {
+  const double* partials;
+  int nblocks, npart;
+  const double *dd, *dvec, *eig, *w, *b, *v;
+  int M, d, scalar_w;
+  DegreeTable deg;
+  double* packed;
+  GpfyElboLayout lay;
+};
+// single block: deterministic tree over the per-block partials, then the scalar chain rules
+__global__ void finalize_kernel(FinalArgs a) {
+  __shared__ double sums[64];
+  __shared__ double red[256];
+  for (int k = 0; k < a.npart; ++k) {
+    double s = 0.0;
+    for (int bI = threadIdx.x; bI < a.nblocks; bI += blockDim.x) s += a.partials[(int64_t)bI * a.npart + k];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[k] = red[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.packed[a.lay.data_term] = sums[PART_E];
+    a.packed[a.lay.d_sigma2] = sums[PART_DS2];
+    a.packed[a.lay.d_b] = sums[PART_DB] / (2.0 * sqrt(a.b[0]));
+    if (a.scalar_w) {
+      double s = 0.0;
+      for (int j = 0; j < a.d; ++j) s += sums[PART_DW + j];
+      a.packed[a.lay.d_w] = s / (2.0 * a.w[0]);
+    } else {
+      for (int j = 0; j < a.d; ++j) a.packed[a.lay.d_w + j] = sums[PART_DW + j] / (2.0 * a.w[j]);
+    }
+    // eigenvalue / variance chain:  d_i = sqrt(eig_l v)
+    double dv = sums[PART_DV];
+    int i = 0;
+    for (int l = 0; l < a.deg.F; ++l) {
+      double s = 0.0;
+      for (int j = 0; j < a.deg.m[l]; ++j, ++i) s += a.dd[i] * a.dvec[i];
+      a.packed[a.lay.d_eig + l] = s / (2.0 * a.eig[l]);
+      dv += s / (2.0 * a.v[0]);
+    }
+    a.packed[a.lay.d_v] = dv;
+  }
+}
+
+// d_mu[i][p] = y[i] (strided store helper is gemv's ys); KL kernels below
+__global__ void kl_tril_kernel(const double* mu, const double* L, double* out, int M, int P) {
+  // variational.py:225-240,262-286:  KL = -MP/2 - 1/2 sum log diag(L)^2 + 1/2 |mu|^2 + 1/2 |L|_F^2
+  __shared__ double red[256];
+  const int64_t nmu = (int64_t)M * P, nL = (int64_t)P * M * M;
+  double s = 0.0;
+  for (int64_t e = threadIdx.x; e < nmu; e += blockDim.x) { s += 0.5 * mu[e] * mu[e]; out[1 + e] = mu[e]; }
+  for (int64_t e = threadIdx.x; e < nL; e += blockDim.x) {
+    const int i = (int)((e / M) % M), j = (int)(e % M);
+    const double v = L[e];
+    s += 0.5 * v * v;
+    double gr = v;
+    if (i == j) { s -= 0.5 * log(v * v); gr -= 1.0 / v; }
+    out[1 + nmu + e] = gr;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0] - 0.5 * (double)nmu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace plan
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+  Shape s;
+  int sms;
+  int64_t nc;       // points per chunk (multiple of 128)
+  int nb, nblk, KS; // SYRK blocks / splits
+  int KSV;          // dVhat splits
+  int64_t nblocks_c; // lik_bwd blocks per full chunk
+  int npart;
+  // offsets (doubles)
+  int64_t o_sw, o_sb, o_dvec, o_vhat_p, o_mu2, o_linv, o_E, o_ET, o_tmp1, o_tmp2, o_tmp3, o_LqP, o_W0, o_W2, o_dE, o_Gz, o_bz,
+      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, total;
+};
+
+static int64_t choose_chunk(int sms, int64_t n) {
+  // GEMM tiles are 96 x 128 with 2 CTAs per SM resident: chunks of 128 * 2 * sms points make every
+  // row-tile sweep an exact number of waves; small inputs use one chunk.
+  int64_t nc = (int64_t)128 * 2 * sms;
+  int64_t need = round_up64(n, 128);
+  return need < nc ? need : nc;
+}
+
+static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
+  p->s = s;
+  p->sms = device_sms();
+  p->nc = choose_chunk(p->sms, n);
+  p->nb = (s.Mp + SYRK_B - 1) / SYRK_B;
+  p->nblk = p->nb * (p->nb + 1) / 2;
+  p->KS = std::max(1, (2 * p->sms) / p->nblk);
+  p->KSV = std::max(1, (4 * p->sms) / (s.Mp / 16));
+  p->nblocks_c = p->nc / 128;
+  p->npart = PART_DW + s.d;
+  const int64_t Mp = s.Mp, Mp2 = Mp * Mp;
+  int64_t o = 0;
+  auto take = [&](int64_t cnt) { int64_t r = o; o += round_up64(cnt, 32); return r; };  // 256-byte aligned
+  p->o_sw = take(s.d);
+  p->o_sb = take(1);
+  p->o_dvec = take(Mp);
+  p->o_vhat_p = take(Mp * s.dimp + (int64_t)s.P * Mp);  // mu2 sits right behind vhat_p (one TMA transaction)
+  p->o_mu2 = p->o_vhat_p + Mp * s.dimp;
+  p->o_linv = take(Mp2);
+  p->o_E = take(Mp2);
+  p->o_ET = take(Mp2);
+  p->o_tmp1 = take(Mp2);
+  p->o_tmp2 = take(Mp2);
+  p->o_tmp3 = take(Mp2);
+  p->o_LqP = take(s.P * Mp2);
+  p->o_W0 = take(s.P * Mp2);
+  p->o_W2 = take(s.P * Mp2);
+  p->o_dE = take(Mp2);
+  p->o_Gz = take(Mp2);
+  p->o_bz = take(s.P * Mp);
+  p->o_dd = take(Mp);
+  p->o_partials = take(p->nblocks_c * p->npart);
+  if (op == GPFY_OP_ELBO) {
+    p->o_Gpart = take((int64_t)s.P * p->KS * p->nblk * SYRK_B * SYRK_B);
+    p->o_bzpart = take((int64_t)s.P * p->KS * p->nb * SYRK_B);
+    p->o_dVpart = take((int64_t)p->KSV * Mp * s.dimp);
+  } else {
+    p->o_Gpart = p->o_bzpart = p->o_dVpart = o;
+  }
+  p->o_Z = take((Mp + 32) * p->nc);
+  p->o_C = take((op == GPFY_OP_FEATURES ? 0 : (int64_t)s.P * Mp * p->nc));
+  p->o_XH = take(p->nc * s.dimp);
+  p->o_R = take(p->nc);
+  p->o_wq = take((int64_t)s.P * p->nc);
+  p->o_wp = take((int64_t)s.P * p->nc);
+  p->total = o;
+}
+
+static DegreeTable degree_table(const GpfyDesc* desc) {
+  DegreeTable t;
+  t.F = desc->num_degrees;
+  for (int l = 0; l < GPFY_MAX_DEGREES; ++l) t.m[l] = l < t.F ? desc->m[l] : 0;
+  return t;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  GPFY_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return GPFY_OK;
+}
+
+// dispatch on the padded ambient dimension
+#define GPFY_DISPATCH_DIMP(dimp, CALL)          \
+  switch (dimp) {                               \
+    case 4: { constexpr int DIMP = 4; CALL; } break;   \
+    case 8: { constexpr int DIMP = 8; CALL; } break;   \
+    case 12: { constexpr int DIMP = 12; CALL; } break; \
+    case 16: { constexpr int DIMP = 16; CALL; } break; \
+    case 20: { constexpr int DIMP = 20; CALL; } break; \
+    case 24: { constexpr int DIMP = 24; CALL; } break; \
+    case 28: { constexpr int DIMP = 28; CALL; } break; \
+    case 32: { constexpr int DIMP = 32; CALL; } break; \
+    case 36: { constexpr int DIMP = 36; CALL; } break; \
+    default: set_error("unsupported padded dim %d", dimp); return GPFY_EUNSUPPORTED; \
+  }
+
+template <int DIMP>
+static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
+  const int smem = a.Mp * DIMP * 8;
+  GPFY_TRY(set_smem(zonal_fwd_kernel<DIMP>, smem));
+  const int64_t nthreads = (a.npts + 1) & ~(int64_t)1;
+  zonal_fwd_kernel<DIMP><<<(unsigned)((nthreads + 127) / 128), 128, smem, st>>>(a);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
+template <int DIMP>
+static int launch_lik_bwd(cudaStream_t st, const LikBwdArgs& a) {
+  const int smem = (a.Mp * DIMP + a.P * a.Mp) * 8;
+  const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 127) / 128);
+#define GPFY_LB(PM)                                              \
+  {                                                              \
+    GPFY_TRY(set_smem(lik_bwd_kernel<DIMP, PM>, smem));          \
+    lik_bwd_kernel<DIMP, PM><<<grid, 128, smem, st>>>(a);        \
+  }
+  if (a.P == 1) GPFY_LB(1) else if (a.P == 2) GPFY_LB(2) else if (a.P <= 4) GPFY_LB(4) else GPFY_LB(8)
+#undef GPFY_LB
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
+template <int DIMP>
+static int launch_dvhat(cudaStream_t st, const DvhatArgs& a) {
+  dvhat_kernel<DIMP><<<(a.Mp / 16) * a.KS, 128, 0, st>>>(a);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
+static int launch_predict(cudaStream_t st, const PredictArgs& a) {
+  const unsigned grid = (unsigned)((a.npts + 127) / 128);
+  if (a.P == 1) predict_kernel<1><<<grid, 128, 0, st>>>(a);
+  else if (a.P == 2) predict_kernel<2><<<grid, 128, 0, st>>>(a);
+  else if (a.P <= 4) predict_kernel<4><<<grid, 128, 0, st>>>(a);
+  else predict_kernel<8><<<grid, 128, 0, st>>>(a);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
+static int gemm_sq(cudaStream_t st, const double* A, const double* B, double* C, int Mp, double alpha, double beta, int sms) {
+  GemmArgs g;
+  g.A = A; g.lda = Mp; g.B = B; g.ldb = Mp; g.C = C; g.ldc = Mp;
+  g.m = g.n = g.k = Mp;
+  g.alpha = alpha; g.beta = beta;
+  return launch_gemm(st, g, sms);
+}
+
+#define GPFY_K(kernel, grid, block, smem, st, ...)    \
+  do {                                                \
+    kernel<<<grid, block, smem, st>>>(__VA_ARGS__);   \
+    GPFY_COUNT_LAUNCH();                              \
+    GPFY_LAUNCH_OK();                                 \
+  } while (0)
+
+// Shared prologue: sqrt weights, padded Vhat, Linv, E = diag(sqrt(eig v)) Linv, E^T, and per output
+// W0 = L L^T - I (or Sigma - I), W2 = E^T W0 E, mu2 = E^T mu.
+static int run_prologue(cudaStream_t st, const GpfyDesc* desc, const Plan& p, double* ws, const double* w, const double* b,
+                        const double* v, const double* eig, const double* vhat, const double* lcat, const double* mu,
+                        const double* sigma, bool need_model) {
+  const Shape& s = p.s;
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  DegreeTable deg = degree_table(desc);
+  PrepArgs pa;
+  pa.w = w; pa.b = b; pa.v = v; pa.eig = eig; pa.vhat = vhat;
+  pa.sw = ws + p.o_sw; pa.sb = ws + p.o_sb; pa.dvec = need_model ? ws + p.o_dvec : nullptr; pa.vhat_p = ws + p.o_vhat_p;
+  pa.d = s.d; pa.dim = s.dim; pa.dimp = s.dimp; pa.M = s.M; pa.Mp = Mp; pa.scalar_w = desc->weight_mode == GPFY_W_SCALAR;
+  pa.deg = deg;
+  GPFY_K(prep_kernel, 32, 256, 0, st, pa);
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_linv, 0, Mp2 * 8, st));
+  GPFY_K(linv_kernel, s.F, 128, 0, st, lcat, ws + p.o_linv, Mp, deg);
+  if (!need_model) return GPFY_OK;
+  dim3 tg(Mp / 32, Mp / 32), tb(32, 8);
+  GPFY_K(scale_rows_transpose_kernel, tg, tb, 0, st, ws + p.o_linv, ws + p.o_dvec, ws + p.o_E, ws + p.o_ET, Mp);
+  const unsigned sqg = (unsigned)((Mp2 + 255) / 256);
+  for (int q = 0; q < s.P; ++q) {
+    double* W0 = ws + p.o_W0 + q * Mp2;
+    if (desc->q_kind == GPFY_Q_TRIL) {
+      double* LqP = ws + p.o_LqP + q * Mp2;
+      GPFY_K(pad_square_kernel, sqg, 256, 0, st, sigma + (int64_t)q * s.M * s.M, LqP, s.M, Mp, 0);
+      GPFY_K(scale_rows_transpose_kernel, tg, tb, 0, st, LqP, (const double*)nullptr, (double*)nullptr, ws + p.o_tmp1, Mp);
+      GPFY_TRY(gemm_sq(st, LqP, ws + p.o_tmp1, W0, Mp, 1.0, 0.0, p.sms));  // L L^T   (variational.py:326-327)
+      GPFY_K(sub_identity_kernel, (s.M + 127) / 128, 128, 0, st, W0, s.M, Mp);
+    } else {
+      GPFY_K(pad_square_kernel, sqg, 256, 0, st, sigma + (int64_t)q * s.M * s.M, W0, s.M, Mp, 1);  // Sigma - I (variational.py:438-440)
+    }
+    GPFY_TRY(gemm_sq(st, W0, ws + p.o_E, ws + p.o_tmp1, Mp, 1.0, 0.0, p.sms));              // W0 E
+    GPFY_TRY(gemm_sq(st, ws + p.o_ET, ws + p.o_tmp1, ws + p.o_W2 + q * Mp2, Mp, 1.0, 0.0, p.sms));  // E^T W0 E
+    // mu2_q = E^T mu[:, q]
+    GPFY_K(gemv_kernel, (Mp + 3) / 4, 128, 0, st, ws + p.o_E, Mp, 1, mu + q, s.P, s.M, ws + p.o_mu2 + (int64_t)q * Mp, 1, Mp);
+  }
+  return GPFY_OK;
+}
+
+static int check_ws(const Plan& p, void* workspace, size_t bytes) {
+  if (!workspace || ((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned and non-NULL"); return GPFY_EWORKSPACE; }
+  if (bytes < (size_t)p.total * 8) { set_error("workspace too small: %zu < %zu bytes", bytes, (size_t)p.total * 8); return GPFY_EWORKSPACE; }
+  return GPFY_OK;
+}
+
+}  // namespace gpfy
+
+using namespace gpfy;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gpfy_abi_version(void) { return GPFY_ABI_VERSION; }
+const char* gpfy_last_error_string(void) { return g_err; }
+GPFY_API unsigned long long gpfy_debug_launch_count(void) { return g_launch_count; }
+
+int64_t gpfy_num_inducing(const GpfyDesc* desc) {
+  Shape s;
+  int rc = make_shape(desc, &s);
+  return rc == GPFY_OK ? s.M : rc;
+}
+
+int gpfy_elbo_packed_layout(const GpfyDesc* desc, GpfyElboLayout* out) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (!out) { set_error("out is NULL"); return GPFY_EINVAL; }
+  int64_t o = 0;
+  out->data_term = o; o += 1;
+  out->d_mu = o; o += (int64_t)s.M * s.P;
+  out->d_sigma = o; o += (int64_t)s.P * s.M * s.M;
+  out->d_eig = o; o += s.F;
+  out->d_vhat = o; o += (int64_t)s.M * s.dim;
+  out->d_lcat = o; o += s.lsize;
+  out->d_w = o; o += desc->weight_mode == GPFY_W_SCALAR ? 1 : s.d;
+  out->d_b = o; o += 1;
+  out->d_v = o; o += 1;
+  out->d_sigma2 = o; o += 1;
+  out->total = o;
+  return GPFY_OK;
+}
+
+int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t* bytes) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (!bytes || n_points < 0 || op < GPFY_OP_FEATURES || op > GPFY_OP_PREDICT) { set_error("bad argument"); return GPFY_EINVAL; }
+  Plan p;
+  make_plan(s, n_points, op, &p);
+  *bytes = (size_t)p.total * 8;
+  return GPFY_OK;
+}
+
+int gpfy_gegenbauer(void* stream, int level, double alpha, const double* x, int64_t n, double* out, double* dout) {
+  if (level < 0 || level > GPFY_MAX_DEGREES) { set_error("level %d out of range", level); return GPFY_EINVAL; }
+  if (n == 0) return GPFY_OK;
+  RecCoef rc = make_rec_coef(alpha);
+  GPFY_K(gegenbauer_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, rc, level, x, n, out, dout);
+  return GPFY_OK;
+}
+
+int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const double* X, int apply_to_sphere, const double* w,
+                         const double* b, const double* vhat, const double* lcat, const double* degree_scale, int mul_r,
+                         double* out, double* r_out, void* workspace, size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (n == 0) return GPFY_OK;
+  Plan p;
+  make_plan(s, n, GPFY_OP_FEATURES, &p);
+  GPFY_TRY(check_ws(p, workspace, workspace_bytes));
+  double* ws = (double*)workspace;
+  const int Mp = s.Mp;
+  DegreeTable deg = degree_table(desc);
+  // parameter prologue; when X is already on the sphere w/b are unused: reuse vhat as a dummy pointer
+  GPFY_TRY(run_prologue(st, desc, p, ws, apply_to_sphere ? w : vhat, apply_to_sphere ? b : vhat, nullptr, nullptr, vhat, lcat,
+                        nullptr, nullptr, false));
+  RecCoef rc = make_rec_coef(desc->alpha);
+  for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
+    const int64_t npts = std::min(p.nc, n - c0);
+    ZonalArgs za;
+    za.X = X + c0 * (apply_to_sphere ? s.d : s.dim);
+    za.xcols = apply_to_sphere ? s.d : s.dim;
+    za.apply_to_sphere = apply_to_sphere;
+    za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
+    za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R;
+    za.deg = deg; za.rc = rc;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+    WhitenArgs wa;
+    wa.Z = ws + p.o_Z; wa.ldz = p.nc; wa.Linv = ws + p.o_linv; wa.Mp = Mp;
+    wa.scale = degree_scale; wa.R = mul_r ? ws + p.o_R : nullptr; wa.npts = npts;
+    wa.out = out + c0; wa.ldo = n; wa.deg = deg;
+    GPFY_K(whiten_kernel, (unsigned)((npts + 127) / 128), 128, 0, st, wa);
+    if (r_out) GPFY_CUDA_OK(cudaMemcpyAsync(r_out + c0, ws + p.o_R, npts * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return GPFY_OK;
+}
+
+int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* Y, const double* w,
+                           const double* b, const double* variance, const double* eig, const double* vhat, const double* lcat,
+                           const double* mu, const double* sigma, const double* sigma2, double* packed, void* workspace,
+                           size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  Plan p;
+  make_plan(s, n, GPFY_OP_ELBO, &p);
+  GPFY_TRY(check_ws(p, workspace, workspace_bytes));
+  GpfyElboLayout lay;
+  GPFY_TRY(gpfy_elbo_packed_layout(desc, &lay));
+  double* ws = (double*)workspace;
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  DegreeTable deg = degree_table(desc);
+  RecCoef rc = make_rec_coef(desc->alpha);
+
+  GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
+  // zero the pad rows of Z once (never written by the zonal kernel) and the accumulators' first use is
+  // handled by accumulate = 0 on the first chunk
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
+  if (n == 0) {
+    GPFY_CUDA_OK(cudaMemsetAsync(packed, 0, lay.total * 8, st));
+    return GPFY_OK;
+  }
+
+  int chunk = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += p.nc, ++chunk) {
+    const int64_t npts = std::min(p.nc, n - c0);
+    const int64_t npts_e = (npts + 1) & ~(int64_t)1;
+    ZonalArgs za;
+    za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
+    za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
+    za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R;
+    za.deg = deg; za.rc = rc;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+
+    for (int q = 0; q < s.P; ++q) {  // C_q = W2_q Z
+      GemmArgs g;
+      g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
+      g.B = ws + p.o_Z; g.ldb = p.nc;
+      g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
+      g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
+      GPFY_TRY(launch_gemm(st, g, p.sms));
+    }
+
+    LikBwdArgs la;
+    la.Z = ws + p.o_Z; la.C = ws + p.o_C; la.ldz = p.nc; la.c_stride = (int64_t)Mp * p.nc;
+    la.XH = ws + p.o_XH; la.R = ws + p.o_R; la.Y = Y + c0 * s.P;
+    la.vhat_p = ws + p.o_vhat_p; la.mu2 = ws + p.o_mu2; la.vptr = variance; la.s2ptr = sigma2;
+    la.Mp = Mp; la.M = s.M; la.d = s.d; la.P = s.P; la.order = desc->kernel_order; la.npts = npts;
+    la.wq = ws + p.o_wq; la.wp = ws + p.o_wp; la.partials = ws + p.o_partials; la.npart = p.npart;
+    la.accumulate = chunk > 0 && (((npts_e + 127) / 128) <= p.nblocks_c);
+    la.lik_kind = desc->likelihood; la.deg = deg; la.rc = rc;
+    if (chunk == 0 && ((npts_e + 127) / 128) < p.nblocks_c)  // single short chunk: clear unused slots
+      GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, p.nblocks_c * p.npart * 8, st));
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_lik_bwd<DIMP>(st, la)));
+
+    for (int q = 0; q < s.P; ++q) {
+      SyrkArgs sa;
+      sa.Z = ws + p.o_Z; sa.ldz = p.nc; sa.Mp = Mp; sa.npts = npts;
+      sa.wq = ws + p.o_wq + (int64_t)q * p.nc; sa.wp = ws + p.o_wp + (int64_t)q * p.nc;
+      sa.Gpart = ws + p.o_Gpart + (int64_t)q * p.KS * p.nblk * SYRK_B * SYRK_B;
+      sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.KS * p.nb * SYRK_B;
+      sa.nb = p.nb; sa.nblk = p.nblk; sa.KS = p.KS;
+      sa.range = round_up64((p.nc + p.KS - 1) / p.KS, SYRK_BK);
+      sa.accumulate = chunk > 0;
+      static bool cfg = false;
+      if (!cfg) { GPFY_TRY(set_smem(syrk_dmma_kernel, SYRK_SMEM)); cfg = true; }
+      GPFY_K(syrk_dmma_kernel, p.nblk * p.KS, SYRK_THREADS, SYRK_SMEM, st, sa);
+    }
+
+    DvhatArgs da;
+    da.dT = ws + p.o_C; da.ldz = p.nc; da.XH = ws + p.o_XH; da.Mp = Mp; da.npts = npts;
+    da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 32);
+    da.accumulate = chunk > 0;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_dvhat<DIMP>(st, da)));
+  }
+
+  // ---- epilogue: gradients of the folded matrices back to the reference's parameters ----
+  const unsigned sqg = (unsigned)((Mp2 + 255) / 256);
+  for (int q = 0; q < s.P; ++q) {
+    double* Gz = ws + p.o_Gz;
+    double* bz = ws + p.o_bz + (int64_t)q * Mp;
+    GPFY_K(reduce_g_kernel, sqg, 256, 0, st, ws + p.o_Gpart + (int64_t)q * p.KS * p.nblk * SYRK_B * SYRK_B,
+           ws + p.o_bzpart + (int64_t)q * p.KS * p.nb * SYRK_B, Gz, bz, Mp, p.nb, p.nblk, p.KS);
+    GPFY_TRY(gemm_sq(st, ws + p.o_E, Gz, ws + p.o_tmp1, Mp, 1.0, 0.0, p.sms));             // T1 = E Gz
+    GPFY_TRY(gemm_sq(st, ws + p.o_tmp1, ws + p.o_ET, ws + p.o_tmp2, Mp, 1.0, 0.0, p.sms));  // dW0 = T1 E^T
+    double* dsig = packed + lay.d_sigma + (int64_t)q * s.M * s.M;
+    const unsigned ug = (unsigned)(((int64_t)s.M * s.M + 255) / 256);
+    if (desc->q_kind == GPFY_Q_TRIL) {
+      GPFY_TRY(gemm_sq(st, ws + p.o_tmp2, ws + p.o_LqP + q * Mp2, ws + p.o_tmp3, Mp, 2.0, 0.0, p.sms));  // 2 dW0 L
+      GPFY_K(unpad_square_kernel, ug, 256, 0, st, ws + p.o_tmp3, dsig, s.M, Mp, 1.0);
+    } else {
+      GPFY_K(unpad_square_kernel, ug, 256, 0, st, ws + p.o_tmp2, dsig, s.M, Mp, 1.0);
+    }
+    // d mu[:, q] = E bz_q
+    GPFY_K(gemv_kernel, (s.M + 3) / 4, 128, 0, st, ws + p.o_E, Mp, 0, bz, 1, Mp, packed + lay.d_mu + q, s.P, s.M);
+    // dE += 2 W0_q T1
+    GPFY_TRY(gemm_sq(st, ws + p.o_W0 + q * Mp2, ws + p.o_tmp1, ws + p.o_dE, Mp, 2.0, q > 0 ? 1.0 : 0.0, p.sms));
+  }
+  GPFY_K(dd_kernel, (s.M + 3) / 4, 128, 0, st, ws + p.o_dE, mu, ws + p.o_bz, ws + p.o_linv, ws + p.o_dd, s.M, Mp, s.P);
+  GPFY_K(dl_step1_kernel, s.F, 256, 0, st, ws + p.o_dE, mu, ws + p.o_bz, ws + p.o_dvec, ws + p.o_linv, ws + p.o_tmp1, Mp, s.P, deg);
+  GPFY_K(dl_step2_kernel, s.F, 256, 0, st, ws + p.o_tmp1, ws + p.o_linv, packed + lay.d_lcat, Mp, deg);
+  GPFY_K(reduce_dv_kernel, (s.M * s.dim + 255) / 256, 256, 0, st, ws + p.o_dVpart, packed + lay.d_vhat, s.M, Mp, s.dim, s.dimp, p.KSV);
+  FinalArgs fa;
+  fa.partials = ws + p.o_partials; fa.nblocks = (int)p.nblocks_c; fa.npart = p.npart;
+  fa.dd = ws + p.o_dd; fa.dvec = ws + p.o_dvec; fa.eig = eig; fa.w = w; fa.b = b; fa.v = variance;
+  fa.M = s.M; fa.d = s.d; fa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; fa.deg = deg; fa.packed = packed; fa.lay = lay;
+  GPFY_K(finalize_kernel, 1, 256, 0, st, fa);
+  return GPFY_OK;
+}
+
+int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (desc->q_kind != GPFY_Q_TRIL) {
+    set_error("prior KL for a full-covariance q needs a Cholesky of Sigma: left to the host framework");
+    return GPFY_EUNSUPPORTED;
+  }
+  GPFY_K(kl_tril_kernel, 1, 256, 0, (cudaStream_t)stream, mu, sigma, out, s.M, s.P);
+  return GPFY_OK;
+}
+
+int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* w, const double* b,
+                      const double* variance, const double* eig, const double* vhat, const double* lcat, const double* mu,
+                      const double* sigma, double* fmu, double* fvar, void* workspace, size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (n == 0) return GPFY_OK;
+  Plan p;
+  make_plan(s, n, GPFY_OP_PREDICT, &p);
+  GPFY_TRY(check_ws(p, workspace, workspace_bytes));
+  double* ws = (double*)workspace;
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  DegreeTable deg = degree_table(desc);
+  RecCoef rc = make_rec_coef(desc->alpha);
+  GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
+  for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
+    const int64_t npts = std::min(p.nc, n - c0);
+    const int64_t npts_e = (npts + 1) & ~(int64_t)1;
+    ZonalArgs za;
+    za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
+    za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
+    za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R;
+    za.deg = deg; za.rc = rc;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+    for (int q = 0; q < s.P; ++q) {
+      GemmArgs g;
+      g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
+      g.B = ws + p.o_Z; g.ldb = p.nc;
+      g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
+      g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
+      GPFY_TRY(launch_gemm(st, g, p.sms));
+    }
+    PredictArgs pa;
+    pa.Z = ws + p.o_Z; pa.C = ws + p.o_C; pa.ldz = p.nc; pa.c_stride = (int64_t)Mp * p.nc;
+    pa.R = ws + p.o_R; pa.mu2 = ws + p.o_mu2; pa.vptr = variance;
+    pa.Mp = Mp; pa.M = s.M; pa.P = s.P; pa.order = desc->kernel_order; pa.npts = npts;
+    pa.fmu = fmu + c0 * s.P; pa.fvar = fvar + c0 * s.P;
+    GPFY_TRY(launch_predict(st, pa));
+  }
+  return GPFY_OK;
+}
+
+// NCCL is resolved from the process at run time (the host framework's copy)
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, void*);
+}  // extern "C"
+
+#include <dlfcn.h>
+extern "C" int gpfy_allreduce_packed(void* nccl_comm, void* stream, double* packed, int64_t count) {
+  static nccl_allreduce_fn fn = nullptr;
+  if (!fn) {
+    fn = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!fn) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) fn = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+    }
+    if (!fn) { set_error("ncclAllReduce not found in the process or libnccl.so.2"); return GPFY_EUNSUPPORTED; }
+  }
+  // ncclDouble = 8, ncclSum = 0
+  int rc = fn(packed, packed, (size_t)count, 8, 0, nccl_comm, stream);
+  if (rc != 0) { set_error("ncclAllReduce returned %d", rc); return GPFY_ECUDA; }
+  return GPFY_OK;
+}

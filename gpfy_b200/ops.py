@@ -1,0 +1,158 @@
+"""Device-side operators of the hot path: thin Python over the C-ABI.
+
+torch is used only for device memory and the current CUDA stream; every computation happens in
+libgpfy_b200.so.  All arrays are float64 (the reference forces x64, utils.py:26 / param.py:151).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _as_dev(x, device):
+    if torch.is_tensor(x):
+        t = x.to(device=device, dtype=torch.float64)
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64)), device=device)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.GpfyError("gpfy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def gegenbauer(level, alpha, x, with_grad=False, device=None):
+    """C_level^alpha(x) (and d/dx) on the device — gegenbauer.py:63-85."""
+    lib = _lib.load()
+    device = require_cuda(device)
+    xt = _as_dev(x, device)
+    out = torch.empty_like(xt)
+    dout = torch.empty_like(xt) if with_grad else None
+    _lib.check(lib.gpfy_gegenbauer(_stream(device), int(level), float(alpha), _ptr(xt), xt.numel(), _ptr(out), _ptr(dout)))
+    return (out, dout) if with_grad else out
+
+
+class HotPath:
+    """One descriptor + cached scratch.  Mirrors the static configuration of
+    (SphericalHarmonics, kernel, q, likelihood) in the reference."""
+
+    def __init__(self, input_dim, m, num_outputs=1, kernel_order=1, likelihood="gaussian", q_kind="tril",
+                 weight_mode="ard", device=None):
+        self.lib = _lib.load()
+        self.device = require_cuda(device)
+        self.m = [int(v) for v in m]
+        self.input_dim = int(input_dim)
+        self.dim = self.input_dim + 1
+        self.M = int(sum(self.m))
+        self.P = int(num_outputs)
+        self.F = len(self.m)
+        self.lsize = int(sum(v * v for v in self.m))
+        self.scalar_w = weight_mode == "scalar"
+        self.desc = _lib.make_desc(
+            input_dim, self.m, num_outputs, kernel_order,
+            _lib.LIK_GAUSSIAN if likelihood == "gaussian" else _lib.LIK_BERNOULLI,
+            _lib.Q_TRIL if q_kind == "tril" else _lib.Q_FULLCOV,
+            _lib.W_SCALAR if self.scalar_w else _lib.W_ARD)
+        self.layout = _lib.GpfyElboLayout()
+        _lib.check(self.lib.gpfy_elbo_packed_layout(ctypes.byref(self.desc), ctypes.byref(self.layout)))
+        self._ws = {}
+
+    # ------------------------------------------------------------------
+    def workspace(self, n, op):
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.gpfy_workspace_bytes(ctypes.byref(self.desc), int(n), int(op), ctypes.byref(nbytes)))
+        key = op
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes.value:
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _dev(self, x):
+        return _as_dev(x, self.device)
+
+    # ------------------------------------------------------------------
+    def features(self, X, vhat, lcat, w=None, b=None, degree_scale=None, mul_r=False, apply_to_sphere=True):
+        """[M, N] feature matrix and radii (spherical_harmonics.py:290-320,344-362,385-387)."""
+        X = self._dev(X)
+        n = X.shape[0]
+        vhat, lcat = self._dev(vhat), self._dev(lcat)
+        w = self._dev(w) if w is not None else None
+        b = self._dev(b) if b is not None else None
+        ds = self._dev(degree_scale) if degree_scale is not None else None
+        out = torch.empty((self.M, n), dtype=torch.float64, device=self.device)
+        r = torch.empty((n,), dtype=torch.float64, device=self.device)
+        ws = self.workspace(n, _lib.OP_FEATURES)
+        _lib.check(self.lib.gpfy_sh_features_fwd(
+            _stream(self.device), ctypes.byref(self.desc), n, _ptr(X), int(bool(apply_to_sphere)), _ptr(w), _ptr(b),
+            _ptr(vhat), _ptr(lcat), _ptr(ds), int(bool(mul_r)), _ptr(out), _ptr(r), _ptr(ws), ws.numel()))
+        return out, r
+
+    def elbo_valgrad_packed(self, X, Y, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out=None):
+        """Packed [data term, gradients] for the rows given (sums; see GpfyElboLayout)."""
+        X, Y = self._dev(X), self._dev(Y)
+        n = X.shape[0]
+        args = [self._dev(a) for a in (w, b, variance, eig, vhat, lcat, mu, sigma)]
+        s2 = self._dev(sigma2 if sigma2 is not None else 1.0)
+        if out is None:
+            out = torch.empty((self.layout.total,), dtype=torch.float64, device=self.device)
+        ws = self.workspace(n, _lib.OP_ELBO)
+        _lib.check(self.lib.gpfy_svgp_elbo_valgrad(
+            _stream(self.device), ctypes.byref(self.desc), n, _ptr(X), _ptr(Y), *[_ptr(a) for a in args], _ptr(s2),
+            _ptr(out), _ptr(ws), ws.numel()))
+        return out
+
+    def unpack(self, packed):
+        """Views of a packed buffer keyed like the oracle's gradient dict."""
+        L = self.layout
+        M, P, F, d, dim = self.M, self.P, self.F, self.input_dim, self.dim
+        g = {
+            "data_term": packed[L.data_term],
+            "mu": packed[L.d_mu:L.d_mu + M * P].view(M, P),
+            "sigma": packed[L.d_sigma:L.d_sigma + P * M * M].view(P, M, M),
+            "eig": packed[L.d_eig:L.d_eig + F],
+            "vhat": packed[L.d_vhat:L.d_vhat + M * dim].view(M, dim),
+            "lcat": packed[L.d_lcat:L.d_lcat + self.lsize],
+            "w": packed[L.d_w:L.d_w + (1 if self.scalar_w else d)],
+            "b": packed[L.d_b],
+            "v": packed[L.d_v],
+            "sigma2": packed[L.d_sigma2],
+        }
+        return g
+
+    def predict_diag(self, X, w, b, variance, eig, vhat, lcat, mu, sigma):
+        """(fmu, fvar), each [N, P] — model.py:201-229."""
+        X = self._dev(X)
+        n = X.shape[0]
+        args = [self._dev(a) for a in (w, b, variance, eig, vhat, lcat, mu, sigma)]
+        fmu = torch.empty((n, self.P), dtype=torch.float64, device=self.device)
+        fvar = torch.empty((n, self.P), dtype=torch.float64, device=self.device)
+        ws = self.workspace(n, _lib.OP_PREDICT)
+        _lib.check(self.lib.gpfy_predict_diag(
+            _stream(self.device), ctypes.byref(self.desc), n, _ptr(X), *[_ptr(a) for a in args], _ptr(fmu), _ptr(fvar),
+            _ptr(ws), ws.numel()))
+        return fmu, fvar
+
+    def prior_kl_valgrad(self, mu, sigma):
+        """KL(q || N(0, I)), dKL/dmu [M, P], dKL/dSigma [P, M, M] (TriL) — variational.py:225-240."""
+        mu, sigma = self._dev(mu), self._dev(sigma)
+        M, P = self.M, self.P
+        out = torch.empty((1 + M * P + P * M * M,), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gpfy_prior_kl_valgrad(_stream(self.device), ctypes.byref(self.desc), _ptr(mu), _ptr(sigma), _ptr(out)))
+        return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
+
+
+def launch_count():
+    return int(_lib.load().gpfy_debug_launch_count())

@@ -1,0 +1,152 @@
+/* gpfy_b200 — C-ABI of the B200-native GPfY hot path (sm_100a).
+ *
+ * Drop-in boundary for ONE path of stefanosele/GPfY: spherical-harmonic features Phi(X) and the
+ * sparse variational ELBO (+ gradient, + predict_diag) built on them.  The reference has no FFI of
+ * its own (pure Python/JAX); these are the entry points its `jax.ffi` custom calls bind (see
+ * INTEGRATION.md and gpfy_b200/csrc/xla_ffi_shim.cc).  Citations: /root/reference/src/gpfy/<file>:<line>.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host".
+ *   - all arithmetic is IEEE float64 (the reference forces x64: utils.py:26, param.py:151).
+ *   - stream-ordered: every call only enqueues work on `stream`; no allocation, no host sync.
+ *     Scratch comes from the caller (`gpfy_workspace_bytes`).
+ *   - return 0 on success, negative GPFY_E* otherwise; `gpfy_last_error_string()` explains
+ *     (thread-local).  No exceptions cross the boundary.
+ *   - layouts follow the reference: X [N, d] row-major; Phi / Kuf / A [M, N] with N contiguous, rows
+ *     ordered by degree then by row of V_l (spherical_harmonics.py:320); mu [M, P]; Sigma [P, M, M]
+ *     dense; fmu / fvar [N, P]; Y [N, P].
+ *   - "Vhat" is the concatenation over degrees of the fundamental points actually used
+ *     (`SphericalHarmonics.Vs`, spherical_harmonics.py:194-217) as [M, dim] row-major; "Lcat" is the
+ *     concatenation of the per-degree lower Cholesky factors (`SphericalHarmonics.Ls`, :219-239),
+ *     each [m_l, m_l] row-major.  Normalising V and the Cholesky of the Gram matrix (O(sum m_l^3),
+ *     N-independent) stay on the host framework's side, like the bijectors.
+ */
+#ifndef GPFY_B200_H_
+#define GPFY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GPFY_API __attribute__((visibility("default")))
+#else
+#define GPFY_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPFY_ABI_VERSION 1
+#define GPFY_MAX_DEGREES 32
+
+enum {
+  GPFY_OK = 0,
+  GPFY_EINVAL = -1,       /* bad descriptor / argument */
+  GPFY_EUNSUPPORTED = -2, /* shape outside what the kernels are built for */
+  GPFY_EWORKSPACE = -3,   /* workspace too small or misaligned */
+  GPFY_ECUDA = -4         /* a CUDA runtime call failed (launch error) */
+};
+
+enum { GPFY_LIK_GAUSSIAN = 0, GPFY_LIK_BERNOULLI = 1 };
+enum { GPFY_Q_TRIL = 0, GPFY_Q_FULLCOV = 1 };
+enum { GPFY_W_ARD = 0, GPFY_W_SCALAR = 1 };
+
+/* POD, versioned.  Mirrors the static (non-pytree) fields the reference keeps on its dataclasses:
+ * SphericalHarmonics.num_frequencies / phase_truncation (spherical_harmonics.py:75-76, via m[]),
+ * Spherical.order / ard (spherical.py:77-80), constants["sphere"] (spherical_harmonics.py:149-153). */
+typedef struct GpfyDesc {
+  uint32_t struct_size; /* sizeof(GpfyDesc) */
+  uint32_t abi_version; /* GPFY_ABI_VERSION */
+  int32_t input_dim;    /* d = X.shape[-1]; ambient dim = d + 1 (bias always appended, spherical.py:243-249) */
+  int32_t num_degrees;  /* F; degrees are 0..F-1 (spherical_harmonics.py:78-80) */
+  int32_t m[GPFY_MAX_DEGREES]; /* rows of V_l = min(phase_truncation, N(dim, l)); M = sum m[l] */
+  int32_t num_outputs;  /* P = num_independent_processes (variational.py:86) */
+  int32_t kernel_order; /* Spherical.order: K_diag = variance * r^(2*order) (spherical.py:400) */
+  int32_t likelihood;   /* GPFY_LIK_* (likelihoods.py:188-220 / :254-278) */
+  int32_t q_kind;       /* GPFY_Q_TRIL: Sigma holds L, q = N(mu, L L^T) (variational.py:243-351);
+                           GPFY_Q_FULLCOV: Sigma is the covariance (variational.py:354-464) */
+  int32_t weight_mode;  /* GPFY_W_ARD: weight_variances [d]; GPFY_W_SCALAR: one value (spherical.py:110-114) */
+  int32_t reserved;
+  double alpha;         /* (dim - 2) / 2 (spherical_harmonics.py:149) */
+} GpfyDesc;
+
+/* Which scratch size to ask for. */
+enum { GPFY_OP_FEATURES = 0, GPFY_OP_ELBO = 1, GPFY_OP_PREDICT = 2 };
+
+/* Layout of the packed ELBO output (doubles); offsets are filled by gpfy_elbo_packed_layout.
+ * Everything is a SUM over the N points passed in (no 1/N, no dataset_size scale, no KL), so ranks
+ * that own disjoint rows of (X, Y) can add their buffers with one allreduce. */
+typedef struct GpfyElboLayout {
+  int64_t total;     /* number of doubles */
+  int64_t data_term; /* [1]  sum_n var_exp_n                         (optimization.py:153,156) */
+  int64_t d_mu;      /* [M, P]                                        (variational.py:305) */
+  int64_t d_sigma;   /* [P, M, M] dense, w.r.t. the constrained Sigma (variational.py:326 / :438) */
+  int64_t d_eig;     /* [F]   w.r.t. kernel.eigenvalues lambda_l      (spherical_harmonics.py:335,385) */
+  int64_t d_vhat;    /* [M, dim]                                      (spherical_harmonics.py:308) */
+  int64_t d_lcat;    /* [sum m_l^2], lower triangles valid            (spherical_harmonics.py:316) */
+  int64_t d_w;       /* [d] or [1]                                    (spherical.py:228) */
+  int64_t d_b;       /* [1] bias_variance                             (spherical.py:245-246) */
+  int64_t d_v;       /* [1] kernel variance                           (spherical_harmonics.py:362, spherical.py:400) */
+  int64_t d_sigma2;  /* [1] Gaussian noise variance; 0 for Bernoulli  (likelihoods.py:210-218) */
+} GpfyElboLayout;
+
+GPFY_API int gpfy_abi_version(void);
+GPFY_API const char* gpfy_last_error_string(void);
+
+/* M and sum m_l^2 of a descriptor; negative error code if the descriptor is invalid. */
+GPFY_API int64_t gpfy_num_inducing(const GpfyDesc* desc);
+GPFY_API int gpfy_elbo_packed_layout(const GpfyDesc* desc, GpfyElboLayout* out /* host */);
+
+/* Bytes of scratch `op` needs for up to n_points rows (host call, no GPU work). */
+GPFY_API int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t* bytes /* host */);
+
+/* Elementwise Gegenbauer polynomial and its derivative 2*alpha*C_{level-1}^{alpha+1}
+ * (replaces gegenbauer.py:27-85: `gegenbauer`, `gegenbauer_fwd`).  `dout` may be NULL. */
+GPFY_API int gpfy_gegenbauer(void* stream, int level, double alpha, const double* x, int64_t n, double* out, double* dout);
+
+/* Spherical-harmonic feature matrix (replaces spherical_harmonics.py:290-320 `polynomial_expansion`,
+ * :344-362 `Kuf`, :385-387 `project_fun`):
+ *     out[i, n] = degree_scale[l(i)] * (r_n if mul_r) * (L_l^{-1} C_l^alpha(V_l xhat_n))[i]
+ * apply_to_sphere != 0: X is [N, d] raw input, xhat/r come from to_sphere (spherical.py:230-249) with w, b.
+ * apply_to_sphere == 0: X is [N, dim] already on the sphere (what `polynomial_expansion` receives);
+ *                       w, b are ignored and r = 1.
+ * degree_scale: [F] device array or NULL (= 1).  Kuf: sqrt(variance) each, mul_r = 1;
+ * projection A: sqrt(lambda_l * variance), mul_r = 1.  r_out [N] may be NULL. */
+GPFY_API int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const double* X, int apply_to_sphere,
+                         const double* w, const double* b, const double* vhat, const double* lcat,
+                         const double* degree_scale, int mul_r, double* out, double* r_out, void* workspace,
+                         size_t workspace_bytes);
+
+/* Fused ELBO data term and all its gradients (replaces optimization.py:125-156 `elbo` composed with
+ * model.py:201-229 `predict_diag`, and the reverse pass `jax.value_and_grad` builds at
+ * optimization.py:113-118), for the N rows given.  Inputs are the CONSTRAINED parameters:
+ *   w [d] or [1], b [1], variance [1], eig [F] (kernel.eigenvalues at levels 0..F-1), vhat [M, dim],
+ *   lcat [sum m_l^2], mu [M, P], sigma [P, M, M], sigma2 [1] (ignored for Bernoulli).
+ * `packed` receives GpfyElboLayout.total doubles. */
+GPFY_API int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* Y,
+                           const double* w, const double* b, const double* variance, const double* eig,
+                           const double* vhat, const double* lcat, const double* mu, const double* sigma,
+                           const double* sigma2, double* packed, void* workspace, size_t workspace_bytes);
+
+/* KL(q || N(0, I)) and its gradients (replaces variational.py:225-240 with :262-286 / :375-399).
+ * out: [1 + M*P + P*M*M] = KL, dKL/dmu, dKL/dSigma.  TriL only reads diag/all of L; full covariance
+ * needs a Cholesky of Sigma and is left to the host framework (returns GPFY_EUNSUPPORTED). */
+GPFY_API int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out);
+
+/* Predictive mean and diagonal variance (replaces model.py:201-229 `GP.predict_diag` with the
+ * conditional of :103-145): fmu, fvar are [N, P]. */
+GPFY_API int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* w,
+                      const double* b, const double* variance, const double* eig, const double* vhat,
+                      const double* lcat, const double* mu, const double* sigma, double* fmu, double* fvar,
+                      void* workspace, size_t workspace_bytes);
+
+/* Sum of the packed buffers of all ranks, in place, on `stream` (the single exchange step).
+ * `nccl_comm` is an ncclComm_t owned by the caller; NCCL is resolved at run time from the process
+ * (the host framework's copy), so this library has no link-time NCCL dependency. */
+GPFY_API int gpfy_allreduce_packed(void* nccl_comm, void* stream, double* packed, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPFY_B200_H_ */
