@@ -3,11 +3,12 @@
 // Used for  C = W2 * Z  (the L_q^T A / L_q (L_q^T A) contractions of variational.py:323-328 and
 // their VJP, folded — see DESIGN.md) and for the O(M^3) per-step parameter algebra.
 //
-// CTA tile 96 x 128, BK = 16, 3-stage cp.async pipeline, 6 warps (3 x 2), warp tile 32 x 64:
-// per k4 step a warp loads 4 A + 8 B fragments (12 LDS.64) for 32 DMMA.  Shared-memory rows are
-// padded by 4 doubles so every fragment load is bank-conflict-free (row stride = 4 mod 16 doubles).
-// Persistent over tiles: grid = min(#tiles, 2 CTAs x #SM); row tiles vary fastest so that CTAs
-// running together read the same B panel from L2.
+// CTA tile 96 x 192, BK = 16, 4-stage cp.async pipeline, 12 warps (4 x 3, three per SM sub-partition
+// so the four FP64 pipes carry equal work), warp tile 24 x 64: per k4 step a warp loads 3 A + 8 B
+// fragments (11 LDS.64) for 24 DMMA.  Shared-memory rows are padded by 4 doubles so every fragment
+// load is bank-conflict-free (row stride = 4 mod 16 doubles).  Persistent: one CTA per SM walks its
+// tiles as ONE flattened stream of k-steps, so the loads of the next tile are in flight while the
+// current tile finishes; row tiles vary fastest so CTAs running together share the B panel in L2.
 #pragma once
 #include "common.cuh"
 
@@ -22,11 +23,19 @@ struct GemmArgs {
   int64_t ldc;
   int m, n, k;  // k must be a multiple of 16 (operands zero padded); n even; lda, ldb, ldc even
   double alpha, beta;
+  // optional fused epilogue (needs m == k, alpha = 1, beta = 0): per-column partial sums of
+  // B[i, n] * C[i, n] over the rows of each (row tile, warp row) slab,
+  //   psi_out[(tile_m * 4 + warp_m) * ld_psi + n] = sum_{i in slab} B[i, n] C[i, n]
+  // i.e. the pieces of z_n^T W2 z_n (variational.py:326-327 folded); fixed layout => deterministic.
+  double* psi_out;
+  int64_t ld_psi;
 };
 
-constexpr int GEMM_BM = 96, GEMM_BN = 128, GEMM_BK = 16, GEMM_STAGES = 3, GEMM_THREADS = 192;
+static inline int gemm_psi_slabs(int m) { return ((m + 95) / 96) * 4; }
+
+constexpr int GEMM_BM = 96, GEMM_BN = 192, GEMM_BK = 16, GEMM_STAGES = 4, GEMM_THREADS = 384;
 constexpr int GEMM_AS = GEMM_BK + 4;   // 20 doubles: A-fragment loads conflict-free
-constexpr int GEMM_BS = GEMM_BN + 4;   // 132 doubles: B-fragment loads conflict-free
+constexpr int GEMM_BS = GEMM_BN + 4;   // 196 doubles: B-fragment loads conflict-free
 constexpr int GEMM_SMEM = GEMM_STAGES * (GEMM_BM * GEMM_AS + GEMM_BK * GEMM_BS) * 8;
 
 int launch_gemm(cudaStream_t stream, const GemmArgs& a, int num_sms);

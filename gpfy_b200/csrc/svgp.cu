@@ -196,7 +196,8 @@ __global__ void reduce_dv_kernel(const double* dVpart, double* out, int M, int M
   if (e >= M * dim) return;
   const int i = e / dim, c = e % dim;
   double s = 0.0;
-  for (int ks = 0; ks < KS; ++ks) s += dVpart[((int64_t)ks * Mp + i) * dimp + c];
+  const int ldv = (dimp + 7) / 8 * 8;
+  for (int ks = 0; ks < KS; ++ks) s += dVpart[((int64_t)ks * Mp + i) * ldv + c];
   out[e] = s;
 }
 
@@ -336,13 +337,15 @@ struct Plan {
   int npart;
   // offsets (doubles)
   int64_t o_sw, o_sb, o_dvec, o_vhat_p, o_mu2, o_linv, o_E, o_ET, o_tmp1, o_tmp2, o_tmp3, o_LqP, o_W0, o_W2, o_dE, o_Gz, o_bz,
-      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, total;
+      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, total;
+  int npsi;
 };
 
 static int64_t choose_chunk(int sms, int64_t n) {
-  // GEMM tiles are 96 x 128 with 2 CTAs per SM resident: chunks of 128 * 2 * sms points make every
-  // row-tile sweep an exact number of waves; small inputs use one chunk.
-  int64_t nc = (int64_t)128 * 2 * sms;
+  // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * 4 points give every
+  // CTA the same number of tiles (no tail wave) and enough threads to fill the per-point kernels;
+  // small inputs use one chunk.
+  int64_t nc = (int64_t)192 * sms * 4;
   int64_t need = round_up64(n, 128);
   return need < nc ? need : nc;
 }
@@ -354,8 +357,9 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->nb = (s.Mp + SYRK_B - 1) / SYRK_B;
   p->nblk = p->nb * (p->nb + 1) / 2;
   p->KS = std::max(1, (2 * p->sms) / p->nblk);
-  p->KSV = std::max(1, (4 * p->sms) / (s.Mp / 16));
-  p->nblocks_c = p->nc / 128;
+  p->KSV = std::max(1, (8 * p->sms) / (s.Mp / 32));  // about 8 warps per SM for the dVhat reduction
+  p->nblocks_c = p->nc / 32;
+  p->npsi = gemm_psi_slabs(s.Mp);
   p->npart = PART_DW + s.d;
   const int64_t Mp = s.Mp, Mp2 = Mp * Mp;
   int64_t o = 0;
@@ -382,7 +386,7 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   if (op == GPFY_OP_ELBO) {
     p->o_Gpart = take((int64_t)s.P * p->KS * p->nblk * SYRK_B * SYRK_B);
     p->o_bzpart = take((int64_t)s.P * p->KS * p->nb * SYRK_B);
-    p->o_dVpart = take((int64_t)p->KSV * Mp * s.dimp);
+    p->o_dVpart = take((int64_t)p->KSV * Mp * ((s.dimp + 7) / 8) * 8);
   } else {
     p->o_Gpart = p->o_bzpart = p->o_dVpart = o;
   }
@@ -392,6 +396,8 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->o_R = take(p->nc);
   p->o_wq = take((int64_t)s.P * p->nc);
   p->o_wp = take((int64_t)s.P * p->nc);
+  p->o_mz = take((int64_t)s.P * p->nc);
+  p->o_psi = take((int64_t)s.P * p->npsi * p->nc);
   p->total = o;
 }
 
@@ -425,10 +431,15 @@ static int set_smem(K kernel, int bytes) {
 
 template <int DIMP>
 static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
-  const int smem = a.Mp * DIMP * 8;
-  GPFY_TRY(set_smem(zonal_fwd_kernel<DIMP>, smem));
-  const int64_t nthreads = (a.npts + 1) & ~(int64_t)1;
-  zonal_fwd_kernel<DIMP><<<(unsigned)((nthreads + 127) / 128), 128, smem, st>>>(a);
+  const int smem = (a.Mp * DIMP + (a.mz ? a.P * a.Mp : 0)) * 8;
+  const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 31) / 32);
+#define GPFY_ZN(PM)                                               \
+  {                                                               \
+    GPFY_TRY(set_smem(zonal_fwd_kernel<DIMP, PM>, smem));         \
+    zonal_fwd_kernel<DIMP, PM><<<grid, 256, smem, st>>>(a);       \
+  }
+  if (a.P == 1) GPFY_ZN(1) else if (a.P == 2) GPFY_ZN(2) else if (a.P <= 4) GPFY_ZN(4) else GPFY_ZN(8)
+#undef GPFY_ZN
   GPFY_COUNT_LAUNCH();
   GPFY_LAUNCH_OK();
   return GPFY_OK;
@@ -436,12 +447,12 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
 
 template <int DIMP>
 static int launch_lik_bwd(cudaStream_t st, const LikBwdArgs& a) {
-  const int smem = (a.Mp * DIMP + a.P * a.Mp) * 8;
-  const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 127) / 128);
+  const int smem = (a.Mp * DIMP + a.P * a.Mp + 8 * DIMP * 32) * 8;
+  const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 31) / 32);
 #define GPFY_LB(PM)                                              \
   {                                                              \
     GPFY_TRY(set_smem(lik_bwd_kernel<DIMP, PM>, smem));          \
-    lik_bwd_kernel<DIMP, PM><<<grid, 128, smem, st>>>(a);        \
+    lik_bwd_kernel<DIMP, PM><<<grid, 256, smem, st>>>(a);        \
   }
   if (a.P == 1) GPFY_LB(1) else if (a.P == 2) GPFY_LB(2) else if (a.P <= 4) GPFY_LB(4) else GPFY_LB(8)
 #undef GPFY_LB
@@ -450,20 +461,23 @@ static int launch_lik_bwd(cudaStream_t st, const LikBwdArgs& a) {
   return GPFY_OK;
 }
 
-template <int DIMP>
 static int launch_dvhat(cudaStream_t st, const DvhatArgs& a) {
-  dvhat_kernel<DIMP><<<(a.Mp / 16) * a.KS, 128, 0, st>>>(a);
+  const int warps = (a.Mp / 32) * a.KS;
+  const unsigned grid = (warps + 3) / 4;
+  switch ((a.dimp + 7) / 8) {
+    case 1: dvhat_dmma_kernel<1><<<grid, 128, 0, st>>>(a); break;
+    case 2: dvhat_dmma_kernel<2><<<grid, 128, 0, st>>>(a); break;
+    case 3: dvhat_dmma_kernel<3><<<grid, 128, 0, st>>>(a); break;
+    case 4: dvhat_dmma_kernel<4><<<grid, 128, 0, st>>>(a); break;
+    default: dvhat_dmma_kernel<5><<<grid, 128, 0, st>>>(a); break;
+  }
   GPFY_COUNT_LAUNCH();
   GPFY_LAUNCH_OK();
   return GPFY_OK;
 }
 
 static int launch_predict(cudaStream_t st, const PredictArgs& a) {
-  const unsigned grid = (unsigned)((a.npts + 127) / 128);
-  if (a.P == 1) predict_kernel<1><<<grid, 128, 0, st>>>(a);
-  else if (a.P == 2) predict_kernel<2><<<grid, 128, 0, st>>>(a);
-  else if (a.P <= 4) predict_kernel<4><<<grid, 128, 0, st>>>(a);
-  else predict_kernel<8><<<grid, 128, 0, st>>>(a);
+  predict_kernel<<<(unsigned)((a.npts + 255) / 256), 256, 0, st>>>(a);
   GPFY_COUNT_LAUNCH();
   GPFY_LAUNCH_OK();
   return GPFY_OK;
@@ -474,6 +488,7 @@ static int gemm_sq(cudaStream_t st, const double* A, const double* B, double* C,
   g.A = A; g.lda = Mp; g.B = B; g.ldb = Mp; g.C = C; g.ldc = Mp;
   g.m = g.n = g.k = Mp;
   g.alpha = alpha; g.beta = beta;
+  g.psi_out = nullptr; g.ld_psi = 0;
   return launch_gemm(st, g, sms);
 }
 
@@ -611,7 +626,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     za.apply_to_sphere = apply_to_sphere;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
-    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R; za.mz = nullptr; za.P = 1;
     za.deg = deg; za.rc = rc;
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
     WhitenArgs wa;
@@ -659,7 +674,7 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
-    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
 
@@ -669,18 +684,20 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
+      g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
     LikBwdArgs la;
-    la.Z = ws + p.o_Z; la.C = ws + p.o_C; la.ldz = p.nc; la.c_stride = (int64_t)Mp * p.nc;
+    la.C = ws + p.o_C; la.ldz = p.nc; la.c_stride = (int64_t)Mp * p.nc;
+    la.psi_part = ws + p.o_psi; la.npsi = p.npsi; la.mz = ws + p.o_mz;
     la.XH = ws + p.o_XH; la.R = ws + p.o_R; la.Y = Y + c0 * s.P;
-    la.vhat_p = ws + p.o_vhat_p; la.mu2 = ws + p.o_mu2; la.vptr = variance; la.s2ptr = sigma2;
+    la.vhat_p = ws + p.o_vhat_p; la.vptr = variance; la.s2ptr = sigma2;
     la.Mp = Mp; la.M = s.M; la.d = s.d; la.P = s.P; la.order = desc->kernel_order; la.npts = npts;
     la.wq = ws + p.o_wq; la.wp = ws + p.o_wp; la.partials = ws + p.o_partials; la.npart = p.npart;
-    la.accumulate = chunk > 0 && (((npts_e + 127) / 128) <= p.nblocks_c);
+    la.accumulate = chunk > 0;
     la.lik_kind = desc->likelihood; la.deg = deg; la.rc = rc;
-    if (chunk == 0 && ((npts_e + 127) / 128) < p.nblocks_c)  // single short chunk: clear unused slots
+    if (chunk == 0 && ((npts_e + 31) / 32) < p.nblocks_c)  // single short chunk: clear unused slots
       GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, p.nblocks_c * p.npart * 8, st));
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_lik_bwd<DIMP>(st, la)));
 
@@ -699,10 +716,10 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
     }
 
     DvhatArgs da;
-    da.dT = ws + p.o_C; da.ldz = p.nc; da.XH = ws + p.o_XH; da.Mp = Mp; da.npts = npts;
-    da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 32);
+    da.dT = ws + p.o_C; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
+    da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
     da.accumulate = chunk > 0;
-    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_dvhat<DIMP>(st, da)));
+    GPFY_TRY(launch_dvhat(st, da));
   }
 
   // ---- epilogue: gradients of the folded matrices back to the reference's parameters ----
@@ -774,7 +791,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
-    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
     for (int q = 0; q < s.P; ++q) {
@@ -783,12 +800,12 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
+      g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
     PredictArgs pa;
-    pa.Z = ws + p.o_Z; pa.C = ws + p.o_C; pa.ldz = p.nc; pa.c_stride = (int64_t)Mp * p.nc;
-    pa.R = ws + p.o_R; pa.mu2 = ws + p.o_mu2; pa.vptr = variance;
-    pa.Mp = Mp; pa.M = s.M; pa.P = s.P; pa.order = desc->kernel_order; pa.npts = npts;
+    pa.psi_part = ws + p.o_psi; pa.npsi = p.npsi; pa.mz = ws + p.o_mz; pa.ldz = p.nc;
+    pa.R = ws + p.o_R; pa.vptr = variance; pa.P = s.P; pa.order = desc->kernel_order; pa.npts = npts;
     pa.fmu = fmu + c0 * s.P; pa.fvar = fvar + c0 * s.P;
     GPFY_TRY(launch_predict(st, pa));
   }

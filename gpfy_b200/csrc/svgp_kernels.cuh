@@ -30,6 +30,8 @@ struct ZonalArgs {
   int64_t ldz;
   double* XH;           // [npts, DIMP] unit vectors (zero padded), may be null
   double* R;            // [npts] radii, may be null
+  double* mz;           // [P][ldz] mu2_p . z_n, may be null (then mu2 is not staged)
+  int P;
   DegreeTable deg;
   RecCoef rc;
 };
@@ -59,40 +61,76 @@ __device__ __forceinline__ double load_point(const double* __restrict__ X, int x
   return r;
 }
 
-template <int DIMP>
-__global__ void __launch_bounds__(128) zonal_fwd_kernel(ZonalArgs a) {
+// Block = 8 warps x 32 points: lane = point, warp w takes rows j = w, w + 8, ... of every degree, so
+// per-thread dependent work is M / 8 rows and every global access is a 256-byte coalesced row segment.
+template <int DIMP, int PMAX>
+__global__ void __launch_bounds__(256) zonal_fwd_kernel(ZonalArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint64_t bar;
-  double* vs = smem;  // [Mp][DIMP]
-  stage_params_tma(vs, a.vhat_p, (unsigned)(a.Mp * DIMP * 8), &bar);
+  __shared__ double red[8][PMAX][32];
+  double* vs = smem;                     // [Mp][DIMP]
+  double* mu2s = smem + a.Mp * DIMP;     // [P][Mp] (only when a.mz)
+  stage_params_tma(vs, a.vhat_p, (unsigned)((a.Mp * DIMP + (a.mz ? a.P * a.Mp : 0)) * 8), &bar);
 
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.npts) {
-    // keep the (even-padded) tail column finite: the GEMM / SYRK read 16-byte pairs of points
-    if (n < ((a.npts + 1) & ~(int64_t)1))
-      for (int i = 0; i < a.Mp; ++i) a.Z[(int64_t)i * a.ldz + n] = 0.0;
-    return;
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+  const bool valid = n < a.npts;
+  const bool padcol = !valid && n < ((a.npts + 1) & ~(int64_t)1);  // keep the even-padded tail column finite
   double xh[DIMP];
-  double r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
-  if (a.R) a.R[n] = r;
-  if (a.XH) {
+  double r = 1.0;
+  if (valid) {
+    r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
+    if (warp == 0) {
+      if (a.R) a.R[n] = r;
+      if (a.XH) {
 #pragma unroll
-    for (int c = 0; c < DIMP; c += 2) *reinterpret_cast<double2*>(a.XH + n * DIMP + c) = make_double2(xh[c], xh[c + 1]);
+        for (int c = 0; c < DIMP; c += 2) *reinterpret_cast<double2*>(a.XH + n * DIMP + c) = make_double2(xh[c], xh[c + 1]);
+      }
+    }
   }
-  int i = 0;
+  double mz[PMAX];
+#pragma unroll
+  for (int p = 0; p < PMAX; ++p) mz[p] = 0.0;
+  int base = 0;
   for (int l = 0; l < a.deg.F; ++l) {
     const int ml = a.deg.m[l];
-    for (int j = 0; j < ml; ++j, ++i) {
-      const double* v = vs + i * DIMP;
-      double t = 0.0;
+    for (int j = warp; j < ml; j += 8) {
+      const int i = base + j;
+      if (valid) {
+        const double* v = vs + i * DIMP;
+        double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-      for (int c = 0; c < DIMP; c += 2) {
-        double2 vv = *reinterpret_cast<const double2*>(v + c);
-        t = fma(vv.x, xh[c], t);
-        t = fma(vv.y, xh[c + 1], t);
+        for (int c = 0; c < DIMP; c += 2) {
+          double2 vv = *reinterpret_cast<const double2*>(v + c);
+          t0 = fma(vv.x, xh[c], t0);
+          t1 = fma(vv.y, xh[c + 1], t1);
+        }
+        const double z = geg_eval(a.rc, l, t0 + t1);
+        a.Z[(int64_t)i * a.ldz + n] = z;
+        if (a.mz) {
+#pragma unroll
+          for (int p = 0; p < PMAX; ++p)
+            if (p < a.P) mz[p] = fma(mu2s[p * a.Mp + i], z, mz[p]);
+        }
+      } else if (padcol) {
+        a.Z[(int64_t)i * a.ldz + n] = 0.0;
       }
-      a.Z[(int64_t)i * a.ldz + n] = geg_eval(a.rc, l, t);
+    }
+    base += ml;
+  }
+  if (a.mz) {  // mz_p[n] = mu2_p . z_n  (variational.py:305 folded), fixed-order sum over the 8 warps
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) red[warp][p][lane] = mz[p];
+    __syncthreads();
+    if (warp == 0 && valid) {
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p)
+        if (p < a.P) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += red[w][p][lane];
+          a.mz[(int64_t)p * a.ldz + n] = s;
+        }
     }
   }
 }
@@ -216,15 +254,16 @@ __device__ __forceinline__ void lik_terms(const LikParams& lp, double fmu, doubl
 constexpr int PART_E = 0, PART_DV = 1, PART_DS2 = 2, PART_DB = 3, PART_DW = 4;  // then d entries
 
 struct LikBwdArgs {
-  const double* Z;
   double* C;            // [P][Mp][ldz]; C[0] is overwritten with dT
   int64_t ldz;
   int64_t c_stride;     // Mp * ldz
+  const double* psi_part; // [P][npsi][ldz] partial sums of z . C_p from the GEMM epilogue
+  int npsi;
+  const double* mz;     // [P][ldz]
   const double* XH;     // [npts][DIMP]
   const double* R;
   const double* Y;      // [npts][P]
-  const double* vhat_p; // [Mp][DIMP]
-  const double* mu2;    // [P][Mp]
+  const double* vhat_p; // [Mp][DIMP], mu2 [P][Mp] right behind it
   const double* vptr;   // [1] kernel variance
   const double* s2ptr;  // [1] noise variance (Gaussian)
   int Mp, M, d, P, order;
@@ -239,179 +278,171 @@ struct LikBwdArgs {
   RecCoef rc;
 };
 
+// Block = 8 warps x 32 points (lane = point, warp w owns rows w, w + 8, ... of every degree).
 template <int DIMP, int PMAX>
-__global__ void __launch_bounds__(128) lik_bwd_kernel(LikBwdArgs a) {
+__global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint64_t bar;
-  __shared__ double red[4][PART_DW + DIMP];
+  __shared__ double s_cp[PMAX][32], s_cq[PMAX][32];
   double* vs = smem;                      // [Mp][DIMP]
   double* mu2s = smem + a.Mp * DIMP;      // [P][Mp]
-  // one TMA transaction covers both panels: the host lays mu2 right behind vhat_p
+  double* red = mu2s + a.P * a.Mp;        // [8][DIMP][32]
   stage_params_tma(vs, a.vhat_p, (unsigned)((a.Mp * DIMP + a.P * a.Mp) * 8), &bar);
 
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * 32 + lane;
   const bool valid = n < a.npts;
   double part[PART_DW + DIMP];
+  double dr = 0.0, r = 1.0;
+  if (warp == 0) {
 #pragma unroll
-  for (int k = 0; k < PART_DW + DIMP; ++k) part[k] = 0.0;
-
-  if (!valid && n < ((a.npts + 1) & ~(int64_t)1)) {
-    for (int p = 0; p < a.P; ++p) { a.wq[p * a.ldz + n] = 0.0; a.wp[p * a.ldz + n] = 0.0; }
+    for (int k = 0; k < PART_DW + DIMP; ++k) part[k] = 0.0;
+    if (!valid && n < ((a.npts + 1) & ~(int64_t)1)) {
+      for (int p = 0; p < a.P; ++p) { a.wq[p * a.ldz + n] = 0.0; a.wp[p * a.ldz + n] = 0.0; }
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) s_cp[p][lane] = s_cq[p][lane] = 0.0;
+    if (valid) {
+      LikParams lp;
+      lp.kind = a.lik_kind;
+      lp.sigma2 = a.lik_kind == GPFY_LIK_GAUSSIAN ? a.s2ptr[0] : 1.0;
+      const double v = a.vptr[0];
+      r = a.R[n];
+      double kd = v, dkd = 0.0;   // K_diag = v r^(2 order) (spherical.py:400) and its r-derivative
+      {
+        double rp = 1.0;
+        for (int k = 0; k < 2 * a.order - 1; ++k) rp *= r;
+        if (a.order > 0) { kd = v * rp * r; dkd = 2.0 * a.order * v * rp; }
+      }
+      const double r2 = r * r;
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p)
+        if (p < a.P) {
+          double psi = 0.0;
+          for (int k = 0; k < a.npsi; ++k) psi += a.psi_part[((int64_t)p * a.npsi + k) * a.ldz + n];
+          const double mzp = a.mz[(int64_t)p * a.ldz + n];
+          const double fmu = r * mzp;
+          const double fvar = kd + r2 * psi;
+          double e, pp, qq, ds2;
+          lik_terms(lp, fmu, fvar, a.Y[n * a.P + p], e, pp, qq, ds2);
+          part[PART_E] += e;
+          part[PART_DS2] += ds2;
+          part[PART_DV] += qq * (kd / v);
+          a.wq[p * a.ldz + n] = qq * r2;
+          a.wp[p * a.ldz + n] = pp * r;
+          s_cp[p][lane] = r * pp;
+          s_cq[p][lane] = 2.0 * qq * r2;
+          dr += pp * mzp + qq * (dkd + 2.0 * r * psi);
+        }
+    }
   }
+  __syncthreads();
+
+  double xh[DIMP], dxh[DIMP];
+#pragma unroll
+  for (int c = 0; c < DIMP; ++c) { xh[c] = 0.0; dxh[c] = 0.0; }
   if (valid) {
-    LikParams lp;
-    lp.kind = a.lik_kind;
-    lp.sigma2 = a.lik_kind == GPFY_LIK_GAUSSIAN ? a.s2ptr[0] : 1.0;
-    const double v = a.vptr[0];
-    const double r = a.R[n];
-    double xh[DIMP];
 #pragma unroll
     for (int c = 0; c < DIMP; c += 2) {
       double2 t2 = *reinterpret_cast<const double2*>(a.XH + n * DIMP + c);
       xh[c] = t2.x; xh[c + 1] = t2.y;
     }
-    double psi[PMAX], mz[PMAX];
+    double cp_[PMAX], cq_[PMAX];
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p) psi[p] = mz[p] = 0.0;
-    const double* zc = a.Z + n;
-    const double* cc = a.C + n;
-#pragma unroll 4
-    for (int i = 0; i < a.M; ++i) {
-      const double z = zc[(int64_t)i * a.ldz];
-#pragma unroll
-      for (int p = 0; p < PMAX; ++p)
-        if (p < a.P) {
-          psi[p] = fma(z, cc[p * a.c_stride + (int64_t)i * a.ldz], psi[p]);
-          mz[p] = fma(mu2s[p * a.Mp + i], z, mz[p]);
-        }
-    }
-    // K_diag = v r^(2 order)  (spherical.py:400); its r-derivative
-    double kd = v, dkd = 0.0;
-    {
-      double rp = 1.0;  // r^(2 order - 1)
-      for (int k = 0; k < 2 * a.order - 1; ++k) rp *= r;
-      if (a.order > 0) { kd = v * rp * r; dkd = 2.0 * a.order * v * rp; }
-    }
-    const double r2 = r * r;
-    double cp_[PMAX], cq_[PMAX];  // r p  and  2 q r^2
-    double dr = 0.0;
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) {
-      cp_[p] = cq_[p] = 0.0;
-      if (p < a.P) {
-        const double fmu = r * mz[p];
-        const double fvar = kd + r2 * psi[p];
-        double e, pp, qq, ds2;
-        lik_terms(lp, fmu, fvar, a.Y[n * a.P + p], e, pp, qq, ds2);
-        part[PART_E] += e;
-        part[PART_DS2] += ds2;
-        part[PART_DV] += qq * (kd / v);
-        a.wq[p * a.ldz + n] = qq * r2;
-        a.wp[p * a.ldz + n] = pp * r;
-        cp_[p] = r * pp;
-        cq_[p] = 2.0 * qq * r2;
-        dr += pp * mz[p] + qq * (dkd + 2.0 * r * psi[p]);
-      }
-    }
-    // pass 2
-    double dxh[DIMP];
-#pragma unroll
-    for (int c = 0; c < DIMP; ++c) dxh[c] = 0.0;
-    int i = 0;
+    for (int p = 0; p < PMAX; ++p) { cp_[p] = s_cp[p][lane]; cq_[p] = s_cq[p][lane]; }
+    int base = 0;
     for (int l = 0; l < a.deg.F; ++l) {
       const int ml = a.deg.m[l];
-      for (int j = 0; j < ml; ++j, ++i) {
+      for (int j = warp; j < ml; j += 8) {
+        const int i = base + j;
+        double cv[PMAX];
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p)
+          if (p < a.P) cv[p] = a.C[p * a.c_stride + (int64_t)i * a.ldz + n];
         const double* vv = vs + i * DIMP;
         double vr[DIMP];
-        double t = 0.0;
+        double t0 = 0.0, t1 = 0.0;
 #pragma unroll
         for (int c = 0; c < DIMP; c += 2) {
           double2 v2 = *reinterpret_cast<const double2*>(vv + c);
           vr[c] = v2.x; vr[c + 1] = v2.y;
-          t = fma(v2.x, xh[c], t);
-          t = fma(v2.y, xh[c + 1], t);
+          t0 = fma(v2.x, xh[c], t0);
+          t1 = fma(v2.y, xh[c + 1], t1);
         }
-        const double zp = geg_deriv(a.rc, l, t);
+        const double zp = geg_deriv(a.rc, l, t0 + t1);
         double dz = 0.0;
 #pragma unroll
         for (int p = 0; p < PMAX; ++p)
-          if (p < a.P) dz += cp_[p] * mu2s[p * a.Mp + i] + cq_[p] * a.C[p * a.c_stride + (int64_t)i * a.ldz + n];
+          if (p < a.P) dz += cp_[p] * mu2s[p * a.Mp + i] + cq_[p] * cv[p];
         const double dt = dz * zp;
         a.C[(int64_t)i * a.ldz + n] = dt;
 #pragma unroll
         for (int c = 0; c < DIMP; ++c) dxh[c] = fma(vr[c], dt, dxh[c]);
       }
-    }
-    // du = (dxh - xh (xh . dxh)) / r + dr xh      (VJP of spherical.py:248-249)
-    double dot = 0.0;
-#pragma unroll
-    for (int c = 0; c < DIMP; ++c) dot = fma(xh[c], dxh[c], dot);
-#pragma unroll
-    for (int c = 0; c < DIMP; ++c) {
-      const double du = (dxh[c] - xh[c] * dot) / r + dr * xh[c];
-      const double u = xh[c] * r;
-      if (c < a.d) part[PART_DW + c] = du * u;   // d w_j = sum du_j x_j / (2 sqrt w_j) = sum du_j u_j / (2 w_j)
-      else if (c == a.d) part[PART_DB] = du;     // d b   = sum du_dim / (2 sqrt b)
+      base += ml;
     }
   }
-  // block reduction (fixed order => deterministic)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < PART_DW + DIMP; ++k) {
-    double s = warp_sum(part[k]);
-    if (lane == 0) red[warp][k] = s;
-  }
+  for (int c = 0; c < DIMP; ++c) red[(warp * DIMP + c) * 32 + lane] = dxh[c];
   __syncthreads();
-  if (threadIdx.x < a.npart) {
-    const int k = threadIdx.x;
-    double s = ((red[0][k] + red[1][k]) + (red[2][k] + red[3][k]));
-    double* dst = a.partials + (int64_t)blockIdx.x * a.npart + k;
-    *dst = a.accumulate ? *dst + s : s;
+  if (warp == 0) {
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < DIMP; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[(w * DIMP + c) * 32 + lane];
+        dxh[c] = s;
+      }
+      // du = (dxh - xh (xh . dxh)) / r + dr xh      (VJP of spherical.py:248-249)
+      double dot = 0.0;
+#pragma unroll
+      for (int c = 0; c < DIMP; ++c) dot = fma(xh[c], dxh[c], dot);
+#pragma unroll
+      for (int c = 0; c < DIMP; ++c) {
+        const double du = (dxh[c] - xh[c] * dot) / r + dr * xh[c];
+        const double u = xh[c] * r;
+        if (c < a.d) part[PART_DW + c] = du * u;   // d w_j = sum du_j x_j / (2 sqrt w_j) = sum du_j u_j / (2 w_j)
+        else if (c == a.d) part[PART_DB] = du;     // d b   = sum du_dim / (2 sqrt b)
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PART_DW + DIMP; ++k) {
+      const double s = warp_sum(part[k]);
+      if (lane == 0 && k < a.npart) {
+        double* dst = a.partials + (int64_t)blockIdx.x * a.npart + k;
+        *dst = a.accumulate ? *dst + s : s;
+      }
+    }
   }
 }
 
-// predict_diag: pass 1 only, stores fmu / fvar [n, P]  (model.py:220-225)
+// predict_diag epilogue: fmu = r mz, fvar = v r^(2 order) + r^2 psi  [n, P]  (model.py:220-225)
 struct PredictArgs {
-  const double* Z;
-  const double* C;
-  int64_t ldz, c_stride;
+  const double* psi_part;  // [P][npsi][ldz]
+  int npsi;
+  const double* mz;        // [P][ldz]
+  int64_t ldz;
   const double* R;
-  const double* mu2;   // [P][Mp]
   const double* vptr;
-  int Mp, M, P, order;
+  int P, order;
   int64_t npts;
   double* fmu;         // [npts][P]
   double* fvar;
 };
 
-template <int PMAX>
-__global__ void __launch_bounds__(128) predict_kernel(PredictArgs a) {
+__global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= a.npts) return;
-  double psi[PMAX], mz[PMAX];
-#pragma unroll
-  for (int p = 0; p < PMAX; ++p) psi[p] = mz[p] = 0.0;
-  const double* zc = a.Z + n;
-  const double* cc = a.C + n;
-#pragma unroll 4
-  for (int i = 0; i < a.M; ++i) {
-    const double z = zc[(int64_t)i * a.ldz];
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p)
-      if (p < a.P) {
-        psi[p] = fma(z, cc[p * a.c_stride + (int64_t)i * a.ldz], psi[p]);
-        mz[p] = fma(__ldg(a.mu2 + p * a.Mp + i), z, mz[p]);
-      }
-  }
   const double r = a.R[n];
   double kd = a.vptr[0];
   for (int k = 0; k < 2 * a.order; ++k) kd *= r;
-#pragma unroll
-  for (int p = 0; p < PMAX; ++p)
-    if (p < a.P) {
-      a.fmu[n * a.P + p] = r * mz[p];
-      a.fvar[n * a.P + p] = kd + r * r * psi[p];
-    }
+  for (int p = 0; p < a.P; ++p) {
+    double psi = 0.0;
+    for (int k = 0; k < a.npsi; ++k) psi += a.psi_part[((int64_t)p * a.npsi + k) * a.ldz + n];
+    a.fmu[n * a.P + p] = r * a.mz[(int64_t)p * a.ldz + n];
+    a.fvar[n * a.P + p] = kd + r * r * psi;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +450,7 @@ __global__ void __launch_bounds__(128) predict_kernel(PredictArgs a) {
 // diagonal blocks, bz += Z wp through one extra MMA column.  Split over points: CTA (blk, ks) owns a
 // contiguous range of the chunk and accumulates into its own slot of Gpart (no atomics, deterministic).
 // ------------------------------------------------------------------------------------------------
-constexpr int SYRK_B = 96, SYRK_BK = 16, SYRK_STAGES = 3, SYRK_THREADS = 192;
+constexpr int SYRK_B = 96, SYRK_BK = 16, SYRK_STAGES = 3, SYRK_THREADS = 256;
 constexpr int SYRK_ZS = SYRK_BK + 4;
 constexpr int SYRK_STAGE_DBL = 2 * SYRK_B * SYRK_ZS + 2 * SYRK_BK;
 constexpr int SYRK_SMEM = SYRK_STAGES * SYRK_STAGE_DBL * 8;
@@ -441,7 +472,7 @@ struct SyrkArgs {
 __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp % 3, wn = warp / 3;
+  const int wm = warp & 3, wn = warp >> 2;   // 4 x 2 warps, warp tile 24 x 48 (two warps per SM sub-partition)
   const int g = lane >> 2, t4 = lane & 3;
   const int blk = blockIdx.x % a.nblk, ks = blockIdx.x / a.nblk;
   // blk -> (bi >= bj)
@@ -460,7 +491,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     double* wqs = zj + SYRK_B * SYRK_ZS;
     const int64_t pt0 = p0 + (int64_t)kb * SYRK_BK;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 6; ++i) {
       int c = tid + i * SYRK_THREADS;  // 2 * 768 chunks
       int which = c >= 768;
       int cc = which ? c - 768 : c;
@@ -478,10 +509,10 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     }
   };
 
-  double acc[4][6][2];
-  double accx[4][2];
+  double acc[3][6][2];
+  double accx[3][2];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < 3; ++r) {
     accx[r][0] = accx[r][1] = 0.0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
@@ -497,25 +528,25 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     if (kb + SYRK_STAGES - 1 < kt) load_stage((kb + SYRK_STAGES - 1) % SYRK_STAGES, kb + SYRK_STAGES - 1);
     cp_async_commit();
     const double* base = smem + (kb % SYRK_STAGES) * SYRK_STAGE_DBL;
-    const double* zi = base + (wm * 32 + g) * SYRK_ZS + t4;
+    const double* zi = base + (wm * 24 + g) * SYRK_ZS + t4;
     const double* zj = base + SYRK_B * SYRK_ZS + (wn * 48 + g) * SYRK_ZS + t4;
     const double* wqs = base + 2 * SYRK_B * SYRK_ZS;
 #pragma unroll
     for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
-      double af[4], bf[6];
+      double af[3], bf[6];
       const double w = wqs[k4 * 4 + t4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) af[r] = zi[r * 8 * SYRK_ZS + k4 * 4];
+      for (int r = 0; r < 3; ++r) af[r] = zi[r * 8 * SYRK_ZS + k4 * 4];
 #pragma unroll
       for (int c = 0; c < 6; ++c) bf[c] = zj[c * 8 * SYRK_ZS + k4 * 4] * w;
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 6; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
       if (diag && wn == 0) {
         const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) dmma884(accx[r][0], accx[r][1], af[r], bx);
+        for (int r = 0; r < 3; ++r) dmma884(accx[r][0], accx[r][1], af[r], bx);
       }
     }
   }
@@ -523,8 +554,8 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
 
   double* gp = a.Gpart + ((int64_t)ks * a.nblk + blk) * (SYRK_B * SYRK_B);
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int row = wm * 32 + r * 8 + g;
+  for (int r = 0; r < 3; ++r) {
+    const int row = wm * 24 + r * 8 + g;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       const int col = wn * 48 + c * 8 + 2 * t4;
@@ -541,58 +572,67 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_E  dVhat = dT Xhat^T  (VJP of spherical_harmonics.py:308).  A warp owns 4 feature rows and a
-// range of points; lanes stride over points, 4 x DIMP accumulators per lane, one warp reduction at
-// the end.  dVpart[ks][Mp][DIMP].
+// K_E  dVhat = dT Xhat^T  (VJP of spherical_harmonics.py:308) on the FP64 tensor cores.  A warp owns 32
+// feature rows and a range of points; A fragments (dT) and B fragments (Xhat) are read straight from
+// global memory (32-byte segments per row), 8 accumulator tiles per warp.  dVpart[ks][Mp][16].
 // ------------------------------------------------------------------------------------------------
 struct DvhatArgs {
   const double* dT;
   int64_t ldz;
-  const double* XH;
+  const double* XH;   // [npts][dimp]
+  int dimp;
   int Mp;
   int64_t npts;
-  double* dVpart;
+  double* dVpart;     // [KS][Mp][CT * 8], CT = ceil(dimp / 8)
   int KS;
-  int64_t range;
+  int64_t range;      // points per split (multiple of 16)
   int accumulate;
 };
 
-template <int DIMP>
-__global__ void __launch_bounds__(128) dvhat_kernel(DvhatArgs a) {
+template <int CT>
+__global__ void __launch_bounds__(128) dvhat_dmma_kernel(DvhatArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rg = blockIdx.x % (a.Mp / 16), ks = blockIdx.x / (a.Mp / 16);
-  const int row0 = rg * 16 + warp * 4;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int nrg = a.Mp / 32;
+  const int wid = blockIdx.x * 4 + warp;
+  const int rg = wid % nrg, ks = wid / nrg;
+  if (ks >= a.KS) return;
+  const int row0 = rg * 32;
   const int64_t p0 = (int64_t)ks * a.range;
   int64_t p1 = p0 + a.range;
   if (p1 > a.npts) p1 = a.npts;
-  double acc[4][DIMP];
+  double acc[4][CT][2];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < DIMP; ++c) acc[r][c] = 0.0;
-  for (int64_t n = p0 + lane; n < p1; n += 32) {
-    double xh[DIMP];
+    for (int c = 0; c < CT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+  constexpr int KU = CT <= 2 ? 4 : 2;  // k4 steps batched per iteration (loads in flight)
+  for (int64_t n0 = p0; n0 < p1; n0 += 4 * KU) {
+    double af[KU][4], bf[KU][CT];
 #pragma unroll
-    for (int c = 0; c < DIMP; c += 2) {
-      double2 t2 = *reinterpret_cast<const double2*>(a.XH + n * DIMP + c);
-      xh[c] = t2.x; xh[c + 1] = t2.y;
+    for (int k4 = 0; k4 < KU; ++k4) {
+      const int64_t n = n0 + k4 * 4 + t4;
+      const bool ok = n < p1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) af[k4][r] = ok ? a.dT[(int64_t)(row0 + r * 8 + g) * a.ldz + n] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) bf[k4][c] = (ok && (c * 8 + g) < a.dimp) ? a.XH[n * a.dimp + c * 8 + g] : 0.0;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const double dt = a.dT[(int64_t)(row0 + r) * a.ldz + n];
+    for (int k4 = 0; k4 < KU; ++k4)
 #pragma unroll
-      for (int c = 0; c < DIMP; ++c) acc[r][c] = fma(dt, xh[c], acc[r][c]);
-    }
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[k4][r], bf[k4][c]);
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < DIMP; ++c) {
-      double s = warp_sum(acc[r][c]);
-      if (lane == 0) {
-        double* dst = a.dVpart + ((int64_t)ks * a.Mp + row0 + r) * DIMP + c;
-        *dst = a.accumulate ? *dst + s : s;
-      }
+    for (int c = 0; c < CT; ++c) {
+      double2* dst = reinterpret_cast<double2*>(a.dVpart + ((int64_t)ks * a.Mp + row0 + r * 8 + g) * (CT * 8) + c * 8 + 2 * t4);
+      double2 v = make_double2(acc[r][c][0], acc[r][c][1]);
+      if (a.accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
+      *dst = v;
     }
 }
 

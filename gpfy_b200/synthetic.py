@@ -1,0 +1,100 @@
+"""Seeded synthetic problems of BASELINE.json's shapes, generated on the device.
+
+Used by bench.py, smoke() and the full-size GPU tests.  There is no network for datasets; the data
+are N(0, I) inputs with a smooth target, the parameters a random but well-conditioned point.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .ops import HotPath
+
+
+def num_harmonics(dim, n):
+    """N(dim, n) of spherical_harmonics.py:31-47 (exact integer arithmetic)."""
+    if n == 0:
+        return 1
+    return math.comb(n + dim - 3, n - 1) + math.comb(n + dim - 2, n)
+
+
+def algorithmic_flops_per_point(dim, m, with_grad=True):
+    """proj + geg + trsv (+ M^2 + 4M forward; + 2M^2 + trsv + 2 geg + 2 proj backward)."""
+    M = sum(m)
+    proj = 2 * dim * M
+    geg = sum(ml * (4 * max(l - 1, 0) + (1 if l >= 1 else 0)) for l, ml in enumerate(m))
+    trsv = sum(ml * ml for ml in m)
+    phi = proj + geg + trsv
+    if not with_grad:
+        return phi
+    return (phi + M * M + 4 * M) + (2 * M * M + trsv + 2 * geg + 2 * proj)
+
+
+def _gegenbauer_np(level, alpha, x):
+    if level == 0:
+        return np.ones_like(x)
+    cp, c = np.ones_like(x), 2 * alpha * x
+    for k in range(2, level + 1):
+        c, cp = (2 * x * (k + alpha - 1) * c - (k + 2 * alpha - 2) * cp) / k, c
+    return c
+
+
+def synthetic_basis(d, F, T, rng):
+    """Vhat rows (unit norm) and Cholesky factors per degree: degree 0 -> e_1, degree 1 -> identity
+    (valid fundamental systems), truncated degrees -> random unit vectors (spherical_harmonics.py:123-127)."""
+    dim = d + 1
+    alpha = (dim - 2.0) / 2.0
+    V, L, m = [], [], []
+    for l in range(F):
+        nl = num_harmonics(dim, l)
+        ml = min(T, nl)
+        if l == 0:
+            v = np.zeros((1, dim)); v[0, 0] = 1.0
+        elif l == 1 and ml == dim:
+            v = np.eye(dim)
+        else:
+            v = rng.standard_normal((ml, dim))
+            v /= np.linalg.norm(v, axis=1, keepdims=True)
+        B = alpha / (alpha + l) * _gegenbauer_np(l, alpha, v @ v.T)
+        L.append(np.linalg.cholesky(B + 1e-16 * np.eye(ml)))
+        V.append(v); m.append(ml)
+    return V, L, m
+
+
+def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, device="cuda", rank=0, world=1):
+    """BASELINE.json configs[2]: full SVGP ELBO+gradient step, d=8, degrees 0..10, phase truncation T.
+    Rank `rank` of `world` owns rows [rank*N/world, (rank+1)*N/world) of the same global dataset."""
+    rng = np.random.default_rng(seed)
+    V, L, m = synthetic_basis(d, F, T, rng)
+    M = sum(m)
+    dim = d + 1
+    alpha = (dim - 2.0) / 2.0
+    # PolynomialDecay eigenvalues at beta = 1 with the default truncation_level = 10 clip (spherical.py:563-587)
+    tl = 10
+    n = np.arange(tl, dtype=np.float64)
+    c1 = np.array([_gegenbauer_np(k, alpha, np.array(1.0)) for k in range(tl)])
+    eigv = (1 + n) ** (-1.0) * (alpha / (n + alpha) / c1)
+    eigv = eigv / np.sum((1 + n) ** (-1.0))
+    eig = eigv[np.clip(np.arange(F), 0, tl - 1)]
+    mu = 0.1 * rng.standard_normal((M, P))
+    Lq = np.stack([np.tril(np.eye(M) + 0.01 * rng.standard_normal((M, M))) for _ in range(P)])
+    w = np.ones(d); b = np.array(1.0); v = np.array(1.0); s2 = np.array(0.1)
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + 7919 * rank)
+    X = torch.randn((hi - lo, d), dtype=torch.float64, device=device, generator=g)
+    f = torch.sin(X).sum(1, keepdim=True) / math.sqrt(d)
+    Y = torch.cat([f * (j + 1) for j in range(P)], 1) + 0.1 * torch.randn((hi - lo, P), dtype=torch.float64, device=device, generator=g)
+    if likelihood == "bernoulli":
+        Y = (Y > 0).to(torch.float64)
+    hp = HotPath(d, m, num_outputs=P, kernel_order=1, likelihood=likelihood, q_kind="tril", weight_mode="ard", device=device)
+    vhat = np.concatenate(V, 0)
+    lcat = np.concatenate([l.ravel() for l in L])
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+    args = (X, Y, dev(w), dev(b), dev(v), dev(eig), dev(vhat), dev(lcat), dev(mu), dev(Lq), dev(s2))
+    return {
+        "hot": hp, "args": args, "m": m, "M": M, "dim": dim,
+        "host": dict(w=w, b=b, v=v, eig=eig, V=V, L=L, mu=mu, Lq=Lq, sigma2=s2, alpha=alpha, order=1, dim=dim, lik=likelihood),
+        "alg_flops_per_point": algorithmic_flops_per_point(dim, m, True),
+        "alg_bytes_per_point": 8 * (d + P),
+    }
