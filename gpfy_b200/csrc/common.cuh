@@ -99,6 +99,72 @@ __device__ __forceinline__ double geg_deriv(const RecCoef& rc, int level, double
   return rc.two_alpha * c;
 }
 
+// Degree known at compile time: fully unrolled, coefficients become constant-bank operands.
+template <int L>
+__device__ __forceinline__ double geg_eval_s(const RecCoef& rc, double t) {
+  if constexpr (L == 0) {
+    return 1.0;
+  } else {
+    double cp = 1.0, c = rc.two_alpha * t;
+#pragma unroll
+    for (int k = 2; k <= L; ++k) {
+      double cn = fma(rc.c1[k] * t, c, -rc.c2[k] * cp);
+      cp = c;
+      c = cn;
+    }
+    return c;
+  }
+}
+template <int L>
+__device__ __forceinline__ double geg_deriv_s(const RecCoef& rc, double t) {
+  if constexpr (L == 0) {
+    return 0.0;
+  } else if constexpr (L == 1) {
+    return rc.two_alpha;
+  } else {
+    double cp = 1.0, c = rc.two_alpha_p1 * t;
+#pragma unroll
+    for (int k = 2; k <= L - 1; ++k) {
+      double cn = fma(rc.d1[k] * t, c, -rc.d2[k] * cp);
+      cp = c;
+      c = cn;
+    }
+    return rc.two_alpha * c;
+  }
+}
+constexpr int GPFY_STATIC_DEGREES = 16;  // degrees below this get unrolled code, the rest the runtime loop
+#define GPFY_DEGREE_SWITCH(l, ...)                                    \
+  switch (l) {                                                        \
+    case 0: { constexpr int LS = 0; __VA_ARGS__; } break;                    \
+    case 1: { constexpr int LS = 1; __VA_ARGS__; } break;                    \
+    case 2: { constexpr int LS = 2; __VA_ARGS__; } break;                    \
+    case 3: { constexpr int LS = 3; __VA_ARGS__; } break;                    \
+    case 4: { constexpr int LS = 4; __VA_ARGS__; } break;                    \
+    case 5: { constexpr int LS = 5; __VA_ARGS__; } break;                    \
+    case 6: { constexpr int LS = 6; __VA_ARGS__; } break;                    \
+    case 7: { constexpr int LS = 7; __VA_ARGS__; } break;                    \
+    case 8: { constexpr int LS = 8; __VA_ARGS__; } break;                    \
+    case 9: { constexpr int LS = 9; __VA_ARGS__; } break;                    \
+    case 10: { constexpr int LS = 10; __VA_ARGS__; } break;                  \
+    case 11: { constexpr int LS = 11; __VA_ARGS__; } break;                  \
+    case 12: { constexpr int LS = 12; __VA_ARGS__; } break;                  \
+    case 13: { constexpr int LS = 13; __VA_ARGS__; } break;                  \
+    case 14: { constexpr int LS = 14; __VA_ARGS__; } break;                  \
+    case 15: { constexpr int LS = 15; __VA_ARGS__; } break;                  \
+    default: { constexpr int LS = -1; __VA_ARGS__; } break;                  \
+  }
+// LS = -1 selects the runtime-degree path
+template <int LS>
+__device__ __forceinline__ double geg_eval_d(const RecCoef& rc, int l, double t) {
+  if constexpr (LS >= 0) return geg_eval_s<LS>(rc, t);
+  else return geg_eval(rc, l, t);
+}
+template <int LS>
+__device__ __forceinline__ double geg_deriv_d(const RecCoef& rc, int l, double t) {
+  if constexpr (LS >= 0) return geg_deriv_s<LS>(rc, t);
+  else return geg_deriv(rc, l, t);
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP64 tensor-core MMA: D(8x8) += A(8x4) B(4x8).  SASS: DMMA.8x8x4 (the only f64 MMA shape sm_100a
 // has; tcgen05 has no f64 kind).  lane l: a = A[l/4][l%4], b = B[l%4][l/4], c0/c1 = C[l/4][2(l%4)+{0,1}].
@@ -161,6 +227,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+
+// cp.async completion tracked by an mbarrier: the barrier gets one arrival from this thread once all
+// of its prior cp.async copies have landed (".noinc": the expected count must include it).
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory");
 }
 
 // Stage `bytes` from global to shared with one elected thread issuing TMA bulk copies (<= 64 KiB

@@ -2,8 +2,17 @@
 
 namespace gpfy {
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) {
+// Producer/consumer pipeline without CTA-wide barriers: every thread copies its share of a stage with
+// cp.async and signals the stage's FULL mbarrier when its copies land; a warp waits on FULL, issues
+// its DMMAs, and arrives on the stage's EMPTY mbarrier; a stage is refilled only after all 12 warps
+// released it.  Warps may therefore drift by up to one k-step and keep the FP64 tensor pipe fed.
+// VAR is 0 in production; tools/gemm_bench.cu instantiates knock-out variants to attribute time:
+//   bit 0: no global loads (stages are signalled full without copying)   bit 1: no epilogue at all
+//   bit 2: epilogue without the psi reduction
+template <int VAR>
+__device__ __forceinline__ void gemm_body(const GemmArgs& a) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ uint64_t bar_full[GEMM_STAGES], bar_empty[GEMM_STAGES];
   double* As = smem;                                           // [STAGES][BM][AS]
   double* Bs = smem + GEMM_STAGES * GEMM_BM * GEMM_AS;         // [STAGES][BK][BS]
   const int tid = threadIdx.x;
@@ -19,59 +28,83 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) 
   const int n_my = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = n_my * kt;
 
-  // producer state: iteration `pit` of the flattened (tile, kb) stream
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&bar_full[s], GEMM_THREADS);
+      mbar_init(&bar_empty[s], GEMM_THREADS / 32);
+    }
+  }
+  __syncthreads();
+
+  // ---- producer state: this thread's 2 A chunks and 4 B chunks (16 bytes each) of every stage ----
+  const int a_r0 = tid >> 3, a_kc = (tid & 7) * 2;          // rows a_r0 and a_r0 + 48
+  const int b_r0 = tid / 96, b_nc = (tid % 96) * 2;         // rows b_r0 + {0, 4, 8, 12}
+  const double* pA[2];
+  const double* pB[4];
+  bool okA[2], okB;
   int p_tile = blockIdx.x, p_kb = 0, pit = 0;
-  auto load_next = [&]() {
+  auto producer_tile = [&]() {
+    const int row0 = (p_tile % m_tiles) * GEMM_BM, col0 = (p_tile / m_tiles) * GEMM_BN;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      okA[i] = (row0 + a_r0 + i * 48) < a.m;
+      pA[i] = okA[i] ? a.A + (int64_t)(row0 + a_r0 + i * 48) * a.lda + a_kc : a.A;
+    }
+    okB = (col0 + b_nc) < a.n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pB[i] = okB ? a.B + (int64_t)(b_r0 + i * 4) * a.ldb + col0 + b_nc : a.B;
+  };
+  producer_tile();
+  auto produce = [&]() {
     if (pit < total) {
       const int st = pit % GEMM_STAGES;
-      const int row0 = (p_tile % m_tiles) * GEMM_BM, col0 = (p_tile / m_tiles) * GEMM_BN;
-      double* as = As + st * GEMM_BM * GEMM_AS;
+      if (pit >= GEMM_STAGES) mbar_wait(&bar_empty[st], ((pit / GEMM_STAGES) - 1) & 1);
+      double* as = As + st * GEMM_BM * GEMM_AS + a_r0 * GEMM_AS + a_kc;
+      double* bs = Bs + st * GEMM_BK * GEMM_BS + b_r0 * GEMM_BS + b_nc;
+      if (!(VAR & 1)) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {  // A: 96 rows x 8 chunks of 16 B
-        int c = tid + i * GEMM_THREADS;
-        int r = c >> 3, kc = (c & 7) * 2;
-        bool p = (row0 + r) < a.m;
-        const double* src = p ? a.A + (int64_t)(row0 + r) * a.lda + p_kb * GEMM_BK + kc : a.A;
-        cp_async16(as + r * GEMM_AS + kc, src, p);
-      }
-      double* bs = Bs + st * GEMM_BK * GEMM_BS;
+        for (int i = 0; i < 2; ++i) cp_async16(as + i * 48 * GEMM_AS, pA[i], okA[i]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {  // B: 16 rows x 96 chunks
-        int c = tid + i * GEMM_THREADS;
-        int r = c / 96, nc = (c % 96) * 2;
-        bool p = (col0 + nc) < a.n;
-        const double* src = p ? a.B + (int64_t)(p_kb * GEMM_BK + r) * a.ldb + col0 + nc : a.B;
-        cp_async16(bs + r * GEMM_BS + nc, src, p);
+        for (int i = 0; i < 4; ++i) cp_async16(bs + i * 4 * GEMM_BS, pB[i], okB);
       }
+      cp_async_mbar_arrive(&bar_full[st]);
       ++pit;
-      if (++p_kb == kt) { p_kb = 0; p_tile += gridDim.x; }
+      if (++p_kb == kt) {
+        p_kb = 0;
+        p_tile += gridDim.x;
+        if (pit < total) producer_tile();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) if (okA[i]) pA[i] += GEMM_BK;
+        if (okB) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pB[i] += (int64_t)GEMM_BK * a.ldb;
+        }
+      }
     }
-    cp_async_commit();
   };
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) produce();
 
   double acc[3][8][2];
-#pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) load_next();
-
   int c_tile = blockIdx.x, c_kb = 0;
+  int row0 = (c_tile % m_tiles) * GEMM_BM, col0 = (c_tile / m_tiles) * GEMM_BN;
+  bool active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;
   for (int it = 0; it < total; ++it) {
-    cp_async_wait<GEMM_STAGES - 2>();
-    __syncthreads();
-    load_next();
+    const int st = it % GEMM_STAGES;
     if (c_kb == 0) {
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
     }
-    const int row0 = (c_tile % m_tiles) * GEMM_BM, col0 = (c_tile / m_tiles) * GEMM_BN;
-    const bool active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;
-    if (active) {
-      const int st = it % GEMM_STAGES;
-      const double* as = As + st * GEMM_BM * GEMM_AS + (wm * 24 + g) * GEMM_AS + t4;
-      const double* bs = Bs + st * GEMM_BK * GEMM_BS + t4 * GEMM_BS + wn * 64 + g;
+    mbar_wait(&bar_full[st], (it / GEMM_STAGES) & 1);
+    const double* as = As + st * GEMM_BM * GEMM_AS + (wm * 24 + g) * GEMM_AS + t4;
+    const double* bs = Bs + st * GEMM_BK * GEMM_BS + t4 * GEMM_BS + wn * 64 + g;
 #pragma unroll
-      for (int k4 = 0; k4 < GEMM_BK / 4; ++k4) {
+    for (int k4 = 0; k4 < GEMM_BK / 4; ++k4) {
+      if (active) {
         double af[3], bf[8];
 #pragma unroll
         for (int r = 0; r < 3; ++r) af[r] = as[r * 8 * GEMM_AS + k4 * 4];
@@ -82,12 +115,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) 
 #pragma unroll
           for (int c = 0; c < 8; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
       }
+      if (k4 == 0) produce();  // the copy issue hides behind the DMMAs just queued
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_empty[st]);
+
     if (++c_kb == kt) {
       double ps[8][2];
 #pragma unroll
       for (int c = 0; c < 8; ++c) ps[c][0] = ps[c][1] = 0.0;
-      if (active) {
+      if (active && !(VAR & 2)) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int row = row0 + wm * 24 + r * 8 + g;
@@ -106,7 +143,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) 
                   v.y += a.beta * o.y;
                 }
                 *dst = v;
-                if (a.psi_out) {
+                if (a.psi_out && !(VAR & 4)) {
                   const double2 z = *reinterpret_cast<const double2*>(a.B + (int64_t)row * a.ldb + col);
                   ps[c][0] = fma(z.x, v.x, ps[c][0]);
                   ps[c][1] = fma(z.y, v.y, ps[c][1]);
@@ -116,7 +153,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) 
           }
         }
       }
-      if (a.psi_out && (col0 + wn * 64) < a.n) {
+      if (a.psi_out && !(VAR & 6) && (col0 + wn * 64) < a.n) {
         double* dst = a.psi_out + (int64_t)((c_tile % m_tiles) * 4 + wm) * a.ld_psi;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -131,10 +168,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) 
       }
       c_kb = 0;
       c_tile += gridDim.x;
+      row0 = (c_tile % m_tiles) * GEMM_BM;
+      col0 = (c_tile / m_tiles) * GEMM_BN;
+      active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;
     }
   }
-  cp_async_wait<0>();
 }
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) { gemm_body<0>(a); }
 
 int launch_gemm(cudaStream_t stream, const GemmArgs& a, int num_sms) {
   if (a.k % GEMM_BK != 0 || (a.n & 1) || (a.lda & 1) || (a.ldb & 1) || (a.ldc & 1)) {

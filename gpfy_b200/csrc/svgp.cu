@@ -177,7 +177,8 @@ __global__ void reduce_g_kernel(const double* Gpart, const double* bzpart, doubl
   if (e < (int64_t)Mp * Mp) {
     const int i = (int)(e / Mp), j = (int)(e % Mp);
     int bi = i / SYRK_B, bj = j / SYRK_B, ri = i % SYRK_B, rj = j % SYRK_B;
-    if (bi < bj) { int t = bi; bi = bj; bj = t; t = ri; ri = rj; rj = t; }
+    // lower blocks only; inside a diagonal block only the lower half is guaranteed (upper warp tiles are skipped)
+    if (bi < bj || (bi == bj && ri < rj)) { int t = bi; bi = bj; bj = t; t = ri; ri = rj; rj = t; }
     const int blk = bi * (bi + 1) / 2 + bj;
     double s = 0.0;
     for (int ks = 0; ks < KS; ++ks) s += Gpart[((int64_t)ks * nblk + blk) * (SYRK_B * SYRK_B) + ri * SYRK_B + rj];
@@ -337,7 +338,7 @@ struct Plan {
   int npart;
   // offsets (doubles)
   int64_t o_sw, o_sb, o_dvec, o_vhat_p, o_mu2, o_linv, o_E, o_ET, o_tmp1, o_tmp2, o_tmp3, o_LqP, o_W0, o_W2, o_dE, o_Gz, o_bz,
-      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, total;
+      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, total;
   int npsi;
 };
 
@@ -398,6 +399,9 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->o_wp = take((int64_t)s.P * p->nc);
   p->o_mz = take((int64_t)s.P * p->nc);
   p->o_psi = take((int64_t)s.P * p->npsi * p->nc);
+  p->o_cq = take((int64_t)s.P * p->nc);
+  p->o_dr = take(p->nc);
+  p->o_dT = take(op == GPFY_OP_ELBO ? Mp * p->nc : 0);
   p->total = o;
 }
 
@@ -446,16 +450,16 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
 }
 
 template <int DIMP>
-static int launch_lik_bwd(cudaStream_t st, const LikBwdArgs& a) {
+static int launch_zonal_bwd(cudaStream_t st, const ZonalBwdArgs& a) {
   const int smem = (a.Mp * DIMP + a.P * a.Mp + 8 * DIMP * 32) * 8;
-  const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 31) / 32);
-#define GPFY_LB(PM)                                              \
-  {                                                              \
-    GPFY_TRY(set_smem(lik_bwd_kernel<DIMP, PM>, smem));          \
-    lik_bwd_kernel<DIMP, PM><<<grid, 256, smem, st>>>(a);        \
+  const unsigned grid = (unsigned)((a.npts + 31) / 32);
+#define GPFY_ZB(PM)                                               \
+  {                                                               \
+    GPFY_TRY(set_smem(zonal_bwd_kernel<DIMP, PM>, smem));         \
+    zonal_bwd_kernel<DIMP, PM><<<grid, 256, smem, st>>>(a);       \
   }
-  if (a.P == 1) GPFY_LB(1) else if (a.P == 2) GPFY_LB(2) else if (a.P <= 4) GPFY_LB(4) else GPFY_LB(8)
-#undef GPFY_LB
+  if (a.P == 1) GPFY_ZB(1) else if (a.P == 2) GPFY_ZB(2) else if (a.P <= 4) GPFY_ZB(4) else GPFY_ZB(8)
+#undef GPFY_ZB
   GPFY_COUNT_LAUNCH();
   GPFY_LAUNCH_OK();
   return GPFY_OK;
@@ -688,18 +692,24 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
-    LikBwdArgs la;
-    la.C = ws + p.o_C; la.ldz = p.nc; la.c_stride = (int64_t)Mp * p.nc;
-    la.psi_part = ws + p.o_psi; la.npsi = p.npsi; la.mz = ws + p.o_mz;
-    la.XH = ws + p.o_XH; la.R = ws + p.o_R; la.Y = Y + c0 * s.P;
-    la.vhat_p = ws + p.o_vhat_p; la.vptr = variance; la.s2ptr = sigma2;
-    la.Mp = Mp; la.M = s.M; la.d = s.d; la.P = s.P; la.order = desc->kernel_order; la.npts = npts;
-    la.wq = ws + p.o_wq; la.wp = ws + p.o_wp; la.partials = ws + p.o_partials; la.npart = p.npart;
-    la.accumulate = chunk > 0;
-    la.lik_kind = desc->likelihood; la.deg = deg; la.rc = rc;
     if (chunk == 0 && ((npts_e + 31) / 32) < p.nblocks_c)  // single short chunk: clear unused slots
       GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, p.nblocks_c * p.npart * 8, st));
-    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_lik_bwd<DIMP>(st, la)));
+    LikPointArgs lp;
+    lp.psi_part = ws + p.o_psi; lp.npsi = p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
+    lp.R = ws + p.o_R; lp.Y = Y + c0 * s.P; lp.vptr = variance; lp.s2ptr = sigma2;
+    lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
+    lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
+    lp.partials = ws + p.o_partials; lp.npart = p.npart; lp.accumulate = chunk > 0;
+    GPFY_K(lik_point_kernel, (unsigned)((npts_e + 255) / 256), 256, 0, st, lp);
+
+    ZonalBwdArgs zb;
+    zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
+    zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
+    zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p;
+    zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.P = s.P; zb.npts = npts;
+    zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.accumulate = chunk > 0;
+    zb.deg = deg; zb.rc = rc;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd<DIMP>(st, zb)));
 
     for (int q = 0; q < s.P; ++q) {
       SyrkArgs sa;
@@ -716,7 +726,7 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
     }
 
     DvhatArgs da;
-    da.dT = ws + p.o_C; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
+    da.dT = ws + p.o_dT; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
     da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
     da.accumulate = chunk > 0;
     GPFY_TRY(launch_dvhat(st, da));

@@ -94,27 +94,29 @@ __global__ void __launch_bounds__(256) zonal_fwd_kernel(ZonalArgs a) {
   int base = 0;
   for (int l = 0; l < a.deg.F; ++l) {
     const int ml = a.deg.m[l];
-    for (int j = warp; j < ml; j += 8) {
-      const int i = base + j;
-      if (valid) {
-        const double* v = vs + i * DIMP;
-        double t0 = 0.0, t1 = 0.0;
+    if (valid) {
+      GPFY_DEGREE_SWITCH(l, {
+        for (int j = warp; j < ml; j += 8) {
+          const int i = base + j;
+          const double* v = vs + i * DIMP;
+          double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < DIMP; c += 2) {
-          double2 vv = *reinterpret_cast<const double2*>(v + c);
-          t0 = fma(vv.x, xh[c], t0);
-          t1 = fma(vv.y, xh[c + 1], t1);
-        }
-        const double z = geg_eval(a.rc, l, t0 + t1);
-        a.Z[(int64_t)i * a.ldz + n] = z;
-        if (a.mz) {
+          for (int c = 0; c < DIMP; c += 2) {
+            double2 vv = *reinterpret_cast<const double2*>(v + c);
+            t0 = fma(vv.x, xh[c], t0);
+            t1 = fma(vv.y, xh[c + 1], t1);
+          }
+          const double z = geg_eval_d<LS>(a.rc, l, t0 + t1);
+          a.Z[(int64_t)i * a.ldz + n] = z;
+          if (a.mz) {
 #pragma unroll
-          for (int p = 0; p < PMAX; ++p)
-            if (p < a.P) mz[p] = fma(mu2s[p * a.Mp + i], z, mz[p]);
+            for (int p = 0; p < PMAX; ++p)
+              if (p < a.P) mz[p] = fma(mu2s[p * a.Mp + i], z, mz[p]);
+          }
         }
-      } else if (padcol) {
-        a.Z[(int64_t)i * a.ldz + n] = 0.0;
-      }
+      });
+    } else if (padcol) {
+      for (int j = warp; j < ml; j += 8) a.Z[(int64_t)(base + j) * a.ldz + n] = 0.0;
     }
     base += ml;
   }
@@ -253,37 +255,103 @@ __device__ __forceinline__ void lik_terms(const LikParams& lp, double fmu, doubl
 // ------------------------------------------------------------------------------------------------
 constexpr int PART_E = 0, PART_DV = 1, PART_DS2 = 2, PART_DB = 3, PART_DW = 4;  // then d entries
 
-struct LikBwdArgs {
-  double* C;            // [P][Mp][ldz]; C[0] is overwritten with dT
-  int64_t ldz;
-  int64_t c_stride;     // Mp * ldz
+struct LikPointArgs {
   const double* psi_part; // [P][npsi][ldz] partial sums of z . C_p from the GEMM epilogue
   int npsi;
   const double* mz;     // [P][ldz]
-  const double* XH;     // [npts][DIMP]
+  int64_t ldz;
   const double* R;
   const double* Y;      // [npts][P]
-  const double* vhat_p; // [Mp][DIMP], mu2 [P][Mp] right behind it
   const double* vptr;   // [1] kernel variance
   const double* s2ptr;  // [1] noise variance (Gaussian)
-  int Mp, M, d, P, order;
+  int P, order, lik_kind;
   int64_t npts;
-  double* wq;           // [P][ldz]
-  double* wp;           // [P][ldz]
-  double* partials;     // [gridDim.x][npart]
+  double* wq;           // [P][ldz]  q r^2   (SYRK weights)
+  double* wp;           // [P][ldz]  p r     (mean-gradient weights)
+  double* cq;           // [P][ldz]  2 q r^2 (coefficient of C in dz)
+  double* dr;           // [ldz]     direct d/dr terms
+  double* partials;     // [npts / 32][npart]: one row per 32 points (PART_E, PART_DV, PART_DS2 written here)
   int npart;
-  int accumulate;       // add to existing partials
-  int lik_kind;
+  int accumulate;
+};
+
+// One point per thread: psi, fmu, fvar, the likelihood terms and everything the backward pass needs
+// per point (model.py:136, spherical.py:400, likelihoods.py:210-218 / :254-278).
+__global__ void __launch_bounds__(256) lik_point_kernel(LikPointArgs a) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = n < a.npts;
+  double pe = 0.0, pdv = 0.0, pds2 = 0.0;
+  if (!valid && n < ((a.npts + 1) & ~(int64_t)1)) {
+    for (int p = 0; p < a.P; ++p) { a.wq[p * a.ldz + n] = 0.0; a.wp[p * a.ldz + n] = 0.0; }
+  }
+  if (valid) {
+    LikParams lp;
+    lp.kind = a.lik_kind;
+    lp.sigma2 = a.lik_kind == GPFY_LIK_GAUSSIAN ? a.s2ptr[0] : 1.0;
+    const double v = a.vptr[0];
+    const double r = a.R[n];
+    double kd = v, dkd = 0.0;   // K_diag = v r^(2 order) and its r-derivative
+    {
+      double rp = 1.0;
+      for (int k = 0; k < 2 * a.order - 1; ++k) rp *= r;
+      if (a.order > 0) { kd = v * rp * r; dkd = 2.0 * a.order * v * rp; }
+    }
+    const double r2 = r * r;
+    double dr = 0.0;
+    for (int p = 0; p < a.P; ++p) {
+      double psi = 0.0;
+      for (int k = 0; k < a.npsi; ++k) psi += a.psi_part[((int64_t)p * a.npsi + k) * a.ldz + n];
+      const double mzp = a.mz[(int64_t)p * a.ldz + n];
+      const double fmu = r * mzp;
+      const double fvar = kd + r2 * psi;
+      double e, pp, qq, ds2;
+      lik_terms(lp, fmu, fvar, a.Y[n * a.P + p], e, pp, qq, ds2);
+      pe += e;
+      pds2 += ds2;
+      pdv += qq * (kd / v);
+      a.wq[p * a.ldz + n] = qq * r2;
+      a.wp[p * a.ldz + n] = pp * r;
+      a.cq[p * a.ldz + n] = 2.0 * qq * r2;
+      dr += pp * mzp + qq * (dkd + 2.0 * r * psi);
+    }
+    a.dr[n] = dr;
+  }
+  pe = warp_sum(pe); pdv = warp_sum(pdv); pds2 = warp_sum(pds2);
+  if ((threadIdx.x & 31) == 0 && (n >> 5) < ((a.npts + 31) >> 5)) {
+    double* dst = a.partials + (n >> 5) * a.npart;
+    if (a.accumulate) { dst[PART_E] += pe; dst[PART_DV] += pdv; dst[PART_DS2] += pds2; }
+    else { dst[PART_E] = pe; dst[PART_DV] = pdv; dst[PART_DS2] = pds2; }
+  }
+}
+
+struct ZonalBwdArgs {
+  const double* C;      // [P][Mp][ldz]
+  double* dT;           // [Mp][ldz] (separate buffer: lets the loads of C run ahead of the stores)
+  int64_t ldz;
+  int64_t c_stride;     // Mp * ldz
+  const double* wp;     // [P][ldz]  p r
+  const double* cq;     // [P][ldz]  2 q r^2
+  const double* dr;     // [ldz]
+  const double* XH;     // [npts][DIMP]
+  const double* R;
+  const double* vhat_p; // [Mp][DIMP], mu2 [P][Mp] right behind it
+  int Mp, M, d, P;
+  int64_t npts;
+  double* partials;     // [npts / 32][npart]; PART_DB and PART_DW.. written here
+  int npart;
+  int accumulate;
   DegreeTable deg;
   RecCoef rc;
 };
 
-// Block = 8 warps x 32 points (lane = point, warp w owns rows w, w + 8, ... of every degree).
+// Backward through the zonal map.  Block = 8 warps x 32 points (lane = point, warp w owns rows
+// w, w + 8, ... of every degree):
+//   dz = sum_p (r p) mu2_p + (2 q r^2) C_p ;  dt = dz * 2 alpha C_{l-1}^{alpha+1}(t)   (gegenbauer.py:73-81)
+//   dT overwrites C_0;  dxhat += Vhat^T dt;  du = (dxhat - xhat (xhat . dxhat)) / r + dr xhat  (VJP of spherical.py:248-249)
 template <int DIMP, int PMAX>
-__global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) zonal_bwd_kernel(ZonalBwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint64_t bar;
-  __shared__ double s_cp[PMAX][32], s_cq[PMAX][32];
   double* vs = smem;                      // [Mp][DIMP]
   double* mu2s = smem + a.Mp * DIMP;      // [P][Mp]
   double* red = mu2s + a.P * a.Mp;        // [8][DIMP][32]
@@ -292,52 +360,6 @@ __global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * 32 + lane;
   const bool valid = n < a.npts;
-  double part[PART_DW + DIMP];
-  double dr = 0.0, r = 1.0;
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < PART_DW + DIMP; ++k) part[k] = 0.0;
-    if (!valid && n < ((a.npts + 1) & ~(int64_t)1)) {
-      for (int p = 0; p < a.P; ++p) { a.wq[p * a.ldz + n] = 0.0; a.wp[p * a.ldz + n] = 0.0; }
-    }
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) s_cp[p][lane] = s_cq[p][lane] = 0.0;
-    if (valid) {
-      LikParams lp;
-      lp.kind = a.lik_kind;
-      lp.sigma2 = a.lik_kind == GPFY_LIK_GAUSSIAN ? a.s2ptr[0] : 1.0;
-      const double v = a.vptr[0];
-      r = a.R[n];
-      double kd = v, dkd = 0.0;   // K_diag = v r^(2 order) (spherical.py:400) and its r-derivative
-      {
-        double rp = 1.0;
-        for (int k = 0; k < 2 * a.order - 1; ++k) rp *= r;
-        if (a.order > 0) { kd = v * rp * r; dkd = 2.0 * a.order * v * rp; }
-      }
-      const double r2 = r * r;
-#pragma unroll
-      for (int p = 0; p < PMAX; ++p)
-        if (p < a.P) {
-          double psi = 0.0;
-          for (int k = 0; k < a.npsi; ++k) psi += a.psi_part[((int64_t)p * a.npsi + k) * a.ldz + n];
-          const double mzp = a.mz[(int64_t)p * a.ldz + n];
-          const double fmu = r * mzp;
-          const double fvar = kd + r2 * psi;
-          double e, pp, qq, ds2;
-          lik_terms(lp, fmu, fvar, a.Y[n * a.P + p], e, pp, qq, ds2);
-          part[PART_E] += e;
-          part[PART_DS2] += ds2;
-          part[PART_DV] += qq * (kd / v);
-          a.wq[p * a.ldz + n] = qq * r2;
-          a.wp[p * a.ldz + n] = pp * r;
-          s_cp[p][lane] = r * pp;
-          s_cq[p][lane] = 2.0 * qq * r2;
-          dr += pp * mzp + qq * (dkd + 2.0 * r * psi);
-        }
-    }
-  }
-  __syncthreads();
-
   double xh[DIMP], dxh[DIMP];
 #pragma unroll
   for (int c = 0; c < DIMP; ++c) { xh[c] = 0.0; dxh[c] = 0.0; }
@@ -349,36 +371,56 @@ __global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
     }
     double cp_[PMAX], cq_[PMAX];
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p) { cp_[p] = s_cp[p][lane]; cq_[p] = s_cq[p][lane]; }
+    for (int p = 0; p < PMAX; ++p) {
+      cp_[p] = (p < a.P) ? a.wp[p * a.ldz + n] : 0.0;
+      cq_[p] = (p < a.P) ? a.cq[p * a.ldz + n] : 0.0;
+    }
+    const double* __restrict__ Cg = a.C;
+    double* __restrict__ dTg = a.dT;
     int base = 0;
     for (int l = 0; l < a.deg.F; ++l) {
       const int ml = a.deg.m[l];
-      for (int j = warp; j < ml; j += 8) {
-        const int i = base + j;
-        double cv[PMAX];
+      GPFY_DEGREE_SWITCH(l, {
+        // rows j, j + 8, j + 16, j + 24 of this warp are batched: 4 independent loads in flight
+        for (int j0 = warp; j0 < ml; j0 += 32) {
+          double cv[4][PMAX];
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p)
-          if (p < a.P) cv[p] = a.C[p * a.c_stride + (int64_t)i * a.ldz + n];
-        const double* vv = vs + i * DIMP;
-        double vr[DIMP];
-        double t0 = 0.0, t1 = 0.0;
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 8 * u;
 #pragma unroll
-        for (int c = 0; c < DIMP; c += 2) {
-          double2 v2 = *reinterpret_cast<const double2*>(vv + c);
-          vr[c] = v2.x; vr[c + 1] = v2.y;
-          t0 = fma(v2.x, xh[c], t0);
-          t1 = fma(v2.y, xh[c + 1], t1);
+            for (int p = 0; p < PMAX; ++p)
+              cv[u][p] = (j < ml && p < a.P) ? __ldg(Cg + p * a.c_stride + (int64_t)(base + j) * a.ldz + n) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 8 * u;
+            if (j < ml) {
+              const int i = base + j;
+              const double* vv = vs + i * DIMP;
+              double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+              for (int c = 0; c < DIMP; c += 2) {
+                double2 v2 = *reinterpret_cast<const double2*>(vv + c);
+                t0 = fma(v2.x, xh[c], t0);
+                t1 = fma(v2.y, xh[c + 1], t1);
+              }
+              const double zp = geg_deriv_d<LS>(a.rc, l, t0 + t1);
+              double dz = 0.0;
+#pragma unroll
+              for (int p = 0; p < PMAX; ++p)
+                if (p < a.P) dz += cp_[p] * mu2s[p * a.Mp + i] + cq_[p] * cv[u][p];
+              const double dt = dz * zp;
+              dTg[(int64_t)i * a.ldz + n] = dt;
+#pragma unroll
+              for (int c = 0; c < DIMP; c += 2) {
+                double2 v2 = *reinterpret_cast<const double2*>(vv + c);
+                dxh[c] = fma(v2.x, dt, dxh[c]);
+                dxh[c + 1] = fma(v2.y, dt, dxh[c + 1]);
+              }
+            }
+          }
         }
-        const double zp = geg_deriv(a.rc, l, t0 + t1);
-        double dz = 0.0;
-#pragma unroll
-        for (int p = 0; p < PMAX; ++p)
-          if (p < a.P) dz += cp_[p] * mu2s[p * a.Mp + i] + cq_[p] * cv[p];
-        const double dt = dz * zp;
-        a.C[(int64_t)i * a.ldz + n] = dt;
-#pragma unroll
-        for (int c = 0; c < DIMP; ++c) dxh[c] = fma(vr[c], dt, dxh[c]);
-      }
+      });
       base += ml;
     }
   }
@@ -386,7 +428,11 @@ __global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
   for (int c = 0; c < DIMP; ++c) red[(warp * DIMP + c) * 32 + lane] = dxh[c];
   __syncthreads();
   if (warp == 0) {
+    double part[1 + DIMP];
+#pragma unroll
+    for (int k = 0; k < 1 + DIMP; ++k) part[k] = 0.0;
     if (valid) {
+      const double r = a.R[n], dr = a.dr[n];
 #pragma unroll
       for (int c = 0; c < DIMP; ++c) {
         double s = 0.0;
@@ -394,7 +440,6 @@ __global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
         for (int w = 0; w < 8; ++w) s += red[(w * DIMP + c) * 32 + lane];
         dxh[c] = s;
       }
-      // du = (dxh - xh (xh . dxh)) / r + dr xh      (VJP of spherical.py:248-249)
       double dot = 0.0;
 #pragma unroll
       for (int c = 0; c < DIMP; ++c) dot = fma(xh[c], dxh[c], dot);
@@ -402,15 +447,15 @@ __global__ void __launch_bounds__(256) lik_bwd_kernel(LikBwdArgs a) {
       for (int c = 0; c < DIMP; ++c) {
         const double du = (dxh[c] - xh[c] * dot) / r + dr * xh[c];
         const double u = xh[c] * r;
-        if (c < a.d) part[PART_DW + c] = du * u;   // d w_j = sum du_j x_j / (2 sqrt w_j) = sum du_j u_j / (2 w_j)
-        else if (c == a.d) part[PART_DB] = du;     // d b   = sum du_dim / (2 sqrt b)
+        if (c < a.d) part[1 + c] = du * u;   // d w_j = sum du_j x_j / (2 sqrt w_j) = sum du_j u_j / (2 w_j)
+        else if (c == a.d) part[0] = du;     // d b   = sum du_dim / (2 sqrt b)
       }
     }
 #pragma unroll
-    for (int k = 0; k < PART_DW + DIMP; ++k) {
+    for (int k = 0; k < 1 + DIMP; ++k) {
       const double s = warp_sum(part[k]);
-      if (lane == 0 && k < a.npart) {
-        double* dst = a.partials + (int64_t)blockIdx.x * a.npart + k;
+      if (lane == 0 && k < 1 + a.d) {
+        double* dst = a.partials + (int64_t)blockIdx.x * a.npart + (k == 0 ? PART_DB : PART_DW + k - 1);
         *dst = a.accumulate ? *dst + s : s;
       }
     }
@@ -450,7 +495,7 @@ __global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
 // diagonal blocks, bz += Z wp through one extra MMA column.  Split over points: CTA (blk, ks) owns a
 // contiguous range of the chunk and accumulates into its own slot of Gpart (no atomics, deterministic).
 // ------------------------------------------------------------------------------------------------
-constexpr int SYRK_B = 96, SYRK_BK = 16, SYRK_STAGES = 3, SYRK_THREADS = 256;
+constexpr int SYRK_B = 96, SYRK_BK = 16, SYRK_STAGES = 3, SYRK_THREADS = 256;  // 768 Z chunks per operand per stage: 3 per thread
 constexpr int SYRK_ZS = SYRK_BK + 4;
 constexpr int SYRK_STAGE_DBL = 2 * SYRK_B * SYRK_ZS + 2 * SYRK_BK;
 constexpr int SYRK_SMEM = SYRK_STAGES * SYRK_STAGE_DBL * 8;
@@ -471,6 +516,7 @@ struct SyrkArgs {
 
 __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ uint64_t bar_full[SYRK_STAGES], bar_empty[SYRK_STAGES];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;   // 4 x 2 warps, warp tile 24 x 48 (two warps per SM sub-partition)
   const int g = lane >> 2, t4 = lane & 3;
@@ -480,32 +526,49 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
   while (rem > bi) { rem -= bi + 1; ++bi; }
   const int bj = rem;
   const bool diag = bi == bj;
+  // on a diagonal block the warp tiles strictly above the diagonal are not needed (G is symmetric)
+  const bool compute = !(diag && wn == 1 && wm < 2);
   const int64_t p0 = (int64_t)ks * a.range;
   int64_t p1 = p0 + a.range;
   if (p1 > a.npts) p1 = a.npts;
   const int kt = p1 > p0 ? (int)((p1 - p0 + SYRK_BK - 1) / SYRK_BK) : 0;
 
-  auto load_stage = [&](int st, int kb) {
-    double* zi = smem + st * SYRK_STAGE_DBL;
-    double* zj = zi + SYRK_B * SYRK_ZS;
-    double* wqs = zj + SYRK_B * SYRK_ZS;
-    const int64_t pt0 = p0 + (int64_t)kb * SYRK_BK;
+  if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      int c = tid + i * SYRK_THREADS;  // 2 * 768 chunks
-      int which = c >= 768;
-      int cc = which ? c - 768 : c;
-      int r = cc >> 3, kc = (cc & 7) * 2;
-      int row = (which ? bj : bi) * SYRK_B + r;
-      bool p = row < a.Mp && (pt0 + kc) < p1;
-      const double* src = p ? a.Z + (int64_t)row * a.ldz + pt0 + kc : a.Z;
-      cp_async16((which ? zj : zi) + r * SYRK_ZS + kc, src, p);
+    for (int s = 0; s < SYRK_STAGES; ++s) {
+      mbar_init(&bar_full[s], SYRK_THREADS);
+      mbar_init(&bar_empty[s], SYRK_THREADS / 32);
     }
-    if (tid < 16) {
-      int which = tid >> 3, kc = (tid & 7) * 2;
-      bool p = (pt0 + kc) < p1;
-      const double* base = which ? a.wp : a.wq;
-      cp_async16(wqs + which * SYRK_BK + kc, p ? base + pt0 + kc : base, p);
+  }
+  __syncthreads();
+
+  // producer: 6 chunks of 16 bytes per thread and stage (Zi rows r, r+32, r+64; same for Zj) + weights
+  const int z_r = tid >> 3, z_kc = (tid & 7) * 2;
+  const double* pz[6];
+  bool okz[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int row = (i < 3 ? bi : bj) * SYRK_B + z_r + (i % 3) * 32;
+    okz[i] = row < a.Mp;
+    pz[i] = a.Z + (int64_t)(okz[i] ? row : 0) * a.ldz + p0 + z_kc;
+  }
+  const double* pw = ((tid >> 3) & 1 ? a.wp : a.wq) + p0 + z_kc;   // threads 0..15
+  int pit = 0;
+  auto produce = [&]() {
+    if (pit < kt) {
+      const int st = pit % SYRK_STAGES;
+      if (pit >= SYRK_STAGES) mbar_wait(&bar_empty[st], ((pit / SYRK_STAGES) - 1) & 1);
+      double* zi = smem + st * SYRK_STAGE_DBL;
+      const bool inr = (p0 + (int64_t)pit * SYRK_BK + z_kc) < p1;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        cp_async16(zi + (i / 3) * SYRK_B * SYRK_ZS + (z_r + (i % 3) * 32) * SYRK_ZS + z_kc, pz[i], okz[i] && inr);
+      if (tid < 16) cp_async16(zi + 2 * SYRK_B * SYRK_ZS + ((tid >> 3) & 1) * SYRK_BK + z_kc, pw, inr);
+      cp_async_mbar_arrive(&bar_full[st]);
+      ++pit;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pz[i] += SYRK_BK;
+      pw += SYRK_BK;
     }
   };
 
@@ -518,39 +581,38 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     for (int c = 0; c < 6; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
   }
 #pragma unroll
-  for (int s = 0; s < SYRK_STAGES - 1; ++s) {
-    if (s < kt) load_stage(s, s);
-    cp_async_commit();
-  }
+  for (int s = 0; s < SYRK_STAGES - 1; ++s) produce();
   for (int kb = 0; kb < kt; ++kb) {
-    cp_async_wait<SYRK_STAGES - 2>();
-    __syncthreads();
-    if (kb + SYRK_STAGES - 1 < kt) load_stage((kb + SYRK_STAGES - 1) % SYRK_STAGES, kb + SYRK_STAGES - 1);
-    cp_async_commit();
-    const double* base = smem + (kb % SYRK_STAGES) * SYRK_STAGE_DBL;
+    const int st = kb % SYRK_STAGES;
+    mbar_wait(&bar_full[st], (kb / SYRK_STAGES) & 1);
+    const double* base = smem + st * SYRK_STAGE_DBL;
     const double* zi = base + (wm * 24 + g) * SYRK_ZS + t4;
     const double* zj = base + SYRK_B * SYRK_ZS + (wn * 48 + g) * SYRK_ZS + t4;
     const double* wqs = base + 2 * SYRK_B * SYRK_ZS;
 #pragma unroll
     for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
-      double af[3], bf[6];
-      const double w = wqs[k4 * 4 + t4];
+      if (compute) {
+        double af[3], bf[6];
+        const double w = wqs[k4 * 4 + t4];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) af[r] = zi[r * 8 * SYRK_ZS + k4 * 4];
+        for (int r = 0; r < 3; ++r) af[r] = zi[r * 8 * SYRK_ZS + k4 * 4];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) bf[c] = zj[c * 8 * SYRK_ZS + k4 * 4] * w;
+        for (int c = 0; c < 6; ++c) bf[c] = zj[c * 8 * SYRK_ZS + k4 * 4] * w;
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
-      if (diag && wn == 0) {
-        const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
+          for (int c = 0; c < 6; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
+        if (diag && wn == 0) {
+          const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) dmma884(accx[r][0], accx[r][1], af[r], bx);
+          for (int r = 0; r < 3; ++r) dmma884(accx[r][0], accx[r][1], af[r], bx);
+        }
       }
+      if (k4 == 0) produce();
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_empty[st]);
   }
-  cp_async_wait<0>();
 
   double* gp = a.Gpart + ((int64_t)ks * a.nblk + blk) * (SYRK_B * SYRK_B);
 #pragma unroll
