@@ -55,6 +55,9 @@ _SIGNATURES = {
     "gpfy_prior_kl_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, _P]),
     "gpfy_predict_diag": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 11 + [_P, ctypes.c_size_t]),
     "gpfy_allreduce_packed": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),
+    "gpfy_to_sphere": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),
+    "gpfy_variational_expectations": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),
+    "gpfy_project_q": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P, _P, ctypes.c_size_t]),
 }
 
 _lib = None

@@ -822,6 +822,75 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
   return GPFY_OK;
 }
 
+int gpfy_to_sphere(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* w, const double* b, double* xs,
+                   double* r) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (n == 0) return GPFY_OK;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  const int sc = desc->weight_mode == GPFY_W_SCALAR;
+  GPFY_DISPATCH_DIMP(s.dimp, GPFY_K(to_sphere_kernel<DIMP>, grid, 128, 0, st, X, s.d, s.dim, w, sc, b, n, xs, r));
+  return GPFY_OK;
+}
+
+int gpfy_variational_expectations(void* stream, const GpfyDesc* desc, int64_t n, const double* fmu, const double* fvar,
+                                  const double* Y, const double* sigma2, double* out) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (n == 0) return GPFY_OK;
+  GPFY_K(var_exp_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, desc->likelihood, sigma2, n, s.P, fmu, fvar, Y,
+         out);
+  return GPFY_OK;
+}
+
+int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* A, const double* mu, const double* sigma,
+                   double* mean, double* var, void* workspace, size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (n == 0) return GPFY_OK;
+  Plan p;
+  make_plan(s, n, GPFY_OP_PREDICT, &p);
+  GPFY_TRY(check_ws(p, workspace, workspace_bytes));
+  double* ws = (double*)workspace;
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  // S_q = L L^T (variational.py:326-327) or Sigma (:438-440), padded, into W2
+  dim3 tg(Mp / 32, Mp / 32), tb(32, 8);
+  const unsigned sqg = (unsigned)((Mp2 + 255) / 256);
+  for (int q = 0; q < s.P; ++q) {
+    double* S = ws + p.o_W2 + q * Mp2;
+    if (desc->q_kind == GPFY_Q_TRIL) {
+      double* LqP = ws + p.o_LqP + q * Mp2;
+      GPFY_K(pad_square_kernel, sqg, 256, 0, st, sigma + (int64_t)q * s.M * s.M, LqP, s.M, Mp, 0);
+      GPFY_K(scale_rows_transpose_kernel, tg, tb, 0, st, LqP, (const double*)nullptr, (double*)nullptr, ws + p.o_tmp1, Mp);
+      GPFY_TRY(gemm_sq(st, LqP, ws + p.o_tmp1, S, Mp, 1.0, 0.0, p.sms));
+    } else {
+      GPFY_K(pad_square_kernel, sqg, 256, 0, st, sigma + (int64_t)q * s.M * s.M, S, s.M, Mp, 0);
+    }
+  }
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
+  for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
+    const int64_t npts = std::min(p.nc, n - c0);
+    const int64_t npts_e = (npts + 1) & ~(int64_t)1;
+    dim3 cg((unsigned)((npts_e + 255) / 256), s.M);
+    GPFY_K(copy_panel_kernel, cg, 256, 0, st, A + c0, n, s.M, npts, ws + p.o_Z, p.nc);
+    for (int q = 0; q < s.P; ++q) {
+      GemmArgs g;
+      g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
+      g.B = ws + p.o_Z; g.ldb = p.nc;
+      g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
+      g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
+      g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
+      GPFY_TRY(launch_gemm(st, g, p.sms));
+    }
+    GPFY_K(project_finish_kernel, (unsigned)((npts + 127) / 128), 128, 0, st, ws + p.o_Z, p.nc, s.M, s.P, mu, ws + p.o_psi, p.npsi,
+           npts, mean + c0 * s.P, var + c0 * s.P);
+  }
+  return GPFY_OK;
+}
+
 // NCCL is resolved from the process at run time (the host framework's copy)
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, void*);
 }  // extern "C"

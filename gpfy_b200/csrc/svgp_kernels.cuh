@@ -490,6 +490,64 @@ __global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
   }
 }
 
+// to_sphere only (spherical.py:214-249); sqrt of the variances is taken once per block in shared memory
+template <int DIMP>
+__global__ void to_sphere_kernel(const double* X, int d, int dim, const double* w, int scalar_w, const double* b, int64_t n,
+                                 double* xs, double* r) {
+  __shared__ double ssw[DIMP];
+  __shared__ double ssb;
+  if (threadIdx.x < d) ssw[threadIdx.x] = sqrt(w[scalar_w ? 0 : threadIdx.x]);
+  if (threadIdx.x == 0) ssb = sqrt(b[0]);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xh[DIMP];
+  const double rr = load_point<DIMP>(X, d, 1, ssw, &ssb, dim, i, xh);
+  r[i] = rr;
+#pragma unroll
+  for (int c = 0; c < DIMP; ++c)
+    if (c < dim) xs[i * dim + c] = xh[c];
+}
+
+// expected log-likelihood per point, summed over outputs (likelihoods.py:188-220, :254-278)
+__global__ void var_exp_kernel(int lik_kind, const double* s2ptr, int64_t n, int P, const double* fmu, const double* fvar,
+                               const double* Y, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LikParams lp;
+  lp.kind = lik_kind;
+  lp.sigma2 = lik_kind == GPFY_LIK_GAUSSIAN ? s2ptr[0] : 1.0;
+  double s = 0.0;
+  for (int p = 0; p < P; ++p) {
+    double e, pp, qq, ds2;
+    lik_terms(lp, fmu[i * P + p], fvar[i * P + p], Y[i * P + p], e, pp, qq, ds2);
+    s += e;
+  }
+  out[i] = s;
+}
+
+// copy a chunk of A [M, N] (ld = N, any parity) into the padded panel [Mp(+pad)][ldz]
+__global__ void copy_panel_kernel(const double* A, int64_t ldA, int M, int64_t npts, double* Zp, int64_t ldz) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (n < ((npts + 1) & ~(int64_t)1)) Zp[(int64_t)i * ldz + n] = (n < npts) ? A[(int64_t)i * ldA + n] : 0.0;
+}
+
+// mean[n, p] = sum_i mu[i, p] A[i, n];  var[n, p] = sum_k psi_part
+__global__ void project_finish_kernel(const double* Zp, int64_t ldz, int M, int P, const double* mu, const double* psi_part,
+                                      int npsi, int64_t npts, double* mean, double* var) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= npts) return;
+  for (int p = 0; p < P; ++p) {
+    double s = 0.0;
+    for (int i = 0; i < M; ++i) s = fma(__ldg(mu + i * P + p), Zp[(int64_t)i * ldz + n], s);
+    mean[n * P + p] = s;
+    double v = 0.0;
+    for (int k = 0; k < npsi; ++k) v += psi_part[((int64_t)p * npsi + k) * ldz + n];
+    var[n * P + p] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K_D  weighted SYRK on the FP64 tensor cores:  G (lower 96x96 blocks) += Z diag(wq) Z^T  and, on the
 // diagonal blocks, bz += Z wp through one extra MMA column.  Split over points: CTA (blk, ks) owns a

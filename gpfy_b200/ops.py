@@ -145,6 +145,38 @@ class HotPath:
             _ptr(ws), ws.numel()))
         return fmu, fvar
 
+    def to_sphere(self, X, w, b):
+        """(x_sphere [N, dim], r [N]) — spherical.py:230-249."""
+        X = self._dev(X)
+        n = X.shape[0]
+        w, b = self._dev(w), self._dev(b)
+        xs = torch.empty((n, self.dim), dtype=torch.float64, device=self.device)
+        r = torch.empty((n,), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gpfy_to_sphere(_stream(self.device), ctypes.byref(self.desc), n, _ptr(X), _ptr(w), _ptr(b), _ptr(xs), _ptr(r)))
+        return xs, r
+
+    def variational_expectations(self, fmu, fvar, Y, sigma2=None):
+        """Expected log-likelihood per point [N] — likelihoods.py:188-220 / :254-278."""
+        fmu, fvar, Y = self._dev(fmu), self._dev(fvar), self._dev(Y)
+        n = fmu.shape[0]
+        s2 = self._dev(sigma2 if sigma2 is not None else 1.0)
+        out = torch.empty((n,), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gpfy_variational_expectations(_stream(self.device), ctypes.byref(self.desc), n, _ptr(fmu), _ptr(fvar),
+                                                          _ptr(Y), _ptr(s2), _ptr(out)))
+        return out
+
+    def project_q(self, A, mu, sigma):
+        """(A^T mu [N, P], diag(A^T S A) [N, P]) for a projection A [M, N] — variational.py:288-328 / :420-441."""
+        A = self._dev(A)
+        n = A.shape[1]
+        mu, sigma = self._dev(mu), self._dev(sigma)
+        mean = torch.empty((n, self.P), dtype=torch.float64, device=self.device)
+        var = torch.empty((n, self.P), dtype=torch.float64, device=self.device)
+        ws = self.workspace(n, _lib.OP_PREDICT)
+        _lib.check(self.lib.gpfy_project_q(_stream(self.device), ctypes.byref(self.desc), n, _ptr(A), _ptr(mu), _ptr(sigma),
+                                           _ptr(mean), _ptr(var), _ptr(ws), ws.numel()))
+        return mean, var
+
     def prior_kl_valgrad(self, mu, sigma):
         """KL(q || N(0, I)), dKL/dmu [M, P], dKL/dSigma [P, M, M] (TriL) — variational.py:225-240."""
         mu, sigma = self._dev(mu), self._dev(sigma)

@@ -1,0 +1,168 @@
+"""Spherical kernels — the thin slice of gpfy/spherical.py the hot path needs:
+`init`, `_scale_X`, `to_sphere`, `K_diag`, `eigenvalues` (NTK / ArcCosine / PolynomialDecay).
+
+`K`, `K2`, `kappa`-based prior covariances and PolynomialDecay's lookup-table shape function only
+serve the full N x N `GP.cov/predict` and are out of scope; calling them raises.
+"""
+import dataclasses
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _runtime
+from .gegenbauer import GegenbauerLookupTable, gegenbauer_host
+from .harmonics.utils import funk_hecke_lambda
+from .param import Param, identity
+
+
+@dataclasses.dataclass(frozen=True)
+class Spherical:
+    order: int = 1
+    ard: bool = True
+    active_dims: Optional[object] = None
+    name: str = "Spherical"
+
+    def replace(self, **kw):
+        return dataclasses.replace(self, **kw)
+
+    # ---- spherical.py:82-151 ----
+    def init(self, key, input_dim: int, projection_dim: Optional[int] = None, max_num_eigvals: Optional[int] = None) -> Param:
+        rng = _runtime.as_rng(key)
+        bijectors = {}
+        if not projection_dim:
+            weight_variances = np.ones(input_dim) if self.ard else np.array(1.0)
+        else:
+            weight_variances = rng.standard_normal((input_dim, projection_dim))
+            bijectors = {"weight_variances": identity()}
+        params = {"weight_variances": weight_variances, "bias_variance": np.array(1.0), "variance": np.array(1.0)}
+        sphere_dim = projection_dim or input_dim
+        dim = sphere_dim + 1
+        alpha = (dim - 2.0) / 2.0
+        constants = {"sphere": {"sphere_dim": sphere_dim, "alpha": alpha}, self.name: {}}
+        if isinstance(self, PolynomialDecay):
+            params["beta"] = np.array(1.0)
+            constants["sphere"]["gegenbauer_lookup_table"] = GegenbauerLookupTable(self.truncation_level, alpha)
+        else:
+            constants[self.name]["eigenvalues"] = self._compute_eigvals(sphere_dim, max_num_eigvals=max_num_eigvals)
+        return Param(params={self.name: params}, _bijectors={self.name: bijectors}, constants=constants)
+
+    def _compute_eigvals(self, sphere_dim: int, *, max_num_eigvals=None, gegenbauer_lookup_table=None):
+        """spherical.py:153-180: Funk-Hecke eigenvalues for degrees 0..max_num_eigvals-1 (default 20)."""
+        max_num_eigvals = max_num_eigvals or 20
+        dim = sphere_dim + 1
+        fn = lambda x: self.shape_function(Param(), x)
+        return np.array([funk_hecke_lambda(fn, n, dim) for n in range(max_num_eigvals)])
+
+    def eigenvalues(self, param: Param, levels) -> np.ndarray:
+        """spherical.py:182-195: precomputed eigenvalues, zeros when absent."""
+        levels = np.asarray(levels, dtype=np.int64)
+        eigval = param.constants.get(self.name, {}).get("eigenvalues", np.zeros(len(levels)))
+        return np.asarray(eigval)[levels]
+
+    # ---- spherical.py:214-249, 384-400: evaluated on the device ----
+    def _weight_mode(self, param: Param) -> str:
+        w = param.params[self.name]["weight_variances"]
+        if np.ndim(w) == 2:
+            raise _runtime.GpfyError("linear-projection weights [d, p] are not built yet (SURVEY.md §8f); use ARD or scalar weights")
+        return "scalar" if np.ndim(w) == 0 else "ard"
+
+    def to_sphere(self, param: Param, X):
+        kp = param.params[self.name]
+        d = int(np.shape(X)[-1])
+        hp = _runtime.hot_path(d, [1], weight_mode=self._weight_mode(param), kernel_order=self.order)
+        return hp.to_sphere(X, kp["weight_variances"], kp["bias_variance"])
+
+    def K_diag(self, param: Param, X):
+        _, r = self.to_sphere(param, X)
+        return float(param.params[self.name]["variance"]) * r ** (2 * self.order)
+
+    def shape_function(self, param: Param, x):
+        raise NotImplementedError
+
+    def K(self, *a, **k):
+        raise NotImplementedError("Spherical.K (N x N prior covariance) is outside the accelerated path (SURVEY.md §2)")
+
+    K2 = K
+
+
+def _kappa(u, order: int):
+    """spherical.py:279-316 (host numpy; only used by the init-time Funk-Hecke quadrature)."""
+    if order == 0:
+        return (np.pi - np.arccos(u)) / np.pi
+    if order == 1:
+        return (u * (np.pi - np.arccos(u)) + np.sqrt(1.0 - np.square(u))) / np.pi
+    return ((1.0 + 2.0 * np.square(u)) / 3 * (np.pi - np.arccos(u)) + np.sqrt(1.0 - np.square(u))) / np.pi
+
+
+@dataclasses.dataclass(frozen=True)
+class ArcCosine(Spherical):
+    depth: int = 1
+    name: str = "ArcCosine"
+
+    def __post_init__(self):
+        if self.order not in {0, 1, 2}:
+            raise ValueError("Requested order is not implemented.")
+
+    def shape_function(self, param, x):
+        """spherical.py:438-455."""
+        y = np.clip(x, -1.0, 1.0)
+        for _ in range(self.depth):
+            y = _kappa(y, self.order)
+        return y
+
+
+@dataclasses.dataclass(frozen=True)
+class NTK(Spherical):
+    depth: int = 1
+    name: str = "NTK"
+
+    def __post_init__(self):
+        object.__setattr__(self, "order", 1)
+
+    def shape_function(self, param, x):
+        """spherical.py:479-500."""
+        x = np.clip(x, -1.0, 1.0)
+        a, y = x, x
+        for _ in range(self.depth):
+            a, y = _kappa(a, 1), y * _kappa(a, 0) + _kappa(a, 1)
+        return y / (self.depth + 1)
+
+
+@dataclasses.dataclass(frozen=True)
+class PolynomialDecay(Spherical):
+    truncation_level: int = 10
+    name: str = "PolynomialDecay"
+
+    def __post_init__(self):
+        object.__setattr__(self, "order", 1)
+
+    def _compute_eigvals(self, sphere_dim: int, *, max_num_eigvals=None, gegenbauer_lookup_table=None):
+        """spherical.py:526-561: alpha / (n + alpha) / C_n^alpha(1)."""
+        if not gegenbauer_lookup_table:
+            raise ValueError("Lookup table should be provided with `PolyDecay` kernel.")
+        alpha = (sphere_dim + 1 - 2.0) / 2.0
+        C_1 = np.array([gegenbauer_lookup_table.at_one(n) for n in range(self.truncation_level)])
+        n = np.arange(self.truncation_level, dtype=np.float64)
+        return alpha / (n + alpha) / C_1
+
+    def eigenvalues(self, param: Param, levels) -> np.ndarray:
+        """spherical.py:563-587, including the clip of `levels` to truncation_level - 1 (:586)."""
+        return self._eigenvalues_and_dbeta(param, levels)[0]
+
+    def _eigenvalues_and_dbeta(self, param: Param, levels):
+        n = np.arange(self.truncation_level, dtype=np.float64)
+        beta = float(param.params[self.name]["beta"])
+        sphere_dim = param.constants["sphere"]["sphere_dim"]
+        geg = param.constants["sphere"]["gegenbauer_lookup_table"]
+        decay = (1 + n) ** (-beta)
+        cf = self._compute_eigvals(sphere_dim, gegenbauer_lookup_table=geg)
+        S = np.sum(decay)
+        eig = decay * cf / S
+        ddecay = -np.log1p(n) * decay
+        deig = ddecay * cf / S - decay * cf * np.sum(ddecay) / S**2
+        lv = np.clip(np.asarray(levels, dtype=np.int64), 0, self.truncation_level - 1)
+        return eig[lv], deig[lv]
+
+    def shape_function(self, param, x):
+        raise NotImplementedError("PolynomialDecay.shape_function only serves the N x N covariance (out of scope)")

@@ -141,6 +141,22 @@ GPFY_API int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, co
                       const double* lcat, const double* mu, const double* sigma, double* fmu, double* fvar,
                       void* workspace, size_t workspace_bytes);
 
+/* to_sphere (replaces spherical.py:214-249 `_scale_X` + `to_sphere`): xs [N, dim] unit vectors, r [N] radii. */
+GPFY_API int gpfy_to_sphere(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* w, const double* b,
+                   double* xs, double* r);
+
+/* Expected log-likelihood per point (replaces likelihoods.py:188-220 `Gaussian.variational_expectations`
+ * and :254-278 `Bernoulli.variational_expectations` with quadrature.py:30-53): out [N] = sum over the P
+ * outputs; fmu, fvar, Y are [N, P]; sigma2 [1] is read for the Gaussian only. */
+GPFY_API int gpfy_variational_expectations(void* stream, const GpfyDesc* desc, int64_t n, const double* fmu, const double* fvar,
+                                  const double* Y, const double* sigma2, double* out);
+
+/* q-projections of a given projection matrix A [M, N] (replaces variational.py:288-305 `project_mean`,
+ * :307-328 / :420-441 `project_diag_variance`): mean [N, P] = A^T mu, var [N, P] = diag(A^T S A) with
+ * S = L L^T (TriL) or Sigma (full covariance).  Uses GPFY_OP_PREDICT scratch. */
+GPFY_API int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* A, const double* mu,
+                   const double* sigma, double* mean, double* var, void* workspace, size_t workspace_bytes);
+
 /* Sum of the packed buffers of all ranks, in place, on `stream` (the single exchange step).
  * `nccl_comm` is an ncclComm_t owned by the caller; NCCL is resolved at run time from the process
  * (the host framework's copy), so this library has no link-time NCCL dependency. */
