@@ -52,9 +52,15 @@ _SIGNATURES = {
                                             _P, ctypes.c_int, _P, _P, _P, ctypes.c_size_t]),
     "gpfy_svgp_elbo_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 12 +
                                [_P, ctypes.c_size_t]),
+    "gpfy_svgp_elbo_begin": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 8 + [_P, ctypes.c_size_t]),
+    "gpfy_svgp_elbo_rows": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, ctypes.c_int64] + [_P] * 4 +
+                            [_P, ctypes.c_size_t]),
+    "gpfy_svgp_elbo_finish": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 6 + [_P, ctypes.c_size_t]),
     "gpfy_prior_kl_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, _P]),
     "gpfy_predict_diag": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 11 + [_P, ctypes.c_size_t]),
     "gpfy_allreduce_packed": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),
+    "gpfy_debug_kernel_timing": (ctypes.c_int, [ctypes.c_int]),
+    "gpfy_debug_kernel_time": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "gpfy_to_sphere": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),
     "gpfy_variational_expectations": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),
     "gpfy_project_q": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P, _P, ctypes.c_size_t]),

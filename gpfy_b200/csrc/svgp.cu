@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "gemm.cuh"
 #include "svgp_kernels.cuh"
@@ -14,6 +15,36 @@ namespace gpfy {
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 unsigned long long g_launch_count = 0;
+
+// Optional per-kernel device timing (bench.py's roofline line): when enabled, the per-chunk kernels
+// of the ELBO step are bracketed by cudaEvents on the launching stream; gpfy_debug_kernel_time
+// synchronises those events and returns the summed durations.  Off by default: zero cost.
+enum { TK_ZONAL_FWD = 0, TK_GEMM = 1, TK_LIK = 2, TK_ZONAL_BWD = 3, TK_SYRK = 4, TK_DVHAT = 5, TK_COUNT = 6 };
+struct KernelTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[TK_COUNT];   // pairs (start, stop)
+  size_t used[TK_COUNT] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t get(int k) {
+    if (used[k] == ev[k].size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev[k].push_back(e);
+    }
+    return ev[k][used[k]++];
+  }
+};
+static KernelTimer g_timer;
+struct ScopedKernelTime {
+  int k;
+  cudaStream_t st;
+  ScopedKernelTime(int k_, cudaStream_t st_) : k(k_), st(st_) {
+    if (g_timer.on) cudaEventRecord(g_timer.get(k), st);
+  }
+  ~ScopedKernelTime() {
+    if (g_timer.on) cudaEventRecord(g_timer.get(k), st);
+  }
+};
+#define GPFY_TIMED(k, st) ScopedKernelTime timed__(k, st)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -562,6 +593,29 @@ int gpfy_abi_version(void) { return GPFY_ABI_VERSION; }
 const char* gpfy_last_error_string(void) { return g_err; }
 GPFY_API unsigned long long gpfy_debug_launch_count(void) { return g_launch_count; }
 
+GPFY_API int gpfy_debug_kernel_timing(int enable) {
+  g_timer.on = enable != 0;
+  for (int k = 0; k < TK_COUNT; ++k) g_timer.used[k] = 0;
+  return GPFY_OK;
+}
+
+// Sum of the recorded durations of kernel class `which` (TK_*), in milliseconds, and the number of
+// launches.  Synchronises on the recorded events (a debug call, not part of the stream-ordered ABI).
+GPFY_API int gpfy_debug_kernel_time(int which, double* ms, int64_t* launches) {
+  if (which < 0 || which >= TK_COUNT || !ms || !launches) { set_error("bad argument"); return GPFY_EINVAL; }
+  double total = 0.0;
+  const size_t n = g_timer.used[which] / 2;
+  for (size_t i = 0; i < n; ++i) {
+    float t = 0.f;
+    GPFY_CUDA_OK(cudaEventSynchronize(g_timer.ev[which][2 * i + 1]));
+    GPFY_CUDA_OK(cudaEventElapsedTime(&t, g_timer.ev[which][2 * i], g_timer.ev[which][2 * i + 1]));
+    total += t;
+  }
+  *ms = total;
+  *launches = (int64_t)n;
+  return GPFY_OK;
+}
+
 int64_t gpfy_num_inducing(const GpfyDesc* desc) {
   Shape s;
   int rc = make_shape(desc, &s);
@@ -643,35 +697,46 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   return GPFY_OK;
 }
 
-int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* Y, const double* w,
-                           const double* b, const double* variance, const double* eig, const double* vhat, const double* lcat,
-                           const double* mu, const double* sigma, const double* sigma2, double* packed, void* workspace,
-                           size_t workspace_bytes) {
+// ---- the ELBO step in three stream-ordered stages sharing one workspace ----------------------------
+// begin : parameter prologue (folded matrices) + zeroed accumulators
+// rows  : any number of calls, each adds the terms of `n` rows of (X, Y) to the accumulators
+// finish: reduces the accumulators and applies the chain rules back to the reference's parameters
+static int elbo_plan(const GpfyDesc* desc, int64_t n_capacity, void* workspace, size_t workspace_bytes, Shape* s, Plan* p) {
+  GPFY_TRY(make_shape(desc, s));
+  if (n_capacity < 0) { set_error("n_capacity < 0"); return GPFY_EINVAL; }
+  make_plan(*s, n_capacity, GPFY_OP_ELBO, p);
+  return check_ws(*p, workspace, workspace_bytes);
+}
+
+int gpfy_svgp_elbo_begin(void* stream, const GpfyDesc* desc, int64_t n_capacity, const double* w, const double* b,
+                         const double* variance, const double* eig, const double* vhat, const double* lcat, const double* mu,
+                         const double* sigma, void* workspace, size_t workspace_bytes) {
   cudaStream_t st = (cudaStream_t)stream;
   Shape s;
-  GPFY_TRY(make_shape(desc, &s));
   Plan p;
-  make_plan(s, n, GPFY_OP_ELBO, &p);
-  GPFY_TRY(check_ws(p, workspace, workspace_bytes));
-  GpfyElboLayout lay;
-  GPFY_TRY(gpfy_elbo_packed_layout(desc, &lay));
+  GPFY_TRY(elbo_plan(desc, n_capacity, workspace, workspace_bytes, &s, &p));
+  double* ws = (double*)workspace;
+  GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
+  // pad rows of Z are never written by the zonal kernel; accumulators start at zero
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp + 32 - s.M) * p.nc * 8, st));
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, (size_t)(p.o_Z - p.o_partials) * 8, st));  // partials, Gpart, bzpart, dVpart
+  return GPFY_OK;
+}
+
+int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, int64_t n, const double* X, const double* Y,
+                        const double* variance, const double* sigma2, void* workspace, size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  Plan p;
+  GPFY_TRY(elbo_plan(desc, n_capacity, workspace, workspace_bytes, &s, &p));
+  if (n < 0) { set_error("n < 0"); return GPFY_EINVAL; }
   double* ws = (double*)workspace;
   const int Mp = s.Mp;
   const int64_t Mp2 = (int64_t)Mp * Mp;
   DegreeTable deg = degree_table(desc);
   RecCoef rc = make_rec_coef(desc->alpha);
 
-  GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
-  // zero the pad rows of Z once (never written by the zonal kernel) and the accumulators' first use is
-  // handled by accumulate = 0 on the first chunk
-  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
-  if (n == 0) {
-    GPFY_CUDA_OK(cudaMemsetAsync(packed, 0, lay.total * 8, st));
-    return GPFY_OK;
-  }
-
-  int chunk = 0;
-  for (int64_t c0 = 0; c0 < n; c0 += p.nc, ++chunk) {
+  for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
@@ -680,9 +745,13 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
     za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
-    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+    {
+      GPFY_TIMED(TK_ZONAL_FWD, st);
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+    }
 
     for (int q = 0; q < s.P; ++q) {  // C_q = W2_q Z
+      GPFY_TIMED(TK_GEMM, st);
       GemmArgs g;
       g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
       g.B = ws + p.o_Z; g.ldb = p.nc;
@@ -692,26 +761,31 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
-    if (chunk == 0 && ((npts_e + 31) / 32) < p.nblocks_c)  // single short chunk: clear unused slots
-      GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, p.nblocks_c * p.npart * 8, st));
     LikPointArgs lp;
     lp.psi_part = ws + p.o_psi; lp.npsi = p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
     lp.R = ws + p.o_R; lp.Y = Y + c0 * s.P; lp.vptr = variance; lp.s2ptr = sigma2;
     lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
     lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
-    lp.partials = ws + p.o_partials; lp.npart = p.npart; lp.accumulate = chunk > 0;
-    GPFY_K(lik_point_kernel, (unsigned)((npts_e + 255) / 256), 256, 0, st, lp);
+    lp.partials = ws + p.o_partials; lp.npart = p.npart; lp.accumulate = 1;
+    {
+      GPFY_TIMED(TK_LIK, st);
+      GPFY_K(lik_point_kernel, (unsigned)((npts_e + 255) / 256), 256, 0, st, lp);
+    }
 
     ZonalBwdArgs zb;
     zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
     zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
     zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p;
     zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.P = s.P; zb.npts = npts;
-    zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.accumulate = chunk > 0;
+    zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.accumulate = 1;
     zb.deg = deg; zb.rc = rc;
-    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd<DIMP>(st, zb)));
+    {
+      GPFY_TIMED(TK_ZONAL_BWD, st);
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd<DIMP>(st, zb)));
+    }
 
     for (int q = 0; q < s.P; ++q) {
+      GPFY_TIMED(TK_SYRK, st);
       SyrkArgs sa;
       sa.Z = ws + p.o_Z; sa.ldz = p.nc; sa.Mp = Mp; sa.npts = npts;
       sa.wq = ws + p.o_wq + (int64_t)q * p.nc; sa.wp = ws + p.o_wp + (int64_t)q * p.nc;
@@ -719,7 +793,7 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
       sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.KS * p.nb * SYRK_B;
       sa.nb = p.nb; sa.nblk = p.nblk; sa.KS = p.KS;
       sa.range = round_up64((p.nc + p.KS - 1) / p.KS, SYRK_BK);
-      sa.accumulate = chunk > 0;
+      sa.accumulate = 1;
       static bool cfg = false;
       if (!cfg) { GPFY_TRY(set_smem(syrk_dmma_kernel, SYRK_SMEM)); cfg = true; }
       GPFY_K(syrk_dmma_kernel, p.nblk * p.KS, SYRK_THREADS, SYRK_SMEM, st, sa);
@@ -728,11 +802,29 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
     DvhatArgs da;
     da.dT = ws + p.o_dT; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
     da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
-    da.accumulate = chunk > 0;
-    GPFY_TRY(launch_dvhat(st, da));
+    da.accumulate = 1;
+    {
+      GPFY_TIMED(TK_DVHAT, st);
+      GPFY_TRY(launch_dvhat(st, da));
+    }
   }
+  return GPFY_OK;
+}
 
-  // ---- epilogue: gradients of the folded matrices back to the reference's parameters ----
+int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity, const double* w, const double* b,
+                          const double* variance, const double* eig, const double* mu, double* packed, void* workspace,
+                          size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  Plan p;
+  GPFY_TRY(elbo_plan(desc, n_capacity, workspace, workspace_bytes, &s, &p));
+  GpfyElboLayout lay;
+  GPFY_TRY(gpfy_elbo_packed_layout(desc, &lay));
+  double* ws = (double*)workspace;
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  DegreeTable deg = degree_table(desc);
+  // ---- gradients of the folded matrices back to the reference's parameters ----
   const unsigned sqg = (unsigned)((Mp2 + 255) / 256);
   for (int q = 0; q < s.P; ++q) {
     double* Gz = ws + p.o_Gz;
@@ -764,6 +856,21 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
   fa.M = s.M; fa.d = s.d; fa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; fa.deg = deg; fa.packed = packed; fa.lay = lay;
   GPFY_K(finalize_kernel, 1, 256, 0, st, fa);
   return GPFY_OK;
+}
+
+int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const double* X, const double* Y, const double* w,
+                           const double* b, const double* variance, const double* eig, const double* vhat, const double* lcat,
+                           const double* mu, const double* sigma, const double* sigma2, double* packed, void* workspace,
+                           size_t workspace_bytes) {
+  if (n == 0) {  // empty shard: all sums are zero
+    GpfyElboLayout lay;
+    GPFY_TRY(gpfy_elbo_packed_layout(desc, &lay));
+    GPFY_CUDA_OK(cudaMemsetAsync(packed, 0, lay.total * 8, (cudaStream_t)stream));
+    return GPFY_OK;
+  }
+  GPFY_TRY(gpfy_svgp_elbo_begin(stream, desc, n, w, b, variance, eig, vhat, lcat, mu, sigma, workspace, workspace_bytes));
+  GPFY_TRY(gpfy_svgp_elbo_rows(stream, desc, n, n, X, Y, variance, sigma2, workspace, workspace_bytes));
+  return gpfy_svgp_elbo_finish(stream, desc, n, w, b, variance, eig, mu, packed, workspace, workspace_bytes);
 }
 
 int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out) {

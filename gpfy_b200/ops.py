@@ -114,6 +114,71 @@ class HotPath:
             _ptr(out), _ptr(ws), ws.numel()))
         return out
 
+    # ---- host-resident data: rows are streamed through the device slab by slab ----
+    def slab_rows(self, n):
+        """Rows per streamed slab: a whole number of the kernels' point chunks (about 1.1 M rows)."""
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        chunk = 192 * sms * 4
+        return max(1, min(int(n), 10 * chunk))
+
+    def elbo_valgrad_host(self, X_host, Y_host, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out_host=None, reduce=None):
+        """Same as `elbo_valgrad_packed` for X [N, d], Y [N, P] in (pinned) HOST memory: slabs of rows are
+        copied on a side stream while the previous slab is being processed (gpfy_svgp_elbo_begin / rows /
+        finish), `reduce` (the ranks' all-reduce, stream-ordered) is applied to the packed buffer on the
+        device, and the result is read back into `out_host` (pinned).  Returns out_host after the device
+        has finished."""
+        if not (torch.is_tensor(X_host) and torch.is_tensor(Y_host)) or X_host.is_cuda or Y_host.is_cuda:
+            raise _lib.GpfyError("elbo_valgrad_host expects CPU torch tensors (pin them for full copy bandwidth)")
+        X_host = X_host.contiguous()
+        Y_host = Y_host.reshape(X_host.shape[0], self.P).contiguous()
+        n = X_host.shape[0]
+        args = [self._dev(a) for a in (w, b, variance, eig, vhat, lcat, mu, sigma)]
+        s2 = self._dev(sigma2 if sigma2 is not None else 1.0)
+        if out_host is None:
+            out_host = torch.empty((self.layout.total,), dtype=torch.float64).pin_memory()
+        cap = self.slab_rows(n)
+        ws = self.workspace(cap, _lib.OP_ELBO)
+        st = self._stream_state(cap)
+        dptr = ctypes.byref(self.desc)
+        main = torch.cuda.current_stream(self.device)
+        wv, bv, vv, ev, vh, lc, muv, sg = args
+        _lib.check(self.lib.gpfy_svgp_elbo_begin(_stream(self.device), dptr, cap, _ptr(wv), _ptr(bv), _ptr(vv), _ptr(ev), _ptr(vh),
+                                                 _ptr(lc), _ptr(muv), _ptr(sg), _ptr(ws), ws.numel()))
+        k = 0
+        for lo in range(0, n, cap):
+            hi = min(n, lo + cap)
+            xb, yb = st["X"][k % 2], st["Y"][k % 2]
+            with torch.cuda.stream(st["copy"]):
+                st["copy"].wait_event(st["free"][k % 2])      # slab buffer no longer read by the compute stream
+                xb[:hi - lo].copy_(X_host[lo:hi], non_blocking=True)
+                yb[:hi - lo].copy_(Y_host[lo:hi], non_blocking=True)
+                st["ready"][k % 2].record(st["copy"])
+            main.wait_event(st["ready"][k % 2])
+            _lib.check(self.lib.gpfy_svgp_elbo_rows(_stream(self.device), dptr, cap, hi - lo, _ptr(xb), _ptr(yb), _ptr(vv), _ptr(s2),
+                                                    _ptr(ws), ws.numel()))
+            st["free"][k % 2].record(main)
+            k += 1
+        out = st["packed"]
+        _lib.check(self.lib.gpfy_svgp_elbo_finish(_stream(self.device), dptr, cap, _ptr(wv), _ptr(bv), _ptr(vv), _ptr(ev), _ptr(muv),
+                                                  _ptr(out), _ptr(ws), ws.numel()))
+        if reduce is not None:
+            reduce(out)
+        out_host.copy_(out, non_blocking=True)
+        main.synchronize()
+        return out_host
+
+    def _stream_state(self, cap):
+        st = getattr(self, "_hs", None)
+        if st is None or st["cap"] < cap:
+            mk = lambda c: [torch.empty((cap, c), dtype=torch.float64, device=self.device) for _ in range(2)]
+            st = {"cap": cap, "X": mk(self.input_dim), "Y": mk(self.P), "copy": torch.cuda.Stream(self.device),
+                  "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+                  "packed": torch.empty((self.layout.total,), dtype=torch.float64, device=self.device)}
+            for e in st["free"]:
+                e.record(torch.cuda.current_stream(self.device))
+            self._hs = st
+        return st
+
     def unpack(self, packed):
         """Views of a packed buffer keyed like the oracle's gradient dict."""
         L = self.layout
@@ -188,3 +253,22 @@ class HotPath:
 
 def launch_count():
     return int(_lib.load().gpfy_debug_launch_count())
+
+
+KERNEL_CLASSES = ("zonal_fwd", "gemm_dmma", "lik_point", "zonal_bwd", "syrk_dmma", "dvhat_dmma")
+
+
+def kernel_timing(enable):
+    """Bracket the per-chunk kernels of the ELBO step with CUDA events on the launching stream."""
+    _lib.check(_lib.load().gpfy_debug_kernel_timing(int(bool(enable))))
+
+
+def kernel_times():
+    """{kernel class: (total ms, launches)} since kernel_timing(True); waits for the recorded events."""
+    lib = _lib.load()
+    out = {}
+    for i, name in enumerate(KERNEL_CLASSES):
+        ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+        _lib.check(lib.gpfy_debug_kernel_time(i, ctypes.byref(ms), ctypes.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out

@@ -61,15 +61,14 @@ def synthetic_basis(d, F, T, rng):
     return V, L, m
 
 
-def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, device="cuda", rank=0, world=1):
-    """BASELINE.json configs[2]: full SVGP ELBO+gradient step, d=8, degrees 0..10, phase truncation T.
-    Rank `rank` of `world` owns rows [rank*N/world, (rank+1)*N/world) of the same global dataset."""
+def headline_params(d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2):
+    """Host-side (numpy) parameter point of BASELINE.json configs[2]: basis, PolynomialDecay eigenvalues at
+    beta = 1 with the default truncation_level = 10 clip (spherical.py:563-587), q = N(mu, L L^T)."""
     rng = np.random.default_rng(seed)
     V, L, m = synthetic_basis(d, F, T, rng)
     M = sum(m)
     dim = d + 1
     alpha = (dim - 2.0) / 2.0
-    # PolynomialDecay eigenvalues at beta = 1 with the default truncation_level = 10 clip (spherical.py:563-587)
     tl = 10
     n = np.arange(tl, dtype=np.float64)
     c1 = np.array([_gegenbauer_np(k, alpha, np.array(1.0)) for k in range(tl)])
@@ -78,8 +77,30 @@ def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, dev
     eig = eigv[np.clip(np.arange(F), 0, tl - 1)]
     mu = 0.1 * rng.standard_normal((M, P))
     Lq = np.stack([np.tril(np.eye(M) + 0.01 * rng.standard_normal((M, M))) for _ in range(P)])
-    w = np.ones(d); b = np.array(1.0); v = np.array(1.0); s2 = np.array(0.1)
-    lo, hi = rank * N // world, (rank + 1) * N // world
+    host = dict(w=np.ones(d), b=np.array(1.0), v=np.array(1.0), eig=eig, V=V, L=L, mu=mu, Lq=Lq, sigma2=np.array(0.1),
+                alpha=alpha, order=1, dim=dim, lik=likelihood)
+    return host, m
+
+
+def headline_host_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2):
+    """CPU-only variant (numpy rows) for the reference arm of bench.py: (host params, X, Y, m)."""
+    host, m = headline_params(d, F, T, P, likelihood, seed)
+    rng = np.random.default_rng(seed + 1000)
+    X = rng.standard_normal((N, d))
+    f = np.sin(X).sum(1, keepdims=True) / math.sqrt(d)
+    Y = np.concatenate([f * (j + 1) for j in range(P)], 1) + 0.1 * rng.standard_normal((N, P))
+    if likelihood == "bernoulli":
+        Y = (Y > 0).astype(np.float64)
+    return host, X, Y, m
+
+
+def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, device="cuda", rank=0, world=1):
+    """BASELINE.json configs[2]: full SVGP ELBO+gradient step, d=8, degrees 0..10, phase truncation T.
+    Rank `rank` of `world` owns a contiguous block of N/world rows of the global data set, generated on the device."""
+    from .distributed import shard_bounds
+    host, m = headline_params(d, F, T, P, likelihood, seed)
+    M, dim = sum(m), d + 1
+    lo, hi = shard_bounds(N, rank, world)
     g = torch.Generator(device=device)
     g.manual_seed(1234 + 7919 * rank)
     X = torch.randn((hi - lo, d), dtype=torch.float64, device=device, generator=g)
@@ -88,13 +109,13 @@ def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, dev
     if likelihood == "bernoulli":
         Y = (Y > 0).to(torch.float64)
     hp = HotPath(d, m, num_outputs=P, kernel_order=1, likelihood=likelihood, q_kind="tril", weight_mode="ard", device=device)
-    vhat = np.concatenate(V, 0)
-    lcat = np.concatenate([l.ravel() for l in L])
+    vhat = np.concatenate(host["V"], 0)
+    lcat = np.concatenate([l.ravel() for l in host["L"]])
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
-    args = (X, Y, dev(w), dev(b), dev(v), dev(eig), dev(vhat), dev(lcat), dev(mu), dev(Lq), dev(s2))
+    args = (X, Y, dev(host["w"]), dev(host["b"]), dev(host["v"]), dev(host["eig"]), dev(vhat), dev(lcat), dev(host["mu"]),
+            dev(host["Lq"]), dev(host["sigma2"]))
     return {
-        "hot": hp, "args": args, "m": m, "M": M, "dim": dim,
-        "host": dict(w=w, b=b, v=v, eig=eig, V=V, L=L, mu=mu, Lq=Lq, sigma2=s2, alpha=alpha, order=1, dim=dim, lik=likelihood),
+        "hot": hp, "args": args, "m": m, "M": M, "dim": dim, "host": host,
         "alg_flops_per_point": algorithmic_flops_per_point(dim, m, True),
         "alg_bytes_per_point": 8 * (d + P),
     }

@@ -129,6 +129,23 @@ GPFY_API int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t 
                            const double* vhat, const double* lcat, const double* mu, const double* sigma,
                            const double* sigma2, double* packed, void* workspace, size_t workspace_bytes);
 
+/* The same step in three stages that share one workspace, for inputs that arrive slab by slab (host-
+ * resident data streamed through the device, minibatches: optimization.py:84-104).  `n_capacity` is
+ * the row count the workspace was sized for with gpfy_workspace_bytes(.., GPFY_OP_ELBO, ..) and must
+ * be the same in all three calls; every `rows` call may pass any n >= 0.
+ *   begin : parameter prologue, zeroed accumulators
+ *   rows  : adds the terms of n rows of (X, Y)
+ *   finish: writes `packed` (sums over all rows added since `begin`) */
+GPFY_API int gpfy_svgp_elbo_begin(void* stream, const GpfyDesc* desc, int64_t n_capacity, const double* w, const double* b,
+                         const double* variance, const double* eig, const double* vhat, const double* lcat,
+                         const double* mu, const double* sigma, void* workspace, size_t workspace_bytes);
+GPFY_API int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, int64_t n, const double* X,
+                        const double* Y, const double* variance, const double* sigma2, void* workspace,
+                        size_t workspace_bytes);
+GPFY_API int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity, const double* w, const double* b,
+                          const double* variance, const double* eig, const double* mu, double* packed, void* workspace,
+                          size_t workspace_bytes);
+
 /* KL(q || N(0, I)) and its gradients (replaces variational.py:225-240 with :262-286 / :375-399).
  * out: [1 + M*P + P*M*M] = KL, dKL/dmu, dKL/dSigma.  TriL only reads diag/all of L; full covariance
  * needs a Cholesky of Sigma and is left to the host framework (returns GPFY_EUNSUPPORTED). */

@@ -1,0 +1,154 @@
+"""GPU parity of the remaining C-ABI entry points: to_sphere, variational_expectations, project_q against
+the reference goldens; the begin/rows/finish stages and the host-streamed path against the one-shot call;
+full-size invariants at BASELINE.json's shapes (SURVEY.md §8c ii)."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpfy_oracle as O
+from tests.golden_util import CASES, golden_pack, load, rel_err
+from tests.test_gpu_parity import ARD_CASES, _cat, _hot, _resolved
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.mark.parametrize("name", ARD_CASES)
+def test_to_sphere_matches_reference_golden(name):
+    g, pack = _resolved(name)
+    hp = _hot(pack, g)
+    xs, r = hp.to_sphere(g["X"], pack["w"], pack["b"])
+    assert rel_err(xs.cpu().numpy(), g["o_x_sphere"]) < 1e-14
+    assert rel_err(r.cpu().numpy(), g["o_r"]) < 1e-14
+    # tests/test_spherical.py:103-120 invariants: unit norm, |scaled|^2 = r^2 - b
+    assert float((xs.norm(dim=1) - 1).abs().max()) < 1e-14
+
+
+@pytest.mark.parametrize("name", ARD_CASES)
+def test_variational_expectations_match_reference_golden(name):
+    g, pack = _resolved(name)
+    hp = _hot(pack, g)
+    ve = hp.variational_expectations(g["o_fmu"], g["o_fvar"], g["Y"], pack.get("sigma2"))
+    assert rel_err(ve.cpu().numpy(), g["o_var_exp"]) < TOL
+    # tests/test_likelihoods.py:32-46: var_exp(f, 0) == log_prob(f)
+    f = torch.as_tensor(g["o_fmu"])
+    y = torch.as_tensor(g["Y"])
+    ve0 = hp.variational_expectations(g["o_fmu"], np.zeros_like(g["o_fvar"]), g["Y"], pack.get("sigma2")).cpu()
+    if pack["lik"] == "gaussian":
+        lp = O.gaussian_var_exp(O.T(pack["sigma2"]), f, torch.zeros_like(f), y)
+    else:
+        lp = O.bernoulli_log_prob(f, y)
+    assert rel_err(ve0.numpy(), lp.numpy()) < TOL
+
+
+@pytest.mark.parametrize("name", ARD_CASES)
+def test_project_q_matches_reference_golden(name):
+    g, pack = _resolved(name)
+    hp = _hot(pack, g)
+    sigma = pack.get("Lq", pack.get("Sigma"))
+    mean, var = hp.project_q(g["o_proj"], pack["mu"], sigma)
+    assert rel_err(mean.cpu().numpy(), g["o_project_mean"]) < TOL
+    assert rel_err(var.cpu().numpy(), g["o_project_diag_variance"]) < TOL
+
+
+def _problem(N, T=30, P=1, lik="gaussian"):
+    from gpfy_b200.synthetic import headline_problem
+    return headline_problem(N, T=T, P=P, likelihood=lik, device="cuda")
+
+
+@pytest.mark.parametrize("N", [1, 31, 1000, 150_001])
+def test_stages_and_host_stream_equal_one_shot(N):
+    """begin / rows (ragged slabs, empty slab) / finish == one call; the pinned-host streamed path too."""
+    from gpfy_b200 import _lib
+    from gpfy_b200.ops import _ptr, _stream
+    prob = _problem(N)
+    hp, args = prob["hot"], prob["args"]
+    ref = hp.elbo_valgrad_packed(*args).clone()
+    X, Y, w, b, v, eig, vh, lc, mu, sg, s2 = args
+    cap = max(1, (N + 2) // 3)
+    ws = hp.workspace(cap, _lib.OP_ELBO)
+    d = ctypes.byref(hp.desc)
+    out = torch.empty_like(ref)
+    st = _stream(hp.device)
+    _lib.check(hp.lib.gpfy_svgp_elbo_begin(st, d, cap, _ptr(w), _ptr(b), _ptr(v), _ptr(eig), _ptr(vh), _ptr(lc), _ptr(mu), _ptr(sg),
+                                           _ptr(ws), ws.numel()))
+    bounds = [0, min(N, cap // 2), min(N, cap // 2), min(N, cap // 2 + cap)]
+    while bounds[-1] < N:
+        bounds.append(min(N, bounds[-1] + cap))
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        xs, ys = X[lo:hi].contiguous(), Y[lo:hi].contiguous()
+        _lib.check(hp.lib.gpfy_svgp_elbo_rows(st, d, cap, hi - lo, _ptr(xs), _ptr(ys), _ptr(v), _ptr(s2), _ptr(ws), ws.numel()))
+    _lib.check(hp.lib.gpfy_svgp_elbo_finish(st, d, cap, _ptr(w), _ptr(b), _ptr(v), _ptr(eig), _ptr(mu), _ptr(out), _ptr(ws), ws.numel()))
+    torch.cuda.synchronize()
+    a, r = hp.unpack(out), hp.unpack(ref)
+    for k in r:
+        assert rel_err(a[k].cpu().numpy(), r[k].cpu().numpy()) < 1e-11, k
+    host = hp.elbo_valgrad_host(X.cpu().pin_memory(), Y.cpu().pin_memory(), *args[2:])
+    h = hp.unpack(host)
+    for k in r:
+        assert rel_err(h[k].numpy(), r[k].cpu().numpy()) < 1e-11, k
+
+
+def test_empty_input_gives_zero_sums():
+    prob = _problem(64)
+    hp, args = prob["hot"], prob["args"]
+    out = hp.elbo_valgrad_packed(args[0][:0], args[1][:0], *args[2:])
+    assert float(out.abs().max()) == 0.0
+
+
+def test_full_size_invariant_at_init_and_determinism():
+    """with mu = 0, L_q = I the data term is sum_n[-1/2 log 2 pi s2 - (y^2 + v r^2)/(2 s2)],
+    independent of Phi — checked at N = 1 M rows of the headline shape; and two runs are bit-identical."""
+    N = 1_000_000
+    prob = _problem(N)
+    hp, args = prob["hot"], list(prob["args"])
+    M = hp.M
+    args[8] = torch.zeros((M, 1), dtype=torch.float64, device="cuda")
+    args[9] = torch.eye(M, dtype=torch.float64, device="cuda")[None]
+    out1 = hp.elbo_valgrad_packed(*args).clone()
+    out2 = hp.elbo_valgrad_packed(*args).clone()
+    assert torch.equal(out1, out2)
+    X, Y, w, b, v, s2 = args[0], args[1], args[2], args[3], args[4], args[10]
+    r2 = (X * X * w).sum(1) + b
+    expect = (-0.5 * math.log(2 * math.pi) - 0.5 * torch.log(s2) - 0.5 * (Y[:, 0] ** 2 + v * r2) / s2).sum()
+    assert abs(float(out1[0]) - float(expect)) <= 1e-10 * abs(float(expect))
+    # d/dmu of the data term at mu = 0 is A y / s2: compare one strided subsample against the oracle
+    idx = torch.arange(0, N, 997, device="cuda")
+    sub = hp.elbo_valgrad_packed(X[idx].contiguous(), Y[idx].contiguous(), *args[2:])
+    host = prob["host"]
+    pack = {"dim": host["dim"], "alpha": host["alpha"], "V": host["V"], "L": host["L"], "w": host["w"], "b": host["b"],
+            "v": host["v"], "eig": host["eig"], "order": 1, "mu": np.zeros((M, 1)), "Lq": np.eye(M)[None],
+            "sigma2": host["sigma2"], "lik": "gaussian"}
+    oval, og = O.elbo_and_grads(pack, X[idx].cpu().numpy(), Y[idx].cpu().numpy(), data_only=True)
+    u = hp.unpack(sub)
+    assert abs(float(u["data_term"]) - oval) <= TOL * abs(oval)
+    assert rel_err(u["mu"].cpu().numpy(), og["mu"]) < TOL
+    assert rel_err(u["sigma"].cpu().numpy(), og["Lq"]) < TOL
+
+
+@pytest.mark.parametrize("T,P,lik", [(30, 1, "gaussian"), (64, 1, "gaussian"), (30, 2, "bernoulli")])
+def test_headline_shapes_match_oracle_on_a_sample(T, P, lik):
+    """BASELINE configs 2/3 (d = 8, degrees 0..10, T = 30 / 64) and a Bernoulli P = 2 variant: 3001 rows
+    (ragged: not a multiple of any tile) against the oracle, every gradient."""
+    N = 3001
+    prob = _problem(N, T=T, P=P, lik=lik)
+    hp, args, host = prob["hot"], prob["args"], prob["host"]
+    out = hp.unpack(hp.elbo_valgrad_packed(*args))
+    pack = {"dim": host["dim"], "alpha": host["alpha"], "V": host["V"], "L": host["L"], "w": host["w"], "b": host["b"],
+            "v": host["v"], "eig": host["eig"], "order": 1, "mu": host["mu"], "Lq": host["Lq"], "sigma2": host["sigma2"], "lik": lik}
+    oval, og = O.elbo_and_grads(pack, args[0].cpu().numpy(), args[1].cpu().numpy(), data_only=True)
+    assert abs(float(out["data_term"]) - oval) <= TOL * abs(oval)
+    F = len(host["V"])
+    cmp = {"mu": og["mu"], "sigma": og["Lq"], "eig": og["eig"], "w": og["w"], "b": og["b"], "v": og["v"],
+           "vhat": np.concatenate([og[f"V{i}"] for i in range(F)], 0),
+           "lcat": np.concatenate([np.tril(og[f"L{i}"]).ravel() for i in range(F)])}
+    if lik == "gaussian":
+        cmp["sigma2"] = og["sigma2"]
+    for k, ref in cmp.items():
+        assert rel_err(out[k].cpu().numpy(), ref) < TOL, k
+    fmu, fvar = hp.predict_diag(*[args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)])
+    ofmu, ofvar = O.predict_diag(O.pack_to_torch(pack), O.T(args[0].cpu().numpy()))
+    assert rel_err(fmu.cpu().numpy(), ofmu.numpy()) < TOL and rel_err(fvar.cpu().numpy(), ofvar.numpy()) < TOL
