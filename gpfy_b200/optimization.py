@@ -1,0 +1,154 @@
+"""The ELBO and its training step (mirror of gpfy/optimization.py:60-156).
+
+`elbo(param, m, q, lik, (X, Y), dataset_size=-1)` keeps the reference's signature.  The reference gets
+gradients from `jax.value_and_grad` through the whole graph; here the N-dependent value AND all its
+gradients come from ONE fused device call (`gpfy_svgp_elbo_valgrad`, sums over the local rows), are
+all-reduced once when rows are sharded over ranks, and the N-independent chain rules (lambda_l(beta),
+V -> Vhat -> chol Gram, bijectors, KL) are applied on the host — O(M^2 + sum m_l^3) numpy."""
+import numpy as np
+import torch
+from scipy.linalg import solve_triangular
+
+from . import distributed as gd
+from .gegenbauer import gegenbauer_grad_host
+from .param import Param, tree_map
+
+
+def _packed(param, m, q, lik, train_data, allreduce):
+    X, Y = train_data
+    hp, args = m.hot_args(param, lik)
+    s2 = lik._sigma2(param)
+    if torch.is_tensor(X) and not X.is_cuda and X.is_pinned():
+        Yh = Y if torch.is_tensor(Y) else torch.as_tensor(np.asarray(Y, dtype=np.float64))
+        host = hp.elbo_valgrad_host(X, Yh, *args, s2, reduce=allreduce if (allreduce and allreduce.world > 1 and allreduce.backend == "nccl") else None)
+        summed = host.numpy().copy()
+        if allreduce is not None and allreduce.world > 1 and allreduce.backend != "nccl":
+            summed = allreduce(torch.from_numpy(summed)).numpy()
+    else:
+        packed = hp.elbo_valgrad_packed(X, Y, *args, s2)
+        if allreduce is not None and allreduce.world > 1:
+            if allreduce.backend == "nccl":
+                allreduce(packed)
+                summed = packed.cpu().numpy()
+            else:
+                summed = allreduce(packed.cpu()).numpy()
+        else:
+            summed = packed.cpu().numpy()
+    return hp, summed
+
+
+def _chol_vjp(L, dL):
+    """Cotangent of B given the cotangent of L = chol(B) (lower), symmetrised like jnp.linalg.cholesky."""
+    P = np.tril(L.T @ np.tril(dL))
+    P[np.diag_indices_from(P)] *= 0.5
+    S = solve_triangular(L, solve_triangular(L, P, lower=True, trans="T").T, lower=True, trans="T").T  # L^-T P L^-1
+    return 0.5 * (S + S.T)
+
+
+def _inducing_chain(sh, param, dvhat, dlcat):
+    """d/dV_l from (dVhat_l, dL_l): V -> V / |V| -> c_l C_l(Vhat Vhat^T) + 1e-16 I -> chol
+    (spherical_harmonics.py:209-217, 265-288; gegenbauer.py:73-81).  Fixed bases: dV = dVhat."""
+    raw = [v for _, v in sorted(param.params["variational"]["inducing_features"].items())]
+    names = sorted(param.params["variational"]["inducing_features"])
+    alpha = param.constants["sphere"]["alpha"]
+    learned = sh._learned(param)
+    out, o, lo = {}, 0, 0
+    Ls = sh.Ls(param) if learned else None
+    for n, (name, V) in enumerate(zip(names, raw)):
+        ml = V.shape[0]
+        dVh = dvhat[o:o + ml]
+        if learned:
+            nrm = np.sqrt(np.sum(np.square(V), axis=1, keepdims=True))
+            Vh = V / nrm
+            dL = dlcat[lo:lo + ml * ml].reshape(ml, ml)
+            dB = _chol_vjp(Ls[n], dL)
+            G = Vh @ Vh.T
+            dG = dB * (alpha / (alpha + float(n))) * gegenbauer_grad_host(n, alpha, G)
+            dVh = dVh + (dG + dG.T) @ Vh
+            out[name] = (dVh - Vh * np.sum(Vh * dVh, axis=1, keepdims=True)) / nrm
+        else:
+            out[name] = dVh.copy()
+        o += ml
+        lo += ml * ml
+    return out
+
+
+def elbo_value_and_grad(param: Param, m, q, lik, train_data, dataset_size: int = -1, allreduce=None, n_total=None):
+    """(ELBO, gradient w.r.t. every leaf of the CONSTRAINED `param.params`, same nested structure).
+
+    `train_data` are this rank's rows; with rows sharded over ranks pass `allreduce`
+    (distributed.PackedAllReduce) and the global row count `n_total`."""
+    if not param._constrained:
+        raise ValueError("elbo expects constrained parameters (call param.constrained())")
+    hp, summed = _packed(param, m, q, lik, train_data, allreduce)
+    n_local = int(np.shape(train_data[0])[0])
+    n_total = int(n_total) if n_total is not None else n_local
+    kl, dkl_mu, dkl_sig = q.prior_KL_and_grad(param)
+    sl = gd.layout_slices(hp.layout, hp.M, hp.P, hp.F, hp.input_dim, hp.dim, hp.lsize, hp.scalar_w)
+    value, g = gd.finish_elbo(summed, n_total, dataset_size, kl, dkl_mu, dkl_sig, sl)
+    kernel, sh = m.kernel, m._sh
+    kp = param.params[kernel.name]
+    grads = tree_map(lambda p: np.zeros_like(p), param.params)
+    gk = grads[kernel.name]
+    gk["weight_variances"] = g["w"].reshape(np.shape(kp["weight_variances"]))
+    gk["bias_variance"] = g["b"].reshape(())
+    gk["variance"] = g["v"].reshape(())
+    if "beta" in kp:  # lambda_l(beta), spherical.py:563-587
+        gk["beta"] = np.array(np.sum(g["eig"] * kernel._eigenvalues_and_dbeta(param, sh.levels)[1]))
+    if lik._sigma2(param) is not None:
+        grads["likelihood"][lik.name]["variance"] = g["sigma2"].reshape(())
+    gv = grads["variational"]
+    gv[q.name]["mu"] = g["mu"].reshape(hp.M, hp.P)
+    gv[q.name]["Sigma"] = g["sigma"].reshape(hp.P, hp.M, hp.M)
+    gv["inducing_features"] = _inducing_chain(sh, param, g["vhat"].reshape(hp.M, hp.dim), g["lcat"])
+    return value, grads
+
+
+def elbo(param: Param, m, q, lik, train_data, dataset_size: int = -1) -> float:
+    """optimization.py:125-156: scale * mean_n(var_exp_n) - KL."""
+    return elbo_value_and_grad(param, m, q, lik, train_data, dataset_size)[0]
+
+
+def loss_and_grad_unconstrained(free_param: Param, m, q, lik, train_data, dataset_size: int = -1, allreduce=None, n_total=None):
+    """(-ELBO, d(-ELBO)/d unconstrained params): what `jax.value_and_grad(loss_fn)(state.params)` returns at
+    optimization.py:113-118; the bijector VJPs of param.py:228-258 are applied here."""
+    con = free_param.constrained()
+    value, g = elbo_value_and_grad(con, m, q, lik, train_data, dataset_size, allreduce, n_total)
+    gfree = tree_map(lambda x, gc, t: -t.forward_vjp(x, gc), free_param.params, g, free_param._bijectors)
+    return -value, gfree
+
+
+def create_training_step(model, dataset, dataset_xy_keys, q, lik, batch_size=None, allreduce=None, n_total=None, seed=0):
+    """optimization.py:60-122.  `dataset` is any mapping of column name -> array (the reference takes a
+    HuggingFace Dataset; `datasets` is a host-side container either way).  Full batch: the rows are captured
+    once; minibatch: a fresh shuffled batch every step with the `dataset_size = N` rescale (the reference
+    freezes its first batch at trace time — a quirk that is not replicated)."""
+    x_key, y_key = dataset_xy_keys
+    X_all, Y_all = dataset[x_key], dataset[y_key]
+    N = int(np.shape(X_all)[0])
+    if batch_size:
+        rng = np.random.default_rng(seed)
+        order = {"perm": rng.permutation(N), "pos": 0}
+
+        def next_batch():
+            if order["pos"] + batch_size > N:  # drop_last_batch=True, reshuffle (optimization.py:48-57)
+                order["perm"], order["pos"] = rng.permutation(N), 0
+            idx = np.sort(order["perm"][order["pos"]:order["pos"] + batch_size])
+            order["pos"] += batch_size
+            if torch.is_tensor(X_all):
+                ti = torch.as_tensor(idx, device=X_all.device)
+                return X_all[ti], Y_all[ti]
+            return X_all[idx], Y_all[idx]
+
+        def train_step(state, _=None):
+            X, Y = next_batch()
+            loss, grads = loss_and_grad_unconstrained(state.apply_fn(state.params), model, q, lik, (X, Y), dataset_size=N,
+                                                      allreduce=allreduce, n_total=None if n_total is None else batch_size * allreduce.world)
+            return state.apply_gradients(grads=grads), loss
+        return train_step
+
+    def train_step(state, _=None):
+        loss, grads = loss_and_grad_unconstrained(state.apply_fn(state.params), model, q, lik, (X_all, Y_all),
+                                                  allreduce=allreduce, n_total=n_total)
+        return state.apply_gradients(grads=grads), loss
+    return train_step

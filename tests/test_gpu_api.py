@@ -1,0 +1,140 @@
+"""The gpfy API mirror end to end on the GPU, against the outputs of the UNMODIFIED reference source
+(tests/golden/*.npz): every hot-path method of SphericalHarmonics / kernels / q / likelihoods / GP / elbo,
+gradients against the reference's finite differences and the oracle's autograd, and a short fit."""
+import numpy as np
+import pytest
+import torch
+
+from gpfy_b200 import optimization as opt
+from gpfy_b200.training import adam
+from oracle import gpfy_oracle as O
+from tests.api_util import objects_from_golden
+from tests.golden_util import CASES, golden_pack, load, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+API_CASES = [c for c in CASES if c != "d6_proj3_arccos"]
+
+
+def _np(t):
+    return t.cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+@pytest.mark.parametrize("name", API_CASES)
+def test_every_hot_path_method_matches_reference(name):
+    g = load(name)
+    o = objects_from_golden(g)
+    kernel, sh, q, lik, m, param = o["kernel"], o["sh"], o["q"], o["lik"], o["m"], o["param"]
+    X, Y = g["X"], g["Y"]
+    xs, r = kernel.to_sphere(param, X)
+    assert rel_err(_np(xs), g["o_x_sphere"]) < 1e-14 and rel_err(_np(r), g["o_r"]) < 1e-14
+    assert rel_err(_np(kernel.K_diag(param, X)), g["o_K_diag"]) < 1e-13
+    assert rel_err(_np(sh.polynomial_expansion(param, g["o_x_sphere"])), g["o_Phi"]) < TOL
+    Kuf = sh.Kuf(param, kernel, X)
+    assert tuple(Kuf.shape) == (sh.num_inducing(param), X.shape[0])     # reference tests/test_spherical_harmonics.py:113-121
+    assert rel_err(_np(Kuf), g["o_Kuf"]) < TOL
+    proj_fun, cond_mean_fun, _, cond_var_fun = m.conditional_fn
+    A = proj_fun(param, X)
+    assert rel_err(_np(A), g["o_proj"]) < TOL
+    assert rel_err(_np(q.project_mean(param, A)), g["o_project_mean"]) < TOL
+    assert rel_err(_np(q.project_diag_variance(param, A)), g["o_project_diag_variance"]) < TOL
+    fmu, fvar = m.predict_diag(param, X)
+    assert rel_err(_np(fmu), g["o_fmu"]) < TOL and rel_err(_np(fvar), g["o_fvar"]) < TOL
+    # predict_diag == (mu, var) composed from the closures (reference tests/test_model.py:160-183)
+    assert rel_err(_np(m.mu(param)(X)), g["o_fmu"]) < TOL
+    assert rel_err(_np(m.var(param)(X)), g["o_fvar"]) < 1e-9
+    ve = lik.variational_expectations(param, fmu, fvar)(Y)
+    assert rel_err(_np(ve), g["o_var_exp"]) < TOL
+    assert abs(q.prior_KL(param) - float(g["o_KL"])) <= TOL * abs(float(g["o_KL"]))
+    N = X.shape[0]
+    assert abs(opt.elbo(param, m, q, lik, (X, Y)) - float(g["o_elbo"])) <= TOL * abs(float(g["o_elbo"]))
+    assert abs(opt.elbo(param, m, q, lik, (X, Y), dataset_size=10 * N) - float(g["o_elbo_ds"])) <= TOL * abs(float(g["o_elbo_ds"]))
+
+
+@pytest.mark.parametrize("name", API_CASES)
+def test_prior_gp_and_likelihood_invariants(name):
+    from gpfy_b200.model import GP
+    g = load(name)
+    o = objects_from_golden(g)
+    prior = GP(o["kernel"])
+    mu, var = prior.predict_diag(o["param"], g["X"])     # reference tests/test_model.py:49-120
+    assert tuple(mu.shape) == (g["X"].shape[0], 1) and float(mu.abs().max()) == 0.0
+    assert rel_err(_np(var)[:, 0], g["o_K_diag"]) < 1e-13
+    f = g["o_fmu"]
+    lp = o["lik"].log_prob(o["param"], f, g["Y"])          # reference tests/test_likelihoods.py:32-46
+    ve0 = o["lik"].variational_expectations(o["param"], f, np.zeros_like(f))(g["Y"])
+    assert rel_err(_np(lp), _np(ve0)) < 1e-14
+
+
+@pytest.mark.parametrize("name", API_CASES)
+def test_gradients_match_reference_finite_differences_and_oracle(name):
+    g = load(name)
+    o = objects_from_golden(g)
+    kernel, sh, q, lik, m, param = o["kernel"], o["sh"], o["q"], o["lik"], o["m"], o["param"]
+    val, grads = opt.elbo_value_and_grad(param, m, q, lik, (g["X"], g["Y"]))
+    assert abs(val - float(g["o_elbo"])) <= TOL * abs(float(g["o_elbo"]))
+    leaves = {"mu": grads["variational"][q.name]["mu"], "Sigma": grads["variational"][q.name]["Sigma"],
+              "w": grads[kernel.name]["weight_variances"], "b": grads[kernel.name]["bias_variance"], "v": grads[kernel.name]["variance"]}
+    if "p_beta" in g:
+        leaves["beta"] = grads[kernel.name]["beta"]
+    if "p_sigma2" in g:
+        leaves["sigma2"] = grads["likelihood"][lik.name]["variance"]
+    for n in range(int(g["meta_F"])):
+        if f"fd_val_V_{n:02d}" in g:
+            leaves[f"V_{n:02d}"] = grads["variational"]["inducing_features"][f"V_{n:02d}"]
+    checked = 0
+    for lname, gr in leaves.items():   # central differences of the REFERENCE elbo along stored directions
+        fd = float(g[f"fd_val_{lname}"])
+        an = float(np.sum(gr * g[f"fd_dir_{lname}"]))
+        assert abs(an - fd) <= 2e-6 * max(abs(fd), 1.0), (lname, an, fd)
+        checked += 1
+    assert checked >= 5
+    # oracle autograd through the full chain (learned V: normalise -> Gram -> Cholesky; beta -> eigenvalues)
+    pack = golden_pack(g)
+    tp = O.pack_to_torch(pack, requires_grad=True)
+    F = int(g["meta_F"])
+    if "p_beta" in g:
+        beta = O.T(g["p_beta"]).clone().requires_grad_(True)
+        tp["eig"] = O.polydecay_eigenvalues(beta, tp["alpha"], int(g["meta_truncation_level"]), range(F))
+    oval = O.elbo(tp, O.T(g["X"]), O.T(g["Y"]))
+    ol = [tp["mu"], tp.get("Lq", tp.get("Sigma")), tp["w"], tp["b"], tp["v"]] + list(tp["V"])
+    og = torch.autograd.grad(oval, ol, allow_unused=True)
+    ours = [leaves["mu"], leaves["Sigma"], leaves["w"], leaves["b"], leaves["v"]] + \
+           [grads["variational"]["inducing_features"][f"V_{n:02d}"] for n in range(F)]
+    learned = bool(g["meta_orth_basis_is_nan"])
+    for i, (a, b) in enumerate(zip(ours, og)):
+        if b is None:
+            continue
+        if i == 1 and "Lq" in tp:
+            b = b  # dense gradient w.r.t. the constrained L (FillTriangular's VJP keeps the lower part)
+        if i >= 5 and not learned:
+            continue  # fixed bases: the packed dVhat treats L as an independent input
+        assert rel_err(a, b.numpy()) < 1e-9, i
+
+
+def test_unconstrained_loss_grad_and_fit_decreases_loss():
+    g = load("d8_F6_T12")
+    o = objects_from_golden(g)
+    kernel, sh, q, lik, m, param = o["kernel"], o["sh"], o["q"], o["lik"], o["m"], o["init_param"]
+    X, Y = g["X"], g["Y"]
+    free = param.unconstrained()
+    loss, gfree = opt.loss_and_grad_unconstrained(free, m, q, lik, (X, Y))
+    # directional finite difference in the unconstrained space (exercises every bijector VJP)
+    from gpfy_b200.param import tree_leaves, tree_map
+    rng = np.random.default_rng(1)
+    dirs = tree_map(lambda p: rng.standard_normal(np.shape(p)), free.params)
+    h = 1e-6
+    fp = opt.loss_and_grad_unconstrained(free.replace(params=tree_map(lambda p, d: p + h * d, free.params, dirs)), m, q, lik, (X, Y))[0]
+    fm = opt.loss_and_grad_unconstrained(free.replace(params=tree_map(lambda p, d: p - h * d, free.params, dirs)), m, q, lik, (X, Y))[0]
+    an = sum(float(np.sum(a * b)) for a, b in zip(tree_leaves(gfree), tree_leaves(dirs)))
+    assert abs(an - (fp - fm) / (2 * h)) <= 1e-5 * max(1.0, abs(an))
+    step = opt.create_training_step(m, {"x": X, "y": Y}, ("x", "y"), q, lik)
+    new_param, state, losses = m.fit(param, step, adam(5e-2), 30, progress_bar=False)
+    assert losses[-1] < losses[0] and np.all(np.isfinite(losses))
+    assert state.step == 30 and new_param._constrained
+    # frozen leaves (fixed fundamental systems of degrees 0, 1) did not move
+    f0 = param.params["variational"]["inducing_features"]["V_01"]
+    np.testing.assert_array_equal(new_param.params["variational"]["inducing_features"]["V_01"], f0)
+    mb = opt.create_training_step(m, {"x": X, "y": Y}, ("x", "y"), q, lik, batch_size=16)
+    _, _, l2 = m.fit(param, mb, adam(5e-2), 5, progress_bar=False)
+    assert np.all(np.isfinite(l2))
