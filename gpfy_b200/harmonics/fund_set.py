@@ -1,43 +1,44 @@
 """Loader of the precomputed fundamental systems (mirror of gpfy/harmonics/fund_set.py:22-39).
 
-The `fs_{dim}D.npz` files are DATA shipped with the gpfy package (not source); they are looked up,
-in order, in $GPFY_FUNDAMENTAL_SYSTEM_DIR, in an installed `gpfy` package, and in the reference
-checkout.  Same error behaviour as the reference: ValueError for a missing dimension or degree.
-"""
-import importlib.util
+The tables are DATA (unit vectors per dimension and degree) that the gpfy package ships; here they live
+repacked in gpfy_b200/data/fundamental_systems.npz (tools/pack_fundamental_systems.py), keys
+d{dim}_n{degree}.  $GPFY_FUNDAMENTAL_SYSTEM_DIR, if set, points at a directory of the original
+fs_{dim}D.npz files instead.  Same error behaviour as the reference: ValueError for a missing dimension
+(:31) or degree (:36)."""
 import os
 from pathlib import Path
 from typing import Callable
 
 import numpy as np
 
+_PACKED = Path(__file__).resolve().parent.parent / "data" / "fundamental_systems.npz"
+_cache = {}
 
-def _search_dirs():
+
+def _tables(dimension: int):
+    if dimension in _cache:
+        return _cache[dimension]
+    tab = None
     env = os.environ.get("GPFY_FUNDAMENTAL_SYSTEM_DIR")
-    if env:
-        yield Path(env)
-    spec = importlib.util.find_spec("gpfy")
-    if spec is not None and spec.submodule_search_locations:
-        for loc in spec.submodule_search_locations:
-            yield Path(loc) / "fundamental_system"
-    yield Path("/root/reference/src/gpfy/fundamental_system")
+    if env and (Path(env) / f"fs_{dimension}D.npz").exists():
+        with np.load(Path(env) / f"fs_{dimension}D.npz") as z:
+            tab = {int(k.split("_")[1]): z[k] for k in z.files}
+    elif _PACKED.exists():
+        with np.load(_PACKED) as z:
+            pre = f"d{dimension}_n"
+            tab = {int(k[len(pre):]): z[k] for k in z.files if k.startswith(pre)} or None
+    _cache[dimension] = tab
+    return tab
 
 
 def fundamental_set_loader(dimension: int) -> Callable[[int], np.ndarray]:
-    cache = None
-    for d in _search_dirs():
-        f = d / f"fs_{dimension}D.npz"
-        if f.exists():
-            with np.load(f) as z:
-                cache = {k: v for k, v in z.items()}
-            break
-    if cache is None:
+    tab = _tables(int(dimension))
+    if tab is None:
         raise ValueError(f"Fundamental system for dimension {dimension} has not been precomputed.")
 
     def load(degree: int) -> np.ndarray:
-        key = f"degree_{degree}"
-        if key not in cache:
-            raise ValueError()
-        return cache[key]
+        if int(degree) not in tab:
+            raise ValueError(f"Degree {degree} is not part of the precomputed fundamental system of dimension {dimension}.")
+        return tab[int(degree)]
 
     return load
