@@ -1,5 +1,6 @@
 // Host orchestration + C-ABI of the gpfy_b200 hot path.  Stream-ordered, no allocation, no sync.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -7,6 +8,7 @@
 
 #include "gemm.cuh"
 #include "svgp_kernels.cuh"
+#include "zonal_bwd2.cuh"
 
 namespace gpfy {
 
@@ -389,7 +391,7 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->nb = (s.Mp + SYRK_B - 1) / SYRK_B;
   p->nblk = p->nb * (p->nb + 1) / 2;
   p->KS = std::max(1, (2 * p->sms) / p->nblk);
-  p->KSV = std::max(1, (8 * p->sms) / (s.Mp / 32));  // about 8 warps per SM for the dVhat reduction
+  p->KSV = std::max(p->sms, (8 * p->sms) / (s.Mp / 32));  // dVhat partial slots: >= one per persistent CTA of the fused backward kernel
   p->nblocks_c = p->nc / 32;
   p->npsi = gemm_psi_slabs(s.Mp);
   p->npart = PART_DW + s.d;
@@ -516,6 +518,33 @@ static int launch_predict(cudaStream_t st, const PredictArgs& a) {
   GPFY_COUNT_LAUNCH();
   GPFY_LAUNCH_OK();
   return GPFY_OK;
+}
+
+// The fused backward kernel covers P = 1, Mp and the ambient dimension small enough for its shared-memory tile.
+static bool fused_bwd_ok(const Shape& s) {
+  return s.P == 1 && s.dimp <= 16 && zb2_smem_bytes(s.Mp, s.dimp) <= 227 * 1024 && getenv("GPFY_NO_FUSED_BWD") == nullptr;
+}
+
+template <int DIMP>
+static int launch_zonal_bwd2(cudaStream_t st, const ZonalBwd2Args& a, bool fuse_lik, int sms) {
+  if constexpr (DIMP <= 16) {
+    const int smem = zb2_smem_bytes(a.Mp, DIMP);
+    const int tiles = (int)((a.npts + 31) / 32);
+    const unsigned grid = (unsigned)std::min(tiles, sms);
+    if (fuse_lik) {
+      GPFY_TRY(set_smem(zonal_bwd2_kernel<DIMP, true>, smem));
+      zonal_bwd2_kernel<DIMP, true><<<grid, ZB2_THREADS, smem, st>>>(a);
+    } else {
+      GPFY_TRY(set_smem(zonal_bwd2_kernel<DIMP, false>, smem));
+      zonal_bwd2_kernel<DIMP, false><<<grid, ZB2_THREADS, smem, st>>>(a);
+    }
+    GPFY_COUNT_LAUNCH();
+    GPFY_LAUNCH_OK();
+    return GPFY_OK;
+  } else {
+    set_error("fused backward kernel is not built for padded dim %d", DIMP);
+    return GPFY_EUNSUPPORTED;
+  }
 }
 
 static int gemm_sq(cudaStream_t st, const double* A, const double* B, double* C, int Mp, double alpha, double beta, int sms) {
@@ -679,6 +708,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     ZonalArgs za;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
     za.X = X + c0 * (apply_to_sphere ? s.d : s.dim);
     za.xcols = apply_to_sphere ? s.d : s.dim;
     za.apply_to_sphere = apply_to_sphere;
@@ -736,15 +766,19 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
   DegreeTable deg = degree_table(desc);
   RecCoef rc = make_rec_coef(desc->alpha);
 
+  const bool fused = fused_bwd_ok(s);                                  // zonal_bwd2: dT stays on chip, dVhat fused
+  const bool fuse_lik = fused && desc->likelihood == GPFY_LIK_GAUSSIAN;  // + psi / likelihood fused (no GEMM psi epilogue)
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
     za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
+    if (fuse_lik) { za.Yg = Y + c0; za.s2g = sigma2; za.wq = ws + p.o_wq; za.wp = ws + p.o_wp; za.cq = ws + p.o_cq; }
     {
       GPFY_TIMED(TK_ZONAL_FWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
@@ -757,29 +791,38 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
-      g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
+      g.psi_out = fuse_lik ? nullptr : ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
-    LikPointArgs lp;
-    lp.psi_part = ws + p.o_psi; lp.npsi = p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
-    lp.R = ws + p.o_R; lp.Y = Y + c0 * s.P; lp.vptr = variance; lp.s2ptr = sigma2;
-    lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
-    lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
-    lp.partials = ws + p.o_partials; lp.npart = p.npart; lp.accumulate = 1;
-    {
+    if (!fuse_lik) {
+      LikPointArgs lp;
+      lp.psi_part = ws + p.o_psi; lp.npsi = p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
+      lp.R = ws + p.o_R; lp.Y = Y + c0 * s.P; lp.vptr = variance; lp.s2ptr = sigma2;
+      lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
+      lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
+      lp.partials = ws + p.o_partials; lp.npart = p.npart; lp.accumulate = 1;
       GPFY_TIMED(TK_LIK, st);
       GPFY_K(lik_point_kernel, (unsigned)((npts_e + 255) / 256), 256, 0, st, lp);
     }
 
-    ZonalBwdArgs zb;
-    zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
-    zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
-    zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p;
-    zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.P = s.P; zb.npts = npts;
-    zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.accumulate = 1;
-    zb.deg = deg; zb.rc = rc;
-    {
+    if (fused) {
+      ZonalBwd2Args zb;
+      zb.C = ws + p.o_C; zb.ldz = p.nc; zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
+      zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.mz = ws + p.o_mz; zb.Y = Y + c0; zb.vptr = variance; zb.s2ptr = sigma2;
+      zb.order = desc->kernel_order; zb.vhat_p = ws + p.o_vhat_p; zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.npts = npts;
+      zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.dVpart = ws + p.o_dVpart;
+      zb.deg = deg; zb.rc = rc; zb.alpha = desc->alpha;
+      GPFY_TIMED(TK_ZONAL_BWD, st);
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd2<DIMP>(st, zb, fuse_lik, p.sms)));
+    } else {
+      ZonalBwdArgs zb;
+      zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
+      zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
+      zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p;
+      zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.P = s.P; zb.npts = npts;
+      zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.accumulate = 1;
+      zb.deg = deg; zb.rc = rc;
       GPFY_TIMED(TK_ZONAL_BWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd<DIMP>(st, zb)));
     }
@@ -799,11 +842,11 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       GPFY_K(syrk_dmma_kernel, p.nblk * p.KS, SYRK_THREADS, SYRK_SMEM, st, sa);
     }
 
-    DvhatArgs da;
-    da.dT = ws + p.o_dT; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
-    da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
-    da.accumulate = 1;
-    {
+    if (!fused) {
+      DvhatArgs da;
+      da.dT = ws + p.o_dT; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
+      da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
+      da.accumulate = 1;
       GPFY_TIMED(TK_DVHAT, st);
       GPFY_TRY(launch_dvhat(st, da));
     }
@@ -905,6 +948,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;

@@ -32,6 +32,13 @@ struct ZonalArgs {
   double* R;            // [npts] radii, may be null
   double* mz;           // [P][ldz] mu2_p . z_n, may be null (then mu2 is not staged)
   int P;
+  // Gaussian likelihood, P = 1 (fused path): the per-point weights only need fmu = r mu2 . z, so they are
+  // produced here (likelihoods.py:210-218: p = (y - fmu) / s2, q = -1 / (2 s2)); null otherwise
+  const double* Yg;     // [npts]
+  const double* s2g;    // [1]
+  double* wq;           // [ldz] q r^2
+  double* wp;           // [ldz] p r
+  double* cq;           // [ldz] 2 q r^2
   DegreeTable deg;
   RecCoef rc;
 };
@@ -132,8 +139,16 @@ __global__ void __launch_bounds__(256) zonal_fwd_kernel(ZonalArgs a) {
 #pragma unroll
           for (int w = 0; w < 8; ++w) s += red[w][p][lane];
           a.mz[(int64_t)p * a.ldz + n] = s;
+          if (a.Yg) {
+            const double inv = 1.0 / a.s2g[0];
+            const double pw = (a.Yg[n] - r * s) * inv, qw = -0.5 * inv;
+            a.wp[n] = pw * r;
+            a.wq[n] = qw * r * r;
+            a.cq[n] = 2.0 * qw * r * r;
+          }
         }
     }
+    if (warp == 0 && padcol && a.Yg) { a.wp[n] = 0.0; a.wq[n] = 0.0; a.cq[n] = 0.0; }
   }
 }
 
