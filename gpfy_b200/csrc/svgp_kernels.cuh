@@ -587,20 +587,58 @@ struct SyrkArgs {
   int accumulate;
 };
 
+// Diagonal blocks only need the lower triangle.  In 8 x 8 tensor-core tiles that is tile row r with columns
+// 0..r (78 of 144 tiles); the 12 tile rows are dealt to the 8 warps as 11 | 10 | 9 | 8 | 7+0 | 6+1 | 5+2 | 4+3, i.e.
+// 12, 11, 10, 9, 9, 9, 9, 9 tiles, which also evens out the four SM sub-partitions (warp w runs on w % 4).
+// An off-diagonal block keeps the 4 x 2 grid of 24 x 48 warp tiles (18 tiles per warp).  Diagonal CTAs come first
+// in the grid so that the two CTAs sharing an SM are one of each kind.
+template <int RA, int RB>
+__device__ __forceinline__ void syrk_diag_step(const double* zs, const double* wqs, double (&acc)[12][2],
+                                               double (&accx)[2][2], int g, int t4) {
+  // one k4 step: rows of tile row RA (and RB < RA) against the weighted columns 0..RA
+#pragma unroll
+  for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
+    const double w = wqs[k4 * 4 + t4];
+    const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
+    const double afa = zs[(RA * 8 + g) * SYRK_ZS + k4 * 4 + t4];
+    double afb = 0.0;
+    if constexpr (RB >= 0) afb = zs[(RB * 8 + g) * SYRK_ZS + k4 * 4 + t4];
+#pragma unroll
+    for (int c = 0; c <= RA; ++c) {
+      const double bf = zs[(c * 8 + g) * SYRK_ZS + k4 * 4 + t4] * w;
+      dmma884(acc[c][0], acc[c][1], afa, bf);
+      if constexpr (RB >= 0) {
+        if (c <= RB) dmma884(acc[RA + 1 + c][0], acc[RA + 1 + c][1], afb, bf);
+      }
+    }
+    dmma884(accx[0][0], accx[0][1], afa, bx);
+    if constexpr (RB >= 0) dmma884(accx[1][0], accx[1][1], afb, bx);
+  }
+}
+
 __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint64_t bar_full[SYRK_STAGES], bar_empty[SYRK_STAGES];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp & 3, wn = warp >> 2;   // 4 x 2 warps, warp tile 24 x 48 (two warps per SM sub-partition)
+  const int wm = warp & 3, wn = warp >> 2;   // off-diagonal: 4 x 2 warps, warp tile 24 x 48
   const int g = lane >> 2, t4 = lane & 3;
-  const int blk = blockIdx.x % a.nblk, ks = blockIdx.x / a.nblk;
-  // blk -> (bi >= bj)
-  int bi = 0, rem = blk;
-  while (rem > bi) { rem -= bi + 1; ++bi; }
-  const int bj = rem;
+  // CTA -> (block, split): the nb diagonal blocks first, then the off-diagonal ones
+  int bi, bj, ks;
+  const int ndiag = a.nb * a.KS;
+  if ((int)blockIdx.x < ndiag) {
+    bi = bj = (int)blockIdx.x % a.nb;
+    ks = (int)blockIdx.x / a.nb;
+  } else {
+    const int noff = a.nblk - a.nb;
+    const int j = (int)blockIdx.x - ndiag;
+    int o = j % noff;
+    ks = j / noff;
+    bi = 1;
+    while (o >= bi) { o -= bi; ++bi; }
+    bj = o;
+  }
   const bool diag = bi == bj;
-  // on a diagonal block the warp tiles strictly above the diagonal are not needed (G is symmetric)
-  const bool compute = !(diag && wn == 1 && wm < 2);
+  const int blk = bi * (bi + 1) / 2 + bj;
   const int64_t p0 = (int64_t)ks * a.range;
   int64_t p1 = p0 + a.range;
   if (p1 > a.npts) p1 = a.npts;
@@ -615,14 +653,15 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
   }
   __syncthreads();
 
-  // producer: 6 chunks of 16 bytes per thread and stage (Zi rows r, r+32, r+64; same for Zj) + weights
+  // producer: 6 chunks of 16 bytes per thread and stage (Zi rows r, r+32, r+64; same for Zj) + weights;
+  // a diagonal block reads its single operand from the Zi half only
   const int z_r = tid >> 3, z_kc = (tid & 7) * 2;
   const double* pz[6];
   bool okz[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int row = (i < 3 ? bi : bj) * SYRK_B + z_r + (i % 3) * 32;
-    okz[i] = row < a.Mp;
+    okz[i] = row < a.Mp && !(diag && i >= 3);
     pz[i] = a.Z + (int64_t)(okz[i] ? row : 0) * a.ldz + p0 + z_kc;
   }
   const double* pw = ((tid >> 3) & 1 ? a.wp : a.wq) + p0 + z_kc;   // threads 0..15
@@ -635,7 +674,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
       const bool inr = (p0 + (int64_t)pit * SYRK_BK + z_kc) < p1;
 #pragma unroll
       for (int i = 0; i < 6; ++i)
-        cp_async16(zi + (i / 3) * SYRK_B * SYRK_ZS + (z_r + (i % 3) * 32) * SYRK_ZS + z_kc, pz[i], okz[i] && inr);
+        if (!(diag && i >= 3)) cp_async16(zi + (i / 3) * SYRK_B * SYRK_ZS + (z_r + (i % 3) * 32) * SYRK_ZS + z_kc, pz[i], okz[i] && inr);
       if (tid < 16) cp_async16(zi + 2 * SYRK_B * SYRK_ZS + ((tid >> 3) & 1) * SYRK_BK + z_kc, pw, inr);
       cp_async_mbar_arrive(&bar_full[st]);
       ++pit;
@@ -644,27 +683,25 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
       pw += SYRK_BK;
     }
   };
-
-  double acc[3][6][2];
-  double accx[3][2];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    accx[r][0] = accx[r][1] = 0.0;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
-  }
 #pragma unroll
   for (int s = 0; s < SYRK_STAGES - 1; ++s) produce();
-  for (int kb = 0; kb < kt; ++kb) {
-    const int st = kb % SYRK_STAGES;
-    mbar_wait(&bar_full[st], (kb / SYRK_STAGES) & 1);
-    const double* base = smem + st * SYRK_STAGE_DBL;
-    const double* zi = base + (wm * 24 + g) * SYRK_ZS + t4;
-    const double* zj = base + SYRK_B * SYRK_ZS + (wn * 48 + g) * SYRK_ZS + t4;
-    const double* wqs = base + 2 * SYRK_B * SYRK_ZS;
+
+  double* gp = a.Gpart + ((int64_t)ks * a.nblk + blk) * (SYRK_B * SYRK_B);
+  if (!diag) {
+    double acc[3][6][2];
 #pragma unroll
-    for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
-      if (compute) {
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+    for (int kb = 0; kb < kt; ++kb) {
+      const int st = kb % SYRK_STAGES;
+      mbar_wait(&bar_full[st], (kb / SYRK_STAGES) & 1);
+      const double* base = smem + st * SYRK_STAGE_DBL;
+      const double* zi = base + (wm * 24 + g) * SYRK_ZS + t4;
+      const double* zj = base + SYRK_B * SYRK_ZS + (wn * 48 + g) * SYRK_ZS + t4;
+      const double* wqs = base + 2 * SYRK_B * SYRK_ZS;
+#pragma unroll
+      for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
         double af[3], bf[6];
         const double w = wqs[k4 * 4 + t4];
 #pragma unroll
@@ -675,33 +712,70 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int c = 0; c < 6; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
-        if (diag && wn == 0) {
-          const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
-#pragma unroll
-          for (int r = 0; r < 3; ++r) dmma884(accx[r][0], accx[r][1], af[r], bx);
-        }
+        if (k4 == 0) produce();
       }
-      if (k4 == 0) produce();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int row = wm * 24 + r * 8 + g;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int col = wn * 48 + c * 8 + 2 * t4;
+        double2* dst = reinterpret_cast<double2*>(gp + row * SYRK_B + col);
+        double2 v = make_double2(acc[r][c][0], acc[r][c][1]);
+        if (a.accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
+        *dst = v;
+      }
+    }
+    return;
+  }
+
+  // ---- diagonal block ----
+  double acc[12][2];
+  double accx[2][2];
+#pragma unroll
+  for (int c = 0; c < 12; ++c) acc[c][0] = acc[c][1] = 0.0;
+  accx[0][0] = accx[0][1] = accx[1][0] = accx[1][1] = 0.0;
+  for (int kb = 0; kb < kt; ++kb) {
+    const int st = kb % SYRK_STAGES;
+    mbar_wait(&bar_full[st], (kb / SYRK_STAGES) & 1);
+    const double* zs = smem + st * SYRK_STAGE_DBL;
+    const double* wqs = zs + 2 * SYRK_B * SYRK_ZS;
+    produce();
+    switch (warp) {
+      case 0: syrk_diag_step<11, -1>(zs, wqs, acc, accx, g, t4); break;
+      case 1: syrk_diag_step<10, -1>(zs, wqs, acc, accx, g, t4); break;
+      case 2: syrk_diag_step<9, -1>(zs, wqs, acc, accx, g, t4); break;
+      case 3: syrk_diag_step<8, -1>(zs, wqs, acc, accx, g, t4); break;
+      case 4: syrk_diag_step<7, 0>(zs, wqs, acc, accx, g, t4); break;
+      case 5: syrk_diag_step<6, 1>(zs, wqs, acc, accx, g, t4); break;
+      case 6: syrk_diag_step<5, 2>(zs, wqs, acc, accx, g, t4); break;
+      default: syrk_diag_step<4, 3>(zs, wqs, acc, accx, g, t4); break;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_empty[st]);
   }
-
-  double* gp = a.Gpart + ((int64_t)ks * a.nblk + blk) * (SYRK_B * SYRK_B);
+  const int ra = warp < 4 ? 11 - warp : 11 - warp, rb = warp < 4 ? -1 : warp - 4;
+  double* bzp = a.bzpart + (int64_t)ks * (a.nb * SYRK_B) + bi * SYRK_B;
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int row = wm * 24 + r * 8 + g;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const int col = wn * 48 + c * 8 + 2 * t4;
-      double2* dst = reinterpret_cast<double2*>(gp + row * SYRK_B + col);
-      double2 v = make_double2(acc[r][c][0], acc[r][c][1]);
-      if (a.accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
-      *dst = v;
-    }
-    if (diag && wn == 0 && t4 == 0) {
-      double* dst = a.bzpart + (int64_t)ks * (a.nb * SYRK_B) + bi * SYRK_B + row;
-      *dst = a.accumulate ? *dst + accx[r][0] : accx[r][0];
+  for (int c = 0; c < 12; ++c) {
+    int row, col;
+    if (c <= ra) { row = ra * 8 + g; col = c * 8 + 2 * t4; }
+    else if (rb >= 0 && c - ra - 1 <= rb) { row = rb * 8 + g; col = (c - ra - 1) * 8 + 2 * t4; }
+    else continue;
+    double2* dst = reinterpret_cast<double2*>(gp + row * SYRK_B + col);
+    double2 v = make_double2(acc[c][0], acc[c][1]);
+    if (a.accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
+    *dst = v;
+  }
+  if (t4 == 0) {
+    double* d0 = bzp + ra * 8 + g;
+    *d0 = a.accumulate ? *d0 + accx[0][0] : accx[0][0];
+    if (rb >= 0) {
+      double* d1 = bzp + rb * 8 + g;
+      *d1 = a.accumulate ? *d1 + accx[1][0] : accx[1][0];
     }
   }
 }

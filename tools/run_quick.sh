@@ -1,7 +1,11 @@
 #!/bin/bash
+# parity + short bench (development loop)
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-python tools/quick_bench.py 1e7 30 3 2>&1 | tee gpurun_out/quick.log
-python tools/quick_bench.py 227328 30 2 > gpurun_out/quick_small.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_quick.csv python tools/quick_bench.py 227328 30 1 > gpurun_out/ncu_quick.log 2>&1
-tail -3 gpurun_out/ncu_quick.log
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python bench.py --no-cpu-baseline --steps 3 ${1:-} 2>gpurun_out/quick.err | tail -1 > gpurun_out/quick.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/quick.json'))
+print(f"{d['value']/1e6:.2f} M pts/s  {d['ms_per_step']:.2f} ms  frac {d['roofline']['step']['frac_of_fp64_peak']:.4f}  e2e {d['e2e']['value']/1e6 if d['e2e'] else 0:.2f}")
+print({k: round(v,2) for k,v in d['roofline']['kernels_ms_per_step'].items()}, d['clocks'])
+PY
