@@ -133,7 +133,9 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
             for (int c = 0; c < 8; ++c) {
               const int col = col0 + wn * 64 + c * 8 + 2 * t4;
               if (col < a.n) {
-                double2* dst = reinterpret_cast<double2*>(a.C + (int64_t)row * a.ldc + col);
+                double2* dst = a.c_blocked
+                                   ? reinterpret_cast<double2*>(a.C + ((int64_t)(col >> 5) * a.m + row) * 32 + ((col & 31) ^ ((row & 3) << 2)))
+                                   : reinterpret_cast<double2*>(a.C + (int64_t)row * a.ldc + col);
                 double2 v;
                 v.x = a.alpha * acc[r][c][0];
                 v.y = a.alpha * acc[r][c][1];
@@ -182,6 +184,7 @@ int launch_gemm(cudaStream_t stream, const GemmArgs& a, int num_sms) {
     set_error("launch_gemm: k=%d must be a multiple of 16 and n=%d, lda, ldb, ldc even", a.k, a.n);
     return GPFY_EINVAL;
   }
+  if (a.c_blocked && a.beta != 0.0) { set_error("launch_gemm: the blocked C layout needs beta = 0"); return GPFY_EINVAL; }
   if (a.psi_out && (a.m != a.k || a.alpha != 1.0 || a.beta != 0.0 || (a.ld_psi & 1))) {
     set_error("launch_gemm: the psi epilogue needs m == k, alpha = 1, beta = 0 and an even ld_psi");
     return GPFY_EINVAL;

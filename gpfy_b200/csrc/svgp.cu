@@ -8,7 +8,7 @@
 
 #include "gemm.cuh"
 #include "svgp_kernels.cuh"
-#include "zonal_bwd2.cuh"
+#include "zonal_bwd3.cuh"
 
 namespace gpfy {
 
@@ -520,23 +520,25 @@ static int launch_predict(cudaStream_t st, const PredictArgs& a) {
   return GPFY_OK;
 }
 
-// The fused backward kernel covers P = 1, Mp and the ambient dimension small enough for its shared-memory tile.
+// The fused backward kernel covers P = 1 and shapes whose [Mp x 32] tile pair fits in shared memory.
+static int fused_red_sep(const Shape& s) { return (s.Mp / 8) < 2 * ZB_WARPS ? 1 : 0; }
 static bool fused_bwd_ok(const Shape& s) {
-  return s.P == 1 && s.dimp <= 16 && zb2_smem_bytes(s.Mp, s.dimp) <= 227 * 1024 && getenv("GPFY_NO_FUSED_BWD") == nullptr;
+  return s.P == 1 && s.dimp <= 16 && (s.Mp / 8) <= ZB_WARPS * ZB_SLOTS &&
+         zb3_smem_bytes(s.Mp, s.dimp, fused_red_sep(s)) <= 227 * 1024 && getenv("GPFY_NO_FUSED_BWD") == nullptr;
 }
 
 template <int DIMP>
-static int launch_zonal_bwd2(cudaStream_t st, const ZonalBwd2Args& a, bool fuse_lik, int sms) {
+static int launch_zonal_bwd3(cudaStream_t st, const ZonalBwd3Args& a, bool fuse_lik, int sms) {
   if constexpr (DIMP <= 16) {
-    const int smem = zb2_smem_bytes(a.Mp, DIMP);
+    const int smem = zb3_smem_bytes(a.Mp, DIMP, a.red_sep);
     const int tiles = (int)((a.npts + 31) / 32);
     const unsigned grid = (unsigned)std::min(tiles, sms);
     if (fuse_lik) {
-      GPFY_TRY(set_smem(zonal_bwd2_kernel<DIMP, true>, smem));
-      zonal_bwd2_kernel<DIMP, true><<<grid, ZB2_THREADS, smem, st>>>(a);
+      GPFY_TRY(set_smem(zonal_bwd3_kernel<DIMP, true>, smem));
+      zonal_bwd3_kernel<DIMP, true><<<grid, ZB_THREADS, smem, st>>>(a);
     } else {
-      GPFY_TRY(set_smem(zonal_bwd2_kernel<DIMP, false>, smem));
-      zonal_bwd2_kernel<DIMP, false><<<grid, ZB2_THREADS, smem, st>>>(a);
+      GPFY_TRY(set_smem(zonal_bwd3_kernel<DIMP, false>, smem));
+      zonal_bwd3_kernel<DIMP, false><<<grid, ZB_THREADS, smem, st>>>(a);
     }
     GPFY_COUNT_LAUNCH();
     GPFY_LAUNCH_OK();
@@ -792,6 +794,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = fuse_lik ? nullptr : ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
+      g.c_blocked = fused ? 1 : 0;  // tile-contiguous, pre-swizzled C for the fused backward kernel
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
@@ -807,14 +810,15 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     }
 
     if (fused) {
-      ZonalBwd2Args zb;
+      ZonalBwd3Args zb;
       zb.C = ws + p.o_C; zb.ldz = p.nc; zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
       zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.mz = ws + p.o_mz; zb.Y = Y + c0; zb.vptr = variance; zb.s2ptr = sigma2;
       zb.order = desc->kernel_order; zb.vhat_p = ws + p.o_vhat_p; zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.npts = npts;
       zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.dVpart = ws + p.o_dVpart;
-      zb.deg = deg; zb.rc = rc; zb.alpha = desc->alpha;
+      zb.deg = deg; zb.red_sep = fused_red_sep(s);
+      zb3_setup(&zb, desc->alpha, deg, s.M, Mp);
       GPFY_TIMED(TK_ZONAL_BWD, st);
-      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd2<DIMP>(st, zb, fuse_lik, p.sms)));
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd3<DIMP>(st, zb, fuse_lik, p.sms)));
     } else {
       ZonalBwdArgs zb;
       zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
