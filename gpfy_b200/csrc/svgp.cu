@@ -376,10 +376,12 @@ struct Plan {
 };
 
 static int64_t choose_chunk(int sms, int64_t n) {
-  // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * 4 points give every
+  // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * 8 points give every
   // CTA the same number of tiles (no tail wave) and enough threads to fill the per-point kernels;
   // small inputs use one chunk.
-  int64_t nc = (int64_t)192 * sms * 4;
+  static int mult = 0;
+  if (!mult) { const char* e = getenv("GPFY_CHUNK_MULT"); mult = e ? atoi(e) : 8; if (mult < 1) mult = 8; }
+  int64_t nc = (int64_t)192 * sms * mult;
   int64_t need = round_up64(n, 128);
   return need < nc ? need : nc;
 }
@@ -624,6 +626,12 @@ int gpfy_abi_version(void) { return GPFY_ABI_VERSION; }
 const char* gpfy_last_error_string(void) { return g_err; }
 GPFY_API unsigned long long gpfy_debug_launch_count(void) { return g_launch_count; }
 
+#ifdef GPFY_ZB_CLOCKS
+GPFY_API int gpfy_debug_zb_clocks(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_zb_clk, sizeof(g_zb_clk)) == cudaSuccess ? 0 : -4;
+}
+#endif
+
 GPFY_API int gpfy_debug_kernel_timing(int enable) {
   g_timer.on = enable != 0;
   for (int k = 0; k < TK_COUNT; ++k) g_timer.used[k] = 0;
@@ -816,6 +824,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       zb.order = desc->kernel_order; zb.vhat_p = ws + p.o_vhat_p; zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.npts = npts;
       zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.dVpart = ws + p.o_dVpart;
       zb.deg = deg; zb.red_sep = fused_red_sep(s);
+      { const char* e = getenv("GPFY_ZB_DBG"); zb.dbg = e ? atoi(e) : 0; }
       zb3_setup(&zb, desc->alpha, deg, s.M, Mp);
       GPFY_TIMED(TK_ZONAL_BWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd3<DIMP>(st, zb, fuse_lik, p.sms)));

@@ -3,8 +3,8 @@
 //
 // One persistent CTA per SM (12 warps) walks 32-point tiles of the chunk.  Per tile:
 //   load   : the [Mp x 32] slice of C = W2 Z plus the tile's xhat rows and per-point weights arrive in shared
-//            memory by a handful of TMA bulk copies (cp.async.bulk + mbarrier complete_tx; the GEMM stores C tile by
-//            tile, pre-swizzled: GemmArgs::c_blocked), two tiles in flight
+//            memory by cp.async + mbarrier (the GEMM stores C tile by tile, pre-swizzled: GemmArgs::c_blocked, so a tile
+//            is one contiguous slab), two tiles in flight; the replicated Vhat / mu2 panel is staged once by TMA
 //   phase 1: lane = point; every warp owns three 8-row tiles (dealt on the host so that the recurrence lengths
 //            balance): t = Vhat xhat, then the monic (alpha + 1) recurrence gives BOTH
 //            d/dt C_l^alpha = 2 alpha C_{l-1}^{alpha+1} (gegenbauer.py:73-81) and, through
@@ -48,6 +48,7 @@ struct ZonalBwd3Args {
   double* partials;      // [gridDim][npart]
   int npart;
   double* dVpart;        // [gridDim][Mp][CT * 8]
+  int dbg;               // development: 1 = skip phases 1/2 (load pipeline only)
   int red_sep;           // 1: dxhat partials in their own buffer (small Mp), 0: parked in the warp's dead dT rows
   unsigned char rt[ZB_WARPS * ZB_SLOTS];  // row tile (8 rows) of each (warp, slot); 255 = none
   DegreeTable deg;
@@ -60,9 +61,9 @@ struct ZonalBwd3Args {
 
 static inline int zb3_smem_bytes(int Mp, int dimp, int red_sep) {
   const int hdr = 64 + 32 * dimp;
-  int dbl = Mp * dimp + Mp + 2 * Mp * ZB_LD + 2 * hdr + 2 * ZB_WARPS * 32 + ZB_WARPS * ZB_SUMS;
+  int dbl = Mp * dimp + Mp + 2 * Mp * ZB_LD + 2 * hdr + 2 * ZB_WARPS * 32 + ZB_SUMS * 32;
   if (red_sep) dbl += 2 * ZB_WARPS * dimp * 32;
-  return dbl * 8 + Mp * 4 + 64;
+  return dbl * 8 + Mp * 4 + 2 * ZB_WARPS * 4 + 64;
 }
 
 // host: recurrence constants and the balanced deal of row tiles to warps
@@ -110,6 +111,13 @@ static inline void zb3_setup(ZonalBwd3Args* a, double alpha, const DegreeTable& 
   }
 }
 
+#ifdef GPFY_ZB_CLOCKS
+__device__ unsigned long long g_zb_clk[12 * 32 * 8];
+#define ZB_CLK(i) do { if (blockIdx.x == 0 && lane == 0 && it < 32) g_zb_clk[(it * 12 + warp) * 8 + (i)] = clock64(); } while (0)
+#else
+#define ZB_CLK(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // four interleaved monic recurrences of degree L: p (= p_L), p1 (= p_{L-1}), p2 (= p_{L-2})
@@ -142,15 +150,15 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
   double* cbuf = mu2s + Mp;                   // [2][Mp][32] swizzled (zb_at)
   double* hdr = cbuf + 2 * Mp * ZB_LD;        // [2][wp(32) | cq(32) | xhat(32 x DIMP)]
   double* psir = hdr + 2 * HDR;               // [2][12][32]
-  double* sums = psir + 2 * ZB_WARPS * 32;    // [12][40]
-  double* redsep = sums + ZB_WARPS * ZB_SUMS; // [2][12][DIMP][32] when a.red_sep
+  double* lsum = psir + 2 * ZB_WARPS * 32;    // [40][32] per-lane running sums of the tail
+  double* redsep = lsum + ZB_SUMS * 32;       // [2][12][DIMP][32] when a.red_sep
   int* rowdeg = reinterpret_cast<int*>(redsep + (a.red_sep ? 2 * ZB_WARPS * DIMP * 32 : 0));  // [Mp]
+  int* prow = rowdeg + Mp;                    // [12][2] first row of each warp's two parking row tiles (-1: none)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int tiles = (int)((a.npts + 31) / 32);
   const int n_my = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const unsigned tile_bytes = (unsigned)(Mp * 256 + HDR * 8);
 
   // ---- one-time setup ----
   for (int i = tid; i < Mp; i += ZB_THREADS) {
@@ -162,10 +170,14 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
     }
     rowdeg[i] = l;
   }
-  for (int i = tid; i < ZB_WARPS * ZB_SUMS; i += ZB_THREADS) sums[i] = 0.0;
+  for (int i = tid; i < ZB_SUMS * 32; i += ZB_THREADS) lsum[i] = 0.0;
+  if (tid < 2 * ZB_WARPS) {
+    const unsigned char t = a.rt[(tid >> 1) * ZB_SLOTS + (tid & 1)];
+    prow[tid] = t == 255 ? -1 : (int)t * 8;
+  }
   if (tid == 0) {
-    mbar_init(&bar_full[0], 1);
-    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_full[0], 32);
+    mbar_init(&bar_full[1], 32);
     mbar_init(&bar_done[0], ZB_WARPS);
     mbar_init(&bar_done[1], ZB_WARPS);
   }
@@ -177,16 +189,16 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
     double* cb = cbuf + buf * Mp * ZB_LD;
     double* hb = hdr + buf * HDR;
-    if (lane == 0) mbar_expect_tx(&bar_full[buf], tile_bytes);
-    __syncwarp();
-    // the tile's [Mp][32] slab is contiguous in C: a few bulk copies of at most 32 KB
-    const unsigned slab = (unsigned)Mp * 256u;
-    const char* src = reinterpret_cast<const char*>(a.C + (p0 >> 5) * (int64_t)Mp * 32);
-    for (unsigned off = (unsigned)lane * 32768u; off < slab; off += 32u * 32768u)
-      tma_bulk_g2s(reinterpret_cast<char*>(cb) + off, src + off, min(32768u, slab - off), &bar_full[buf]);
-    if (lane == 29) tma_bulk_g2s(hb, a.wp + p0, 256, &bar_full[buf]);
-    if (lane == 30) tma_bulk_g2s(hb + 32, a.cq + p0, 256, &bar_full[buf]);
-    if (lane == 31) tma_bulk_g2s(hb + 64, a.XH + p0 * DIMP, 32 * DIMP * 8, &bar_full[buf]);
+    // The tile's [Mp][32] slab is contiguous in C: 16-byte cp.async (LDGSTS) requests from the 32 lanes of the
+    // producing warp, completion counted on bar_full (TMA bulk copies measured the same on B200).
+    const int nchunk = Mp * 16;
+    const double* src = a.C + (p0 >> 5) * (int64_t)Mp * 32;
+    for (int q = lane; q < nchunk; q += 32) cp_async16(cb + 2 * q, src + 2 * q, true);
+    for (int q = lane; q < HDR / 2; q += 32) {
+      const double* g = q < 16 ? a.wp + p0 + 2 * q : (q < 32 ? a.cq + p0 + 2 * (q - 16) : a.XH + p0 * DIMP + 2 * (q - 32));
+      cp_async16(hb + 2 * q, g, true);
+    }
+    cp_async_mbar_arrive(&bar_full[buf]);
   };
   if (warp == 0) {
     if (n_my > 0) issue_tile(0);
@@ -204,9 +216,8 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
 #pragma unroll
     for (int c = 0; c < CT; ++c) accv[r][c][0] = accv[r][c][1] = 0.0;
 
-  LikParams lp;
-  lp.kind = GPFY_LIK_GAUSSIAN;
-  lp.sigma2 = FUSE_LIK ? a.s2ptr[0] : 1.0;
+  const double s2 = FUSE_LIK ? a.s2ptr[0] : 1.0, s2inv = 1.0 / s2;
+  const double e_const = -0.5 * 1.8378770664093454835606594728112 - 0.5 * log(s2);
   const double kv = FUSE_LIK ? a.vptr[0] : 1.0;
 
   for (int it = 0; it < n_my; ++it) {
@@ -225,7 +236,9 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
       if (FUSE_LIK) { t_mz = a.mz[n]; t_y = a.Y[n]; }
       else t_dr = a.dr[n];
     }
+    ZB_CLK(0);
     mbar_wait(&bar_full[buf], par);
+    ZB_CLK(1);
 
     // ---- phase 1: own rows, lane = point.  Points past the end of the chunk read whatever the buffers hold:
     // every per-point input is masked so that their dT is exactly zero ----
@@ -240,7 +253,7 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
     double psi = 0.0;
 #pragma unroll 1
     for (int s = 0; s < ZB_SLOTS; ++s) {
-      if (myrt[s] < 0) continue;
+      if (myrt[s] < 0 || (a.dbg & 1)) continue;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int r0 = myrt[s] * 8 + 4 * h;
@@ -316,8 +329,10 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
       }
     }
     __syncwarp();
+    ZB_CLK(2);
 
     // ---- phase 2a: dVhat[own rows] += dT Xhat ----
+    if (!(a.dbg & 2))
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
       double af[ZB_SLOTS], bf[CT];
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
       for (int nt = 0; nt < 4; ++nt) acc2[mt][nt][0] = acc2[mt][nt][1] = 0.0;
 #pragma unroll 1
     for (int s = 0; s < ZB_SLOTS; ++s) {
-      if (myrt[s] < 0) continue;
+      if (myrt[s] < 0 || (a.dbg & 2)) continue;
 #pragma unroll
       for (int k4 = 0; k4 < 2; ++k4) {
         const int row = myrt[s] * 8 + 4 * k4 + t4;
@@ -373,44 +388,56 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
     psir[(buf * ZB_WARPS + warp) * 32 + lane] = psi;
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_done[buf]);
+    ZB_CLK(3);
 
-    // ---- tail: one warp, lane = point ----
+    // ---- tail: one warp, lane = point.  Order matters for the pipeline: gather the parked partials, hand the
+    // buffer back to the TMA for tile + 2 at once, and only then do the per-point arithmetic ----
     if (warp == tw) {
       mbar_wait(&bar_done[buf], par);
-      double part[4 + DIMP];  // [0] DB, [1 .. 1 + d) DW, then E, DV, DS2
+      ZB_CLK(4);
+      double dxh[DIMP];
 #pragma unroll
-      for (int k = 0; k < 4 + DIMP; ++k) part[k] = 0.0;
-      if (valid) {
-        double dxh[DIMP];
+      for (int c = 0; c < DIMP; ++c) dxh[c] = 0.0;
+      for (int w = 0; w < ZB_WARPS; ++w) {
+        const int pr0 = prow[2 * w], pr1 = prow[2 * w + 1];
+        if (pr0 < 0) continue;
 #pragma unroll
-        for (int c = 0; c < DIMP; ++c) dxh[c] = 0.0;
-        for (int w = 0; w < ZB_WARPS; ++w) {
-          if (a.rt[w * ZB_SLOTS] == 255) continue;
-#pragma unroll
-          for (int c = 0; c < DIMP; ++c) {
-            const double* src = a.red_sep ? redsep + ((buf * ZB_WARPS + w) * DIMP + c) * 32
-                                          : cb + zb_at((int)a.rt[w * ZB_SLOTS + c / 8] * 8 + (c & 7), lane) - lane;
-            dxh[c] += src[lane];
-          }
+        for (int c = 0; c < DIMP; ++c) {
+          const double* src = a.red_sep ? redsep + ((buf * ZB_WARPS + w) * DIMP + c) * 32 + lane
+                                        : cb + zb_at((c < 8 ? pr0 : pr1) + (c & 7), lane);
+          dxh[c] += *src;
         }
-        const double r = t_r;
+      }
+      double ps = 0.0;
+      if (FUSE_LIK) {
+#pragma unroll
+        for (int w = 0; w < ZB_WARPS; ++w) ps += psir[(buf * ZB_WARPS + w) * 32 + lane];
+      }
+      __syncwarp();
+      if (it + 2 < n_my) {
+        issue_tile(it + 2);
+      }
+      ZB_CLK(5);
+      if (valid) {
+        double part[4 + DIMP];  // [0] DB, [1 .. 1 + d) DW, then E, DV, DS2
+#pragma unroll
+        for (int k = 0; k < 4 + DIMP; ++k) part[k] = 0.0;
+        const double r = t_r, rinv = 1.0 / r;
         double drv = t_dr;
         if (FUSE_LIK) {
-          double ps = 0.0;
-#pragma unroll
-          for (int w = 0; w < ZB_WARPS; ++w) ps += psir[(buf * ZB_WARPS + w) * 32 + lane];
           double kd = kv, dkd = 0.0;
           {
             double rp = 1.0;
             for (int k = 0; k < 2 * a.order - 1; ++k) rp *= r;
             if (a.order > 0) { kd = kv * rp * r; dkd = 2.0 * a.order * kv * rp; }
           }
+          // Gaussian terms (likelihoods.py:210-218) with the uniform pieces hoisted out of the loop
           const double fmu = r * t_mz, fvar = kd + r * r * ps;
-          double e, pp, qq, ds2;
-          lik_terms(lp, fmu, fvar, t_y, e, pp, qq, ds2);
-          part[1 + DIMP] = e;
+          const double res = t_y - fmu, sq = res * res + fvar;
+          const double pp = res * s2inv, qq = -0.5 * s2inv;
+          part[1 + DIMP] = e_const - 0.5 * sq * s2inv;
           part[2 + DIMP] = qq * (kd / kv);
-          part[3 + DIMP] = ds2;
+          part[3 + DIMP] = -0.5 * s2inv + 0.5 * sq * s2inv * s2inv;
           drv = pp * t_mz + qq * (dkd + 2.0 * r * ps);
         }
         double dot = 0.0;
@@ -418,38 +445,32 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
         for (int c = 0; c < DIMP; ++c) dot = fma(xh[c], dxh[c], dot);
 #pragma unroll
         for (int c = 0; c < DIMP; ++c) {
-          const double du = (dxh[c] - xh[c] * dot) / r + drv * xh[c];
+          const double du = (dxh[c] - xh[c] * dot) * rinv + drv * xh[c];
           const double u = xh[c] * r;
           if (c < a.d) part[1 + c] = du * u;
           else if (c == a.d) part[0] = du;
         }
-      }
-      double* sw = sums + warp * ZB_SUMS;
+        // per-lane running sums shared by the successive tail warps (they run strictly one after the other)
 #pragma unroll
-      for (int k = 0; k < 4 + DIMP; ++k) {
-        const double s = warp_sum(part[k]);
-        if (lane == 0) sw[k] += s;
+        for (int k = 0; k < 4 + DIMP; ++k) lsum[k * 32 + lane] += part[k];
       }
-      __syncwarp();
-      if (it + 2 < n_my) {
-        fence_proxy_async();  // generic-proxy accesses to this buffer are ordered before the async-proxy refill
-        issue_tile(it + 2);
-      }
+      ZB_CLK(6);
     }
   }
 
   // ---- write-out (accumulating over chunks) ----
   __syncthreads();
-  if (tid < a.npart) {
-    int k;
-    if (tid == PART_E) k = 1 + DIMP;
-    else if (tid == PART_DV) k = 2 + DIMP;
-    else if (tid == PART_DS2) k = 3 + DIMP;
-    else if (tid == PART_DB) k = 0;
-    else k = 1 + (tid - PART_DW);
-    double s = 0.0;
-    for (int w = 0; w < ZB_WARPS; ++w) s += sums[w * ZB_SUMS + k];
-    if (FUSE_LIK || (tid != PART_E && tid != PART_DV && tid != PART_DS2)) a.partials[(int64_t)blockIdx.x * a.npart + tid] += s;
+  if (warp < 2) {  // fixed-order reduction of the per-lane sums: slot k handled by (warp, pass)
+    for (int k = warp; k < a.npart; k += 2) {
+      int src;
+      if (k == PART_E) src = 1 + DIMP;
+      else if (k == PART_DV) src = 2 + DIMP;
+      else if (k == PART_DS2) src = 3 + DIMP;
+      else if (k == PART_DB) src = 0;
+      else src = 1 + (k - PART_DW);
+      const double sres = warp_sum(lsum[src * 32 + lane]);
+      if (lane == 0 && (FUSE_LIK || (k != PART_E && k != PART_DV && k != PART_DS2))) a.partials[(int64_t)blockIdx.x * a.npart + k] += sres;
+    }
   }
 #pragma unroll
   for (int r = 0; r < ZB_SLOTS; ++r) {

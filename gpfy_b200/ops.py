@@ -118,8 +118,8 @@ class HotPath:
     def slab_rows(self, n):
         """Rows per streamed slab: a whole number of the kernels' point chunks (about 1.1 M rows)."""
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        chunk = 192 * sms * 4
-        return max(1, min(int(n), 10 * chunk))
+        chunk = 192 * sms * 8
+        return max(1, min(int(n), 5 * chunk))
 
     def elbo_valgrad_host(self, X_host, Y_host, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out_host=None, reduce=None):
         """Same as `elbo_valgrad_packed` for X [N, d], Y [N, P] in (pinned) HOST memory: slabs of rows are
