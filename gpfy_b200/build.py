@@ -6,7 +6,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libgpfy_b200.so")
 SOURCES = ["gemm.cu", "svgp.cu", "xla_ffi_shim.cc"]
-HEADERS = ["common.cuh", "gemm.cuh", "svgp_kernels.cuh", "gh20.h", os.path.join("..", "..", "include", "gpfy_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "gpfy_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -24,14 +24,17 @@ def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
-    for src in SOURCES:
+    objs, procs = [], []
+    for src in SOURCES:  # the translation units compile in parallel
         obj = os.path.join(CSRC, src.rsplit(".", 1)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + (["-x", "cu"] if src.endswith(".cc") else []) + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
-        subprocess.run(cmd, cwd=CSRC, check=True)
+        procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
         objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     if verbose:
         print(" ".join(cmd))

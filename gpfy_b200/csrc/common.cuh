@@ -132,27 +132,10 @@ __device__ __forceinline__ double geg_deriv_s(const RecCoef& rc, double t) {
     return rc.two_alpha * c;
   }
 }
-constexpr int GPFY_STATIC_DEGREES = 16;  // degrees below this get unrolled code, the rest the runtime loop
-#define GPFY_DEGREE_SWITCH(l, ...)                                    \
-  switch (l) {                                                        \
-    case 0: { constexpr int LS = 0; __VA_ARGS__; } break;                    \
-    case 1: { constexpr int LS = 1; __VA_ARGS__; } break;                    \
-    case 2: { constexpr int LS = 2; __VA_ARGS__; } break;                    \
-    case 3: { constexpr int LS = 3; __VA_ARGS__; } break;                    \
-    case 4: { constexpr int LS = 4; __VA_ARGS__; } break;                    \
-    case 5: { constexpr int LS = 5; __VA_ARGS__; } break;                    \
-    case 6: { constexpr int LS = 6; __VA_ARGS__; } break;                    \
-    case 7: { constexpr int LS = 7; __VA_ARGS__; } break;                    \
-    case 8: { constexpr int LS = 8; __VA_ARGS__; } break;                    \
-    case 9: { constexpr int LS = 9; __VA_ARGS__; } break;                    \
-    case 10: { constexpr int LS = 10; __VA_ARGS__; } break;                  \
-    case 11: { constexpr int LS = 11; __VA_ARGS__; } break;                  \
-    case 12: { constexpr int LS = 12; __VA_ARGS__; } break;                  \
-    case 13: { constexpr int LS = 13; __VA_ARGS__; } break;                  \
-    case 14: { constexpr int LS = 14; __VA_ARGS__; } break;                  \
-    case 15: { constexpr int LS = 15; __VA_ARGS__; } break;                  \
-    default: { constexpr int LS = -1; __VA_ARGS__; } break;                  \
-  }
+// The legacy one-point-per-lane zonal kernels (fallback for P > 1 / large M / large dim) once carried a fully
+// unrolled code path per degree; the tensor-core kernels made that obsolete, so the switch now only selects the
+// runtime-degree loop (LS = -1), which also keeps the 72 template instantiations quick to compile.
+#define GPFY_DEGREE_SWITCH(l, ...) { constexpr int LS = -1; __VA_ARGS__; }
 // LS = -1 selects the runtime-degree path
 template <int LS>
 __device__ __forceinline__ double geg_eval_d(const RecCoef& rc, int l, double t) {

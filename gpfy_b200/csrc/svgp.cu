@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include "svgp_kernels.cuh"
 #include "zonal_bwd3.cuh"
+#include "zonal_fwd2.cuh"
 
 namespace gpfy {
 
@@ -470,8 +471,26 @@ static int set_smem(K kernel, int bytes) {
 
 template <int DIMP>
 static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
-  const int smem = (a.Mp * DIMP + (a.mz ? a.P * a.Mp : 0)) * 8;
   const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 31) / 32);
+  if (a.P <= 4 && getenv("GPFY_OLD_FWD") == nullptr) {  // tensor-core forward kernel
+    ZonalFwd2Args fa;
+    fa.z = a;
+    fa.mt = make_monic(0.5 * a.rc.two_alpha);
+    const int pmax = a.P == 1 ? 1 : (a.P == 2 ? 2 : 4);
+    const int smem = zf2_smem_bytes(a.Mp, DIMP, a.P, a.mz != nullptr, pmax);
+    const unsigned pgrid = std::min(grid, (unsigned)(2 * device_sms()));  // persistent: two CTAs per SM
+#define GPFY_ZF(PM)                                                \
+  {                                                                \
+    GPFY_TRY(set_smem(zonal_fwd2_kernel<DIMP, PM>, smem));         \
+    zonal_fwd2_kernel<DIMP, PM><<<pgrid, 256, smem, st>>>(fa);     \
+  }
+    if (pmax == 1) GPFY_ZF(1) else if (pmax == 2) GPFY_ZF(2) else GPFY_ZF(4)
+#undef GPFY_ZF
+    GPFY_COUNT_LAUNCH();
+    GPFY_LAUNCH_OK();
+    return GPFY_OK;
+  }
+  const int smem = (a.Mp * DIMP + (a.mz ? a.P * a.Mp : 0)) * 8;
 #define GPFY_ZN(PM)                                               \
   {                                                               \
     GPFY_TRY(set_smem(zonal_fwd_kernel<DIMP, PM>, smem));         \

@@ -1,0 +1,192 @@
+// K_A  zonal forward on the FP64 tensor cores: to_sphere (spherical.py:214-249), t = Vhat xhat
+// (spherical_harmonics.py:308) as DMMA with the points' coordinates held in registers as B fragments, the
+// Gegenbauer recurrence (gegenbauer.py:47-60, monic form) on the accumulator fragments, mu2 . z
+// (variational.py:305 folded) and, for the Gaussian likelihood, the per-point weights (likelihoods.py:210-218).
+// One CTA = 32 points x all rows; warp w takes the 8-row tiles w, w + 8, ...
+#pragma once
+#include "svgp_kernels.cuh"
+#include "zonal_common.cuh"
+
+namespace gpfy {
+
+struct ZonalFwd2Args {
+  ZonalArgs z;
+  MonicTab mt;  // parameter alpha
+};
+
+static inline int zf2_smem_bytes(int Mp, int dimp, int P, bool with_mz, int pmax) {
+  int dbl = Mp * dimp + (with_mz ? P * Mp : 0) + 2 * 32 * dimp + 2 * 8 * pmax * 32 + 2 * 32 + GPFY_MAX_DEGREES + 2;
+  return dbl * 8 + Mp * 4 + 16;
+}
+
+// Persistent: every CTA stages Vhat / mu2 once (TMA bulk copy) and then walks 32-point tiles
+// blockIdx, blockIdx + gridDim, ...  Per tile there is ONE CTA barrier: warp 0 loads and projects the NEXT tile's
+// points while all warps work on the current one (coordinates and the mu2 . z partial sums are double-buffered in
+// shared memory), and finishes the previous tile's per-point outputs right after the barrier.
+template <int DIMP, int PMAX>
+__global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constant__ ZonalFwd2Args args) {
+  constexpr int KS = DIMP / 4;
+  const ZonalArgs& a = args.z;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint64_t bar;
+  const int Mp = a.Mp;
+  double* vs = smem;                                   // [Mp][DIMP]
+  double* mu2s = vs + Mp * DIMP;                       // [P][Mp] (only when a.mz)
+  double* xs = mu2s + (a.mz ? a.P * Mp : 0);           // [2][32][DIMP]
+  double* red = xs + 2 * 32 * DIMP;                    // [2][8][PMAX][32]
+  double* rs = red + 2 * 8 * PMAX * 32;                // [2][32] radii of the tile's points
+  double* leads = rs + 2 * 32;                         // [MAX_DEGREES + 2]
+  int* rowdeg = reinterpret_cast<int*>(leads + GPFY_MAX_DEGREES + 2);  // [Mp]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int64_t npts_e = (a.npts + 1) & ~(int64_t)1;
+  const int tiles = (int)((npts_e + 31) / 32);
+  const int n_my = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  for (int i = tid; i < Mp; i += 256) {
+    int l = -1;
+    if (i < a.M) {
+      int o = 0;
+      l = 0;
+      while (i >= o + a.deg.m[l]) { o += a.deg.m[l]; ++l; }
+    }
+    rowdeg[i] = l;
+  }
+  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) leads[i] = args.mt.lead[i];
+
+  // warp 0, lane = point: onto the sphere (spherical.py:214-249); coordinates to shared memory, r and xhat to HBM
+  auto project_tile = [&](int it) {
+    const int64_t n = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32 + lane;
+    double xh[DIMP];
+#pragma unroll
+    for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
+    double r = 1.0;
+    if (n < a.npts) {
+      r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
+      if (a.R) a.R[n] = r;
+      if (a.XH) {
+#pragma unroll
+        for (int c = 0; c < DIMP; c += 2) *reinterpret_cast<double2*>(a.XH + n * DIMP + c) = make_double2(xh[c], xh[c + 1]);
+      }
+    }
+    double* x = xs + (it & 1) * 32 * DIMP;
+#pragma unroll
+    for (int c = 0; c < DIMP; c += 2) *reinterpret_cast<double2*>(x + lane * DIMP + c) = make_double2(xh[c], xh[c + 1]);
+    rs[(it & 1) * 32 + lane] = r;
+  };
+  // warp 0, lane = point: mz_p[n] = mu2_p . z_n summed over the warps in a fixed order (variational.py:305 folded),
+  // and the Gaussian per-point weights (likelihoods.py:210-218)
+  auto finish_tile = [&](int it) {
+    const int64_t n = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32 + lane;
+    const bool valid = n < a.npts;
+    const double* rd = red + (it & 1) * 8 * PMAX * 32;
+    const double r = rs[(it & 1) * 32 + lane];
+#pragma unroll
+    for (int pp = 0; pp < PMAX; ++pp)
+      if (pp < a.P) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += rd[(w * PMAX + pp) * 32 + lane];
+        if (valid) {
+          a.mz[(int64_t)pp * a.ldz + n] = s;
+          if (a.Yg) {
+            const double inv = 1.0 / a.s2g[0];
+            const double pw = (a.Yg[n] - r * s) * inv, qw = -0.5 * inv;
+            a.wp[n] = pw * r;
+            a.wq[n] = qw * r * r;
+            a.cq[n] = 2.0 * qw * r * r;
+          }
+        }
+      }
+    if (!valid && n < npts_e && a.Yg) { a.wp[n] = 0.0; a.wq[n] = 0.0; a.cq[n] = 0.0; }
+  };
+
+  if (warp == 0 && n_my > 0) project_tile(0);
+  stage_params_tma(vs, a.vhat_p, (unsigned)((Mp * DIMP + (a.mz ? a.P * Mp : 0)) * 8), &bar);
+  __syncthreads();
+
+  const int ntile = (a.M + 7) / 8;
+  for (int it = 0; it < n_my; ++it) {
+    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
+    const double* x = xs + (it & 1) * 32 * DIMP;
+    double xb[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) xb[ks][nt] = x[(8 * nt + g) * DIMP + 4 * ks + t4];
+
+    double mzacc[PMAX][8];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mzacc[p][u] = 0.0;
+
+    for (int rt = warp; rt < ntile; rt += 8) {
+      const int row = rt * 8 + g;
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double av = vs[row * DIMP + 4 * ks + t4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(t[2 * nt], t[2 * nt + 1], av, xb[ks][nt]);
+      }
+      const int l = rowdeg[row];
+      const int lo = rowdeg[rt * 8], hi = rowdeg[rt * 8 + 7];
+      double p[8], p1[8], p2[8], z[8];
+      if (lo == hi && lo >= 1) {
+        monic_uniform<8>(args.mt.beta, lo, t, p, p1, p2);
+        const double ld = leads[lo];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
+      } else {
+        const int lmax = __reduce_max_sync(0xffffffffu, l);
+        monic_mixed<8>(args.mt.beta, l, lmax, t, p, p1, p2);
+        const double ld = l >= 1 ? leads[l] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
+      }
+      if (row < a.M) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int64_t n0 = p0 + 8 * nt + 2 * t4;
+          double* dst = a.Z + (int64_t)row * a.ldz + n0;
+          if (n0 + 1 < a.npts) *reinterpret_cast<double2*>(dst) = make_double2(z[2 * nt], z[2 * nt + 1]);
+          else if (n0 < a.npts) {
+            dst[0] = z[2 * nt];
+            if (n0 + 1 < npts_e) dst[1] = 0.0;  // keep the even-padded tail column finite
+          }
+        }
+        if (a.mz) {
+#pragma unroll
+          for (int pp = 0; pp < PMAX; ++pp)
+            if (pp < a.P) {
+              const double m2 = mu2s[pp * Mp + row];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) mzacc[pp][u] = fma(m2, z[u], mzacc[pp][u]);
+            }
+        }
+      }
+    }
+    if (a.mz) {  // over the 8 row lanes by shuffles; the warps' parts go to shared memory
+      double* rd = red + (it & 1) * 8 * PMAX * 32;
+#pragma unroll
+      for (int pp = 0; pp < PMAX; ++pp)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          double v = mzacc[pp][u];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) rd[(warp * PMAX + pp) * 32 + 8 * (u >> 1) + 2 * t4 + (u & 1)] = v;
+        }
+    }
+    if (warp == 0 && it + 1 < n_my) project_tile(it + 1);
+    __syncthreads();
+    if (warp == 0 && a.mz) finish_tile(it);
+  }
+}
+
+}  // namespace gpfy
