@@ -504,6 +504,18 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
 }
 
 template <int DIMP>
+static int launch_features2(cudaStream_t st, const FeaturesArgs& fa) {
+  const int smem = ft_smem_bytes(fa.z.Mp, DIMP);
+  const int tiles = (int)((fa.z.npts + 31) / 32);
+  const unsigned grid = (unsigned)std::min(tiles, 2 * device_sms());
+  GPFY_TRY(set_smem(features2_kernel<DIMP>, smem));
+  features2_kernel<DIMP><<<grid, 256, smem, st>>>(fa);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
+template <int DIMP>
 static int launch_zonal_bwd(cudaStream_t st, const ZonalBwdArgs& a) {
   const int smem = (a.Mp * DIMP + a.P * a.Mp + 8 * DIMP * 32) * 8;
   const unsigned grid = (unsigned)((a.npts + 31) / 32);
@@ -734,6 +746,21 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   GPFY_TRY(run_prologue(st, desc, p, ws, apply_to_sphere ? w : vhat, apply_to_sphere ? b : vhat, nullptr, nullptr, vhat, lcat,
                         nullptr, nullptr, false));
   RecCoef rc = make_rec_coef(desc->alpha);
+  if (ft_smem_bytes(Mp, s.dimp) <= 113 * 1024 && getenv("GPFY_OLD_FEATURES") == nullptr) {
+    // one fused kernel (two CTAs per SM): the zonal values stay in shared memory
+    FeaturesArgs fa;
+    ZonalArgs& za = fa.z;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
+    za.X = X; za.xcols = apply_to_sphere ? s.d : s.dim; za.apply_to_sphere = apply_to_sphere;
+    za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
+    za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = n;
+    za.Z = nullptr; za.ldz = 0; za.XH = nullptr; za.R = nullptr; za.mz = nullptr; za.P = 1;
+    za.deg = deg; za.rc = rc;
+    fa.mt = make_monic(desc->alpha);
+    fa.Linv = ws + p.o_linv; fa.scale = degree_scale; fa.mul_r = mul_r; fa.out = out; fa.ldo = n; fa.r_out = r_out;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_features2<DIMP>(st, fa)));
+    return GPFY_OK;
+  }
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     ZonalArgs za;

@@ -190,3 +190,191 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
 }
 
 }  // namespace gpfy
+
+namespace gpfy {
+
+// ------------------------------------------------------------------------------------------------
+// K_F  fused feature matrix (spherical_harmonics.py:290-320, :344-362, :385-387):
+//     out[off_l + i, n] = scale_l * (r_n) * sum_k Linv_l[i][k] C_l^alpha(Vhat_l xhat_n)[k]
+// One persistent CTA walks 32-point tiles.  Phase A is the tensor-core zonal forward above, but the zonal values go
+// to a swizzled shared-memory tile instead of HBM; phase B is the per-degree whitening as a block-triangular DMMA
+// product (row tile i of degree l only needs columns 0 .. 8 i + 7 of Linv_l), scaled and stored straight into the
+// [M, N] output.  Z never touches HBM: the kernel writes 8 M bytes per point and reads 8 d.
+// ------------------------------------------------------------------------------------------------
+struct FeaturesArgs {
+  ZonalArgs z;            // Z / ldz unused
+  MonicTab mt;
+  const double* Linv;     // dense block-diagonal [Mp][Mp] (prologue)
+  const double* scale;    // [F] or null
+  int mul_r;
+  double* out;            // [M][ldo], first column of this launch
+  int64_t ldo;
+  double* r_out;          // [npts] or null
+};
+
+constexpr int FT_LD = 32;
+__device__ __forceinline__ int ft_at(int row, int pt) { return row * FT_LD + (pt ^ ((row & 3) << 2)); }
+
+static inline int ft_smem_bytes(int Mp, int dimp) {
+  int dbl = Mp * dimp + Mp * FT_LD + 2 * 32 * dimp + 2 * 32 + 2 * (GPFY_MAX_DEGREES + 2);
+  return dbl * 8 + Mp * 4 + (GPFY_MAX_DEGREES + 1) * 4 + 16;
+}
+
+template <int DIMP>
+__global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant__ FeaturesArgs args) {
+  constexpr int KS = DIMP / 4;
+  const ZonalArgs& a = args.z;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint64_t bar;
+  const int Mp = a.Mp;
+  double* vs = smem;                          // [Mp][DIMP]
+  double* zt = vs + Mp * DIMP;                // [Mp][32] swizzled zonal tile
+  double* xs = zt + Mp * FT_LD;               // [2][32][DIMP]
+  double* rs = xs + 2 * 32 * DIMP;            // [2][32]
+  double* leads = rs + 2 * 32;                // [MAX_DEGREES + 2]
+  double* scl = leads + GPFY_MAX_DEGREES + 2; // [MAX_DEGREES + 2] per-degree output scale
+  int* rowdeg = reinterpret_cast<int*>(scl + GPFY_MAX_DEGREES + 2);  // [Mp]
+  int* offs = rowdeg + Mp;                    // [F + 1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int tiles = (int)((a.npts + 31) / 32);
+  const int n_my = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int F = a.deg.F;
+
+  for (int i = tid; i < Mp; i += 256) {
+    int l = -1;
+    if (i < a.M) {
+      int o = 0;
+      l = 0;
+      while (i >= o + a.deg.m[l]) { o += a.deg.m[l]; ++l; }
+    }
+    rowdeg[i] = l;
+  }
+  for (int i = tid; i < Mp * FT_LD; i += 256) zt[i] = 0.0;  // padding rows stay zero
+  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) {
+    leads[i] = args.mt.lead[i];
+    scl[i] = (i < F && args.scale) ? args.scale[i] : 1.0;
+  }
+  if (tid == 0) {
+    int o = 0;
+    for (int l = 0; l < F; ++l) { offs[l] = o; o += a.deg.m[l]; }
+    offs[F] = o;
+  }
+
+  auto project_tile = [&](int it) {
+    const int64_t n = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32 + lane;
+    double xh[DIMP];
+#pragma unroll
+    for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
+    double r = 1.0;
+    if (n < a.npts) {
+      r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
+      if (args.r_out) args.r_out[n] = r;
+    }
+    double* x = xs + (it & 1) * 32 * DIMP;
+#pragma unroll
+    for (int c = 0; c < DIMP; c += 2) *reinterpret_cast<double2*>(x + lane * DIMP + c) = make_double2(xh[c], xh[c + 1]);
+    rs[(it & 1) * 32 + lane] = args.mul_r ? r : 1.0;
+  };
+
+  if (warp == 0 && n_my > 0) project_tile(0);
+  stage_params_tma(vs, a.vhat_p, (unsigned)(Mp * DIMP * 8), &bar);
+  __syncthreads();
+
+  const int ntile = (a.M + 7) / 8;
+  const bool vec_ok = (args.ldo & 1) == 0;
+  for (int it = 0; it < n_my; ++it) {
+    const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
+    const double* x = xs + (it & 1) * 32 * DIMP;
+    // ---- phase A: zonal values of the tile into shared memory ----
+    {
+      double xb[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) xb[ks][nt] = x[(8 * nt + g) * DIMP + 4 * ks + t4];
+      for (int rt = warp; rt < ntile; rt += 8) {
+        const int row = rt * 8 + g;
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const double av = vs[row * DIMP + 4 * ks + t4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(t[2 * nt], t[2 * nt + 1], av, xb[ks][nt]);
+        }
+        const int l = rowdeg[row];
+        const int lo = rowdeg[rt * 8], hi = rowdeg[rt * 8 + 7];
+        double p[8], p1[8], p2[8], z[8];
+        if (lo == hi && lo >= 1) {
+          monic_uniform<8>(args.mt.beta, lo, t, p, p1, p2);
+          const double ld = leads[lo];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
+        } else {
+          const int lmax = __reduce_max_sync(0xffffffffu, l);
+          monic_mixed<8>(args.mt.beta, l, lmax, t, p, p1, p2);
+          const double ld = l >= 1 ? leads[l] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
+        }
+        if (row < a.M) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<double2*>(zt + ft_at(row, 8 * nt + 2 * t4)) = make_double2(z[2 * nt], z[2 * nt + 1]);
+        }
+      }
+    }
+    if (warp == 0 && it + 1 < n_my) project_tile(it + 1);
+    __syncthreads();
+
+    // ---- phase B: whitening, work item = (degree, 8-row tile of that degree) dealt round-robin to the warps ----
+    {
+      double rr[8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        rr[2 * nt] = rs[(it & 1) * 32 + 8 * nt + 2 * t4];
+        rr[2 * nt + 1] = rs[(it & 1) * 32 + 8 * nt + 2 * t4 + 1];
+      }
+      int item = 0;
+      for (int l = 0; l < F; ++l) {
+        const int off = offs[l], ml = offs[l + 1] - off;
+        const double sc = scl[l];
+        for (int i = 0; i * 8 < ml; ++i, ++item) {
+          if ((item & 7) != warp) continue;
+          double acc[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+          const int rloc = 8 * i + g;                 // row inside the degree block
+          const int kend = min(ml, 8 * i + 8);        // lower triangular: columns 0 .. 8 i + 7
+          const bool rok = rloc < ml;
+          const double* Lrow = args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off;
+          for (int k0 = 0; k0 < kend; k0 += 4) {
+            const int kc = k0 + t4;
+            const double av = (rok && kc < ml) ? __ldg(Lrow + kc) : 0.0;
+            const int zrow = min(off + kc, Mp - 1);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[2 * nt], acc[2 * nt + 1], av, zt[ft_at(zrow, 8 * nt + g)]);
+          }
+          if (rok) {
+            double* orow = args.out + (int64_t)(off + rloc) * args.ldo + p0;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const int c = 8 * nt + 2 * t4;
+              const double v0 = sc * rr[2 * nt] * acc[2 * nt], v1 = sc * rr[2 * nt + 1] * acc[2 * nt + 1];
+              if (p0 + c + 1 < a.npts && vec_ok) *reinterpret_cast<double2*>(orow + c) = make_double2(v0, v1);
+              else {
+                if (p0 + c < a.npts) orow[c] = v0;
+                if (p0 + c + 1 < a.npts) orow[c + 1] = v1;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // the tile is consumed before the next phase A overwrites it
+  }
+}
+
+}  // namespace gpfy
