@@ -305,11 +305,33 @@ def run_ours(a):
                          f"(oracle/gpfy_oracle.py; JAX not installable)",
                "elbo_rel_diff_gpu_vs_oracle_on_sample": abs(gpu_val - val) / abs(val)}
 
+    # ---- BASELINE.json configs[1]: Phi(X) only (projection A = sqrt(lambda v) r Phi), device resident ----
+    phi = None
+    if world == 1:
+        nphi = min(n_local, 2_000_000)
+        ds = torch.sqrt(args[5] * args[4])
+        f = lambda: hp.features(X[:nphi], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)
+        f(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            f()
+        e1.record(); torch.cuda.synchronize()
+        pms = e0.elapsed_time(e1) / 3
+        hbm_peak = 6549.8
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except (OSError, ValueError, KeyError):
+            pass
+        gbs = 8.0 * (8 + M) * nphi / (pms * 1e-3) * 1e-9
+        phi = {"workload": "Phi(X) [M, N] feature matrix, d=8, degrees 0..10, T=%d" % a.T, "N": nphi, "value": nphi / (pms * 1e-3),
+               "unit": UNIT, "ms": pms, "alg_bytes_per_point": 8 * (8 + M), "achieved_gbs": gbs, "hbm_peak_gbs": hbm_peak,
+               "frac_of_hbm_peak": gbs / hbm_peak}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(N, a.T, M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu, "elbo_data_term": data_term, "kl": float(kl[0]),
+        "roofline": roofline, "cpu_baseline": cpu, "phi_only": phi, "elbo_data_term": data_term, "kl": float(kl[0]),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

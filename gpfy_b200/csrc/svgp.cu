@@ -225,15 +225,21 @@ __global__ void reduce_g_kernel(const double* Gpart, const double* bzpart, doubl
   }
 }
 
-// dVhat[i][c] = sum_ks dVpart[ks][i][c]  -> packed [M, dim]
+// dVhat[i][c] = sum_ks dVpart[ks][i][c]  -> packed [M, dim].  Eight lanes share one element (strided over ks,
+// then a fixed xor tree), so the KS-long dependent chain of loads is 8 times shorter.
 __global__ void reduce_dv_kernel(const double* dVpart, double* out, int M, int Mp, int dim, int dimp, int KS) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= M * dim) return;
-  const int i = e / dim, c = e % dim;
-  double s = 0.0;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 3, sub = t & 7;
+  const bool ok = e < M * dim;
+  const int i = ok ? e / dim : 0, c = ok ? e % dim : 0;
   const int ldv = (dimp + 7) / 8 * 8;
-  for (int ks = 0; ks < KS; ++ks) s += dVpart[((int64_t)ks * Mp + i) * ldv + c];
-  out[e] = s;
+  double s = 0.0;
+  if (ok)
+    for (int ks = sub; ks < KS; ks += 8) s += dVpart[((int64_t)ks * Mp + i) * ldv + c];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) out[e] = s;
 }
 
 // dd[i] = sum_j (dE[i][j] + sum_p mu[i][p] bz[p][j]) * Linv[i][j]      (one warp per row, i < M)
@@ -335,22 +341,35 @@ __global__ void finalize_kernel(FinalArgs a) {
   }
 }
 
-// d_mu[i][p] = y[i] (strided store helper is gemv's ys); KL kernels below
-__global__ void kl_tril_kernel(const double* mu, const double* L, double* out, int M, int P) {
-  // variational.py:225-240,262-286:  KL = -MP/2 - 1/2 sum log diag(L)^2 + 1/2 |mu|^2 + 1/2 |L|_F^2
-  __shared__ double red[256];
+// KL(q || N(0, I)) for q = N(mu, L L^T) (variational.py:225-240, 262-286):
+//   KL = -MP/2 - 1/2 sum log diag(L)^2 + 1/2 |mu|^2 + 1/2 |L|_F^2
+// The gradients are elementwise (many blocks); the scalar is one block's fixed-order tree (deterministic).
+__global__ void kl_tril_grad_kernel(const double* mu, const double* L, double* out, int M, int P) {
   const int64_t nmu = (int64_t)M * P, nL = (int64_t)P * M * M;
-  double s = 0.0;
-  for (int64_t e = threadIdx.x; e < nmu; e += blockDim.x) { s += 0.5 * mu[e] * mu[e]; out[1 + e] = mu[e]; }
-  for (int64_t e = threadIdx.x; e < nL; e += blockDim.x) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nmu) out[1 + e] = mu[e];
+  if (e < nL) {
     const int i = (int)((e / M) % M), j = (int)(e % M);
     const double v = L[e];
-    s += 0.5 * v * v;
-    double gr = v;
-    if (i == j) { s -= 0.5 * log(v * v); gr -= 1.0 / v; }
-    out[1 + nmu + e] = gr;
+    out[1 + nmu + e] = (i == j) ? v - 1.0 / v : v;
   }
-  red[threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(1024) kl_tril_value_kernel(const double* mu, const double* L, double* out, int M, int P) {
+  __shared__ double red[1024];
+  const int64_t nmu = (int64_t)M * P, nL = (int64_t)P * M * M;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int64_t e = threadIdx.x; e < nmu; e += blockDim.x) s0 = fma(0.5 * mu[e], mu[e], s0);
+  int64_t e = threadIdx.x;
+  for (; e + 3 * (int64_t)blockDim.x < nL; e += 4 * (int64_t)blockDim.x) {
+    const double a0 = L[e], a1 = L[e + blockDim.x], a2 = L[e + 2 * (int64_t)blockDim.x], a3 = L[e + 3 * (int64_t)blockDim.x];
+    s0 = fma(0.5 * a0, a0, s0); s1 = fma(0.5 * a1, a1, s1); s2 = fma(0.5 * a2, a2, s2); s3 = fma(0.5 * a3, a3, s3);
+  }
+  for (; e < nL; e += blockDim.x) s0 = fma(0.5 * L[e], L[e], s0);
+  for (int64_t d = threadIdx.x; d < (int64_t)P * M; d += blockDim.x) {
+    const double v = L[(d / M) * M * M + (d % M) * (int64_t)(M + 1)];
+    s1 -= 0.5 * log(v * v);
+  }
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
@@ -951,7 +970,7 @@ int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity
   GPFY_K(dd_kernel, (s.M + 3) / 4, 128, 0, st, ws + p.o_dE, mu, ws + p.o_bz, ws + p.o_linv, ws + p.o_dd, s.M, Mp, s.P);
   GPFY_K(dl_step1_kernel, s.F, 256, 0, st, ws + p.o_dE, mu, ws + p.o_bz, ws + p.o_dvec, ws + p.o_linv, ws + p.o_tmp1, Mp, s.P, deg);
   GPFY_K(dl_step2_kernel, s.F, 256, 0, st, ws + p.o_tmp1, ws + p.o_linv, packed + lay.d_lcat, Mp, deg);
-  GPFY_K(reduce_dv_kernel, (s.M * s.dim + 255) / 256, 256, 0, st, ws + p.o_dVpart, packed + lay.d_vhat, s.M, Mp, s.dim, s.dimp, p.KSV);
+  GPFY_K(reduce_dv_kernel, (8 * s.M * s.dim + 255) / 256, 256, 0, st, ws + p.o_dVpart, packed + lay.d_vhat, s.M, Mp, s.dim, s.dimp, p.KSV);
   FinalArgs fa;
   fa.partials = ws + p.o_partials; fa.nblocks = (int)p.nblocks_c; fa.npart = p.npart;
   fa.dd = ws + p.o_dd; fa.dvec = ws + p.o_dvec; fa.eig = eig; fa.w = w; fa.b = b; fa.v = variance;
@@ -982,7 +1001,9 @@ int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, 
     set_error("prior KL for a full-covariance q needs a Cholesky of Sigma: left to the host framework");
     return GPFY_EUNSUPPORTED;
   }
-  GPFY_K(kl_tril_kernel, 1, 256, 0, (cudaStream_t)stream, mu, sigma, out, s.M, s.P);
+  const int64_t nL = (int64_t)s.P * s.M * s.M;
+  GPFY_K(kl_tril_grad_kernel, (unsigned)((nL + 255) / 256), 256, 0, (cudaStream_t)stream, mu, sigma, out, s.M, s.P);
+  GPFY_K(kl_tril_value_kernel, 1, 1024, 0, (cudaStream_t)stream, mu, sigma, out, s.M, s.P);
   return GPFY_OK;
 }
 
