@@ -8,7 +8,7 @@ GPFY_ABI_VERSION = 1
 GPFY_MAX_DEGREES = 32
 LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1
 Q_TRIL, Q_FULLCOV = 0, 1
-W_ARD, W_SCALAR = 0, 1
+W_ARD, W_SCALAR, W_PROJECTION = 0, 1, 2
 OP_FEATURES, OP_ELBO, OP_PREDICT = 0, 1, 2
 
 
@@ -24,7 +24,7 @@ class GpfyDesc(ctypes.Structure):
         ("likelihood", ctypes.c_int32),
         ("q_kind", ctypes.c_int32),
         ("weight_mode", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("projection_dim", ctypes.c_int32),
         ("alpha", ctypes.c_double),
     ]
 
@@ -98,7 +98,8 @@ def check(rc):
         raise GpfyError(f"gpfy_b200 error {rc}: {load().gpfy_last_error_string().decode()}")
 
 
-def make_desc(input_dim, m, num_outputs=1, kernel_order=1, likelihood=LIK_GAUSSIAN, q_kind=Q_TRIL, weight_mode=W_ARD):
+def make_desc(input_dim, m, num_outputs=1, kernel_order=1, likelihood=LIK_GAUSSIAN, q_kind=Q_TRIL, weight_mode=W_ARD,
+              projection_dim=0):
     d = GpfyDesc()
     d.struct_size = ctypes.sizeof(GpfyDesc)
     d.abi_version = GPFY_ABI_VERSION
@@ -113,5 +114,7 @@ def make_desc(input_dim, m, num_outputs=1, kernel_order=1, likelihood=LIK_GAUSSI
     d.likelihood = int(likelihood)
     d.q_kind = int(q_kind)
     d.weight_mode = int(weight_mode)
-    d.alpha = (input_dim + 1 - 2.0) / 2.0
+    d.projection_dim = int(projection_dim) if weight_mode == W_PROJECTION else 0
+    sphere_dim = d.projection_dim if d.projection_dim > 0 else int(input_dim)
+    d.alpha = (sphere_dim + 1 - 2.0) / 2.0
     return d

@@ -6,14 +6,14 @@ from ._lib import GpfyError  # noqa: F401
 _CACHE = {}
 
 
-def hot_path(input_dim, m, num_outputs=1, kernel_order=1, likelihood="gaussian", q_kind="tril", weight_mode="ard"):
+def hot_path(input_dim, m, num_outputs=1, kernel_order=1, likelihood="gaussian", q_kind="tril", weight_mode="ard", projection_dim=0):
     """One `ops.HotPath` (descriptor + scratch) per static configuration."""
     from .ops import HotPath, require_cuda
     dev = require_cuda()
-    key = (int(input_dim), tuple(int(v) for v in m), int(num_outputs), int(kernel_order), likelihood, q_kind, weight_mode, str(dev))
+    key = (int(input_dim), tuple(int(v) for v in m), int(num_outputs), int(kernel_order), likelihood, q_kind, weight_mode, int(projection_dim), str(dev))
     hp = _CACHE.get(key)
     if hp is None:
-        hp = HotPath(input_dim, m, num_outputs, kernel_order, likelihood, q_kind, weight_mode, device=dev)
+        hp = HotPath(input_dim, m, num_outputs, kernel_order, likelihood, q_kind, weight_mode, device=dev, projection_dim=projection_dim)
         _CACHE[key] = hp
     return hp
 

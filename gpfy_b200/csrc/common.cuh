@@ -255,6 +255,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------------------------------------
 struct Shape {
   int d, dim, dimp;  // input dim, ambient dim, ambient dim rounded up to a multiple of 4
+  int sd, proj, nw;  // sphere dim (= proj or d), projection dim (0: none), number of weight entries (d, 1 or d * p)
   int F, P, M, Mp;   // degrees, outputs, inducing features, M rounded up to a multiple of 32
   int off[GPFY_MAX_DEGREES + 1];   // row offset of each degree
   int64_t loff[GPFY_MAX_DEGREES + 1];  // offset of L_l inside lcat

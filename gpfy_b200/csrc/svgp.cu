@@ -68,7 +68,11 @@ int make_shape(const GpfyDesc* desc, Shape* s) {
     return GPFY_EINVAL;
   }
   s->d = desc->input_dim;
-  s->dim = s->d + 1;
+  s->proj = desc->weight_mode == GPFY_W_PROJECTION ? desc->projection_dim : 0;
+  if (desc->weight_mode == GPFY_W_PROJECTION && s->proj < 1) { set_error("projection_dim must be >= 1 for GPFY_W_PROJECTION"); return GPFY_EINVAL; }
+  s->sd = s->proj > 0 ? s->proj : s->d;
+  s->nw = s->proj > 0 ? s->d * s->proj : (desc->weight_mode == GPFY_W_SCALAR ? 1 : s->d);
+  s->dim = s->sd + 1;
   s->dimp = round_up(s->dim, 4);
   s->F = desc->num_degrees;
   s->P = desc->num_outputs;
@@ -91,7 +95,8 @@ int make_shape(const GpfyDesc* desc, Shape* s) {
   if (desc->kernel_order < 0 || desc->kernel_order > 8) { set_error("kernel_order %d out of range", desc->kernel_order); return GPFY_EINVAL; }
   if (desc->likelihood != GPFY_LIK_GAUSSIAN && desc->likelihood != GPFY_LIK_BERNOULLI) { set_error("unknown likelihood %d", desc->likelihood); return GPFY_EINVAL; }
   if (desc->q_kind != GPFY_Q_TRIL && desc->q_kind != GPFY_Q_FULLCOV) { set_error("unknown q_kind %d", desc->q_kind); return GPFY_EINVAL; }
-  if (desc->weight_mode != GPFY_W_ARD && desc->weight_mode != GPFY_W_SCALAR) { set_error("unknown weight_mode %d", desc->weight_mode); return GPFY_EINVAL; }
+  if (desc->weight_mode < GPFY_W_ARD || desc->weight_mode > GPFY_W_PROJECTION) { set_error("unknown weight_mode %d", desc->weight_mode); return GPFY_EINVAL; }
+  if (s->nw > 1024) { set_error("projection with %d weights > 1024 is not built", s->nw); return GPFY_EUNSUPPORTED; }
   if (s->mmax > 1024) { set_error("m_l = %d > 1024 is not built", s->mmax); return GPFY_EUNSUPPORTED; }
   return GPFY_OK;
 }
@@ -112,13 +117,17 @@ static int device_sms() {
 struct PrepArgs {
   const double *w, *b, *v, *eig, *vhat;
   double *sw, *sb, *dvec, *vhat_p;
-  int d, dim, dimp, M, Mp, scalar_w;
+  int d, dim, dimp, M, Mp, scalar_w, proj;
   DegreeTable deg;
 };
 
 __global__ void prep_kernel(PrepArgs a) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (int j = tid; j < a.d; j += nth) a.sw[j] = sqrt(a.w[a.scalar_w ? 0 : j]);
+  if (a.proj > 0) {
+    for (int j = tid; j < a.d * a.proj; j += nth) a.sw[j] = a.w[j];  // [d, p] projection: identity bijector, no sqrt
+  } else {
+    for (int j = tid; j < a.d; j += nth) a.sw[j] = sqrt(a.w[a.scalar_w ? 0 : j]);
+  }
   if (tid == 0) a.sb[0] = sqrt(a.b[0]);
   if (a.dvec) {
     for (int i = tid; i < a.Mp; i += nth) {
@@ -296,14 +305,14 @@ struct FinalArgs {
   const double* partials;
   int nblocks, npart;
   const double *dd, *dvec, *eig, *w, *b, *v;
-  int M, d, scalar_w;
+  int M, d, scalar_w, proj, nw;
   DegreeTable deg;
   double* packed;
   GpfyElboLayout lay;
 };
 // single block: deterministic tree over the per-block partials, then the scalar chain rules
 __global__ void finalize_kernel(FinalArgs a) {
-  __shared__ double sums[64];
+  extern __shared__ double sums[];  // [npart]
   __shared__ double red[256];
   for (int k = 0; k < a.npart; ++k) {
     double s = 0.0;
@@ -321,7 +330,9 @@ __global__ void finalize_kernel(FinalArgs a) {
     a.packed[a.lay.data_term] = sums[PART_E];
     a.packed[a.lay.d_sigma2] = sums[PART_DS2];
     a.packed[a.lay.d_b] = sums[PART_DB] / (2.0 * sqrt(a.b[0]));
-    if (a.scalar_w) {
+    if (a.proj > 0) {
+      for (int j = 0; j < a.nw; ++j) a.packed[a.lay.d_w + j] = sums[PART_DW + j];  // W has the identity bijector, no sqrt
+    } else if (a.scalar_w) {
       double s = 0.0;
       for (int j = 0; j < a.d; ++j) s += sums[PART_DW + j];
       a.packed[a.lay.d_w] = s / (2.0 * a.w[0]);
@@ -416,11 +427,11 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->KSV = std::max(p->sms, (8 * p->sms) / (s.Mp / 32));  // dVhat partial slots: >= one per persistent CTA of the fused backward kernel
   p->nblocks_c = p->nc / 32;
   p->npsi = gemm_psi_slabs(s.Mp);
-  p->npart = PART_DW + s.d;
+  p->npart = PART_DW + (s.proj > 0 ? s.nw : s.d);
   const int64_t Mp = s.Mp, Mp2 = Mp * Mp;
   int64_t o = 0;
   auto take = [&](int64_t cnt) { int64_t r = o; o += round_up64(cnt, 32); return r; };  // 256-byte aligned
-  p->o_sw = take(s.d);
+  p->o_sw = take(std::max(s.d, s.nw));
   p->o_sb = take(1);
   p->o_dvec = take(Mp);
   p->o_vhat_p = take(Mp * s.dimp + (int64_t)s.P * Mp);  // mu2 sits right behind vhat_p (one TMA transaction)
@@ -575,7 +586,7 @@ static int launch_predict(cudaStream_t st, const PredictArgs& a) {
 // The fused backward kernel covers P = 1 and shapes whose [Mp x 32] tile pair fits in shared memory.
 static int fused_red_sep(const Shape& s) { return (s.Mp / 8) < 2 * ZB_WARPS ? 1 : 0; }
 static bool fused_bwd_ok(const Shape& s) {
-  return s.P == 1 && s.dimp <= 16 && (s.Mp / 8) <= ZB_WARPS * ZB_SLOTS &&
+  return s.P == 1 && s.proj == 0 && s.dimp <= 16 && (s.Mp / 8) <= ZB_WARPS * ZB_SLOTS &&
          zb3_smem_bytes(s.Mp, s.dimp, fused_red_sep(s)) <= 227 * 1024 && getenv("GPFY_NO_FUSED_BWD") == nullptr;
 }
 
@@ -629,7 +640,7 @@ static int run_prologue(cudaStream_t st, const GpfyDesc* desc, const Plan& p, do
   PrepArgs pa;
   pa.w = w; pa.b = b; pa.v = v; pa.eig = eig; pa.vhat = vhat;
   pa.sw = ws + p.o_sw; pa.sb = ws + p.o_sb; pa.dvec = need_model ? ws + p.o_dvec : nullptr; pa.vhat_p = ws + p.o_vhat_p;
-  pa.d = s.d; pa.dim = s.dim; pa.dimp = s.dimp; pa.M = s.M; pa.Mp = Mp; pa.scalar_w = desc->weight_mode == GPFY_W_SCALAR;
+  pa.d = s.d; pa.dim = s.dim; pa.dimp = s.dimp; pa.M = s.M; pa.Mp = Mp; pa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; pa.proj = s.proj;
   pa.deg = deg;
   GPFY_K(prep_kernel, 32, 256, 0, st, pa);
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_linv, 0, Mp2 * 8, st));
@@ -722,7 +733,7 @@ int gpfy_elbo_packed_layout(const GpfyDesc* desc, GpfyElboLayout* out) {
   out->d_eig = o; o += s.F;
   out->d_vhat = o; o += (int64_t)s.M * s.dim;
   out->d_lcat = o; o += s.lsize;
-  out->d_w = o; o += desc->weight_mode == GPFY_W_SCALAR ? 1 : s.d;
+  out->d_w = o; o += s.nw;
   out->d_b = o; o += 1;
   out->d_v = o; o += 1;
   out->d_sigma2 = o; o += 1;
@@ -769,7 +780,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     // one fused kernel (two CTAs per SM): the zonal values stay in shared memory
     FeaturesArgs fa;
     ZonalArgs& za = fa.z;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
     za.X = X; za.xcols = apply_to_sphere ? s.d : s.dim; za.apply_to_sphere = apply_to_sphere;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = n;
@@ -783,7 +794,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     ZonalArgs za;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
     za.X = X + c0 * (apply_to_sphere ? s.d : s.dim);
     za.xcols = apply_to_sphere ? s.d : s.dim;
     za.apply_to_sphere = apply_to_sphere;
@@ -847,7 +858,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
@@ -898,7 +909,8 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
       zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
       zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p;
-      zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.P = s.P; zb.npts = npts;
+      zb.Mp = Mp; zb.M = s.M; zb.d = s.sd; zb.P = s.P; zb.npts = npts;
+      zb.X = X + c0 * s.d; zb.W = ws + p.o_sw; zb.xcols = s.d; zb.proj = s.proj;
       zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.accumulate = 1;
       zb.deg = deg; zb.rc = rc;
       GPFY_TIMED(TK_ZONAL_BWD, st);
@@ -974,8 +986,8 @@ int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity
   FinalArgs fa;
   fa.partials = ws + p.o_partials; fa.nblocks = (int)p.nblocks_c; fa.npart = p.npart;
   fa.dd = ws + p.o_dd; fa.dvec = ws + p.o_dvec; fa.eig = eig; fa.w = w; fa.b = b; fa.v = variance;
-  fa.M = s.M; fa.d = s.d; fa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; fa.deg = deg; fa.packed = packed; fa.lay = lay;
-  GPFY_K(finalize_kernel, 1, 256, 0, st, fa);
+  fa.M = s.M; fa.d = s.d; fa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; fa.proj = s.proj; fa.nw = s.nw; fa.deg = deg; fa.packed = packed; fa.lay = lay;
+  GPFY_K(finalize_kernel, 1, 256, p.npart * 8, st, fa);
   return GPFY_OK;
 }
 
@@ -1028,7 +1040,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
+    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
@@ -1061,7 +1073,7 @@ int gpfy_to_sphere(void* stream, const GpfyDesc* desc, int64_t n, const double* 
   if (n == 0) return GPFY_OK;
   const unsigned grid = (unsigned)((n + 127) / 128);
   const int sc = desc->weight_mode == GPFY_W_SCALAR;
-  GPFY_DISPATCH_DIMP(s.dimp, GPFY_K(to_sphere_kernel<DIMP>, grid, 128, 0, st, X, s.d, s.dim, w, sc, b, n, xs, r));
+  GPFY_DISPATCH_DIMP(s.dimp, GPFY_K(to_sphere_kernel<DIMP>, grid, 128, 0, st, X, s.d, s.dim, w, sc, b, n, xs, r, s.proj));
   return GPFY_OK;
 }
 

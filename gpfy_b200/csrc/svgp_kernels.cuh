@@ -21,6 +21,7 @@ struct ZonalArgs {
   const double* X;      // [n, xcols] row-major; xcols = d (raw) or dim (already on the sphere)
   int xcols;
   int apply_to_sphere;  // 1: scale by sw, append sb, normalise;  0: X rows are unit vectors of length dim
+  int proj;             // > 0: sw is a [xcols, proj] projection matrix W and u = x W (spherical.py:225-226)
   const double* sw;     // [d] sqrt(weight_variances) (already broadcast in scalar mode)
   const double* sb;     // [1] sqrt(bias_variance)
   const double* vhat_p; // [Mp, DIMP] zero padded
@@ -45,18 +46,36 @@ struct ZonalArgs {
 
 template <int DIMP>
 __device__ __forceinline__ double load_point(const double* __restrict__ X, int xcols, int apply, const double* sw,
-                                             const double* sb, int dim, int64_t n, double (&xh)[DIMP]) {
+                                             const double* sb, int dim, int64_t n, double (&xh)[DIMP], int proj = 0) {
   const double* x = X + n * (int64_t)xcols;
   double r = 1.0;
   if (apply) {
     double ss = 0.0;
+    if (proj > 0) {                           // u = x W, W [xcols, proj]   spherical.py:225-226
 #pragma unroll
-    for (int c = 0; c < DIMP; ++c) {
-      double u = 0.0;
-      if (c < xcols) u = x[c] * sw[c];       // X * sqrt(w)              spherical.py:228
-      else if (c == xcols) u = sb[0];         // bias = sqrt(b)           spherical.py:245-247
-      xh[c] = u;
-      ss += u * u;
+      for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < xcols; ++j) {
+        const double xj = x[j];
+        const double* wr = sw + j * proj;
+#pragma unroll
+        for (int c = 0; c < DIMP; ++c)
+          if (c < proj) xh[c] = fma(xj, wr[c], xh[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < DIMP; ++c) {
+        if (c == proj) xh[c] = sb[0];         // bias = sqrt(b)           spherical.py:245-247
+        ss += xh[c] * xh[c];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < DIMP; ++c) {
+        double u = 0.0;
+        if (c < xcols) u = x[c] * sw[c];       // X * sqrt(w)              spherical.py:228
+        else if (c == xcols) u = sb[0];         // bias = sqrt(b)           spherical.py:245-247
+        xh[c] = u;
+        ss += u * u;
+      }
     }
     r = sqrt(ss);                             // spherical.py:248
 #pragma unroll
@@ -86,7 +105,7 @@ __global__ void __launch_bounds__(256) zonal_fwd_kernel(ZonalArgs a) {
   double xh[DIMP];
   double r = 1.0;
   if (valid) {
-    r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
+    r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh, a.proj);
     if (warp == 0) {
       if (a.R) a.R[n] = r;
       if (a.XH) {
@@ -350,7 +369,10 @@ struct ZonalBwdArgs {
   const double* XH;     // [npts][DIMP]
   const double* R;
   const double* vhat_p; // [Mp][DIMP], mu2 [P][Mp] right behind it
-  int Mp, M, d, P;
+  int Mp, M, d, P;      // d = sphere dim (index of the bias coordinate)
+  const double* X;      // raw rows [npts][xcols] and W [xcols][proj]: only read for a projection kernel (proj > 0)
+  const double* W;
+  int xcols, proj;
   int64_t npts;
   double* partials;     // [npts / 32][npart]; PART_DB and PART_DW.. written here
   int npart;
@@ -462,16 +484,44 @@ __global__ void __launch_bounds__(256, 2) zonal_bwd_kernel(ZonalBwdArgs a) {
       for (int c = 0; c < DIMP; ++c) {
         const double du = (dxh[c] - xh[c] * dot) / r + dr * xh[c];
         const double u = xh[c] * r;
-        if (c < a.d) part[1 + c] = du * u;   // d w_j = sum du_j x_j / (2 sqrt w_j) = sum du_j u_j / (2 w_j)
+        if (c < a.d) part[1 + c] = a.proj > 0 ? du : du * u;   // d w_j = sum du_j x_j / (2 sqrt w_j) = sum du_j u_j / (2 w_j)
         else if (c == a.d) part[0] = du;     // d b   = sum du_dim / (2 sqrt b)
       }
     }
+    if (a.proj > 0) {
+      // d W[j][k] = sum_n x_nj du_nk (VJP of X @ W, spherical.py:225-226); part[1 + k] holds du_k here.  The du
+      // go through shared memory so that the (j, k) loops stay rolled (this is the rarely used path).
+      __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 1 + DIMP; ++k) {
-      const double s = warp_sum(part[k]);
-      if (lane == 0 && k < 1 + a.d) {
-        double* dst = a.partials + (int64_t)blockIdx.x * a.npart + (k == 0 ? PART_DB : PART_DW + k - 1);
-        *dst = a.accumulate ? *dst + s : s;
+      for (int c = 0; c < DIMP; ++c) red[c * 32 + lane] = c < a.d ? part[1 + c] : 0.0;
+      __syncwarp();
+      {
+        const double s0 = warp_sum(part[0]);
+        if (lane == 0) {
+          double* dst = a.partials + (int64_t)blockIdx.x * a.npart + PART_DB;
+          *dst = a.accumulate ? *dst + s0 : s0;
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < a.xcols; ++j) {
+        const double xj = valid ? a.X[n * a.xcols + j] : 0.0;
+#pragma unroll 1
+        for (int k = 0; k < a.proj; ++k) {
+          const double sv = warp_sum(xj * red[k * 32 + lane]);
+          if (lane == 0) {
+            double* dst = a.partials + (int64_t)blockIdx.x * a.npart + PART_DW + j * a.proj + k;
+            *dst = a.accumulate ? *dst + sv : sv;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 1 + DIMP; ++k) {
+        const double s = warp_sum(part[k]);
+        if (lane == 0 && k < 1 + a.d) {
+          double* dst = a.partials + (int64_t)blockIdx.x * a.npart + (k == 0 ? PART_DB : PART_DW + k - 1);
+          *dst = a.accumulate ? *dst + s : s;
+        }
       }
     }
   }
@@ -508,16 +558,16 @@ __global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
 // to_sphere only (spherical.py:214-249); sqrt of the variances is taken once per block in shared memory
 template <int DIMP>
 __global__ void to_sphere_kernel(const double* X, int d, int dim, const double* w, int scalar_w, const double* b, int64_t n,
-                                 double* xs, double* r) {
-  __shared__ double ssw[DIMP];
+                                 double* xs, double* r, int proj) {
+  __shared__ double ssw[64];
   __shared__ double ssb;
-  if (threadIdx.x < d) ssw[threadIdx.x] = sqrt(w[scalar_w ? 0 : threadIdx.x]);
+  if (proj == 0 && threadIdx.x < d) ssw[threadIdx.x] = sqrt(w[scalar_w ? 0 : threadIdx.x]);
   if (threadIdx.x == 0) ssb = sqrt(b[0]);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double xh[DIMP];
-  const double rr = load_point<DIMP>(X, d, 1, ssw, &ssb, dim, i, xh);
+  const double rr = load_point<DIMP>(X, d, 1, proj > 0 ? w : ssw, &ssb, dim, i, xh, proj);
   r[i] = rr;
 #pragma unroll
   for (int c = 0; c < DIMP; ++c)

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
     for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
     double r = 1.0;
     if (n < a.npts) {
-      r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
+      r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh, a.proj);
       if (a.R) a.R[n] = r;
       if (a.XH) {
 #pragma unroll
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
     for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
     double r = 1.0;
     if (n < a.npts) {
-      r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh);
+      r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh, a.proj);
       if (args.r_out) args.r_out[n] = r;
     }
     double* x = xs + (it & 1) * 32 * DIMP;

@@ -122,7 +122,7 @@ def finish_elbo(summed, n_total, dataset_size, kl, dkl_mu, dkl_sigma, layout_sli
     return value, g
 
 
-def layout_slices(layout, M, P, F, d, dim, lsize, scalar_w):
+def layout_slices(layout, M, P, F, d, dim, lsize, scalar_w, nw=None):
     L = layout
     return {
         "data_term": slice(L.data_term, L.data_term + 1),
@@ -131,7 +131,7 @@ def layout_slices(layout, M, P, F, d, dim, lsize, scalar_w):
         "eig": slice(L.d_eig, L.d_eig + F),
         "vhat": slice(L.d_vhat, L.d_vhat + M * dim),
         "lcat": slice(L.d_lcat, L.d_lcat + lsize),
-        "w": slice(L.d_w, L.d_w + (1 if scalar_w else d)),
+        "w": slice(L.d_w, L.d_w + (nw if nw is not None else (1 if scalar_w else d))),
         "b": slice(L.d_b, L.d_b + 1),
         "v": slice(L.d_v, L.d_v + 1),
         "sigma2": slice(L.d_sigma2, L.d_sigma2 + 1),

@@ -70,9 +70,11 @@ class GP:
         kp = param.params[kernel.name]
         vhat, lcat, m = sh._cat(param)
         P = q.mu(param).shape[1]
-        hp = _runtime.hot_path(vhat.shape[1] - 1, m, num_outputs=P, kernel_order=kernel.order,
+        wv = kp["weight_variances"]
+        input_dim = int(np.shape(wv)[0]) if np.ndim(wv) >= 1 else vhat.shape[1] - 1
+        hp = _runtime.hot_path(input_dim, m, num_outputs=P, kernel_order=kernel.order,
                                likelihood=lik._kind if lik is not None else "gaussian", q_kind=q._q_kind,
-                               weight_mode=kernel._weight_mode(param))
+                               weight_mode=kernel._weight_mode(param), projection_dim=kernel._projection_dim(param))
         args = (kp["weight_variances"], kp["bias_variance"], kp["variance"], kernel.eigenvalues(param, sh.levels), vhat, lcat,
                 q.mu(param), q.cov_part(param))
         return hp, args

@@ -49,12 +49,13 @@ class HotPath:
     (SphericalHarmonics, kernel, q, likelihood) in the reference."""
 
     def __init__(self, input_dim, m, num_outputs=1, kernel_order=1, likelihood="gaussian", q_kind="tril",
-                 weight_mode="ard", device=None):
+                 weight_mode="ard", device=None, projection_dim=0):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.m = [int(v) for v in m]
         self.input_dim = int(input_dim)
-        self.dim = self.input_dim + 1
+        self.projection_dim = int(projection_dim) if weight_mode == "projection" else 0
+        self.dim = (self.projection_dim or self.input_dim) + 1
         self.M = int(sum(self.m))
         self.P = int(num_outputs)
         self.F = len(self.m)
@@ -64,7 +65,8 @@ class HotPath:
             input_dim, self.m, num_outputs, kernel_order,
             _lib.LIK_GAUSSIAN if likelihood == "gaussian" else _lib.LIK_BERNOULLI,
             _lib.Q_TRIL if q_kind == "tril" else _lib.Q_FULLCOV,
-            _lib.W_SCALAR if self.scalar_w else _lib.W_ARD)
+            {"scalar": _lib.W_SCALAR, "projection": _lib.W_PROJECTION}.get(weight_mode, _lib.W_ARD), self.projection_dim)
+        self.nw = self.input_dim * self.projection_dim if self.projection_dim else (1 if self.scalar_w else self.input_dim)
         self.layout = _lib.GpfyElboLayout()
         _lib.check(self.lib.gpfy_elbo_packed_layout(ctypes.byref(self.desc), ctypes.byref(self.layout)))
         self._ws = {}
@@ -190,7 +192,7 @@ class HotPath:
             "eig": packed[L.d_eig:L.d_eig + F],
             "vhat": packed[L.d_vhat:L.d_vhat + M * dim].view(M, dim),
             "lcat": packed[L.d_lcat:L.d_lcat + self.lsize],
-            "w": packed[L.d_w:L.d_w + (1 if self.scalar_w else d)],
+            "w": packed[L.d_w:L.d_w + self.nw],
             "b": packed[L.d_b],
             "v": packed[L.d_v],
             "sigma2": packed[L.d_sigma2],

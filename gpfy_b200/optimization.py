@@ -84,7 +84,7 @@ def elbo_value_and_grad(param: Param, m, q, lik, train_data, dataset_size: int =
     n_local = int(np.shape(train_data[0])[0])
     n_total = int(n_total) if n_total is not None else n_local
     kl, dkl_mu, dkl_sig = q.prior_KL_and_grad(param)
-    sl = gd.layout_slices(hp.layout, hp.M, hp.P, hp.F, hp.input_dim, hp.dim, hp.lsize, hp.scalar_w)
+    sl = gd.layout_slices(hp.layout, hp.M, hp.P, hp.F, hp.input_dim, hp.dim, hp.lsize, hp.scalar_w, hp.nw)
     value, g = gd.finish_elbo(summed, n_total, dataset_size, kl, dkl_mu, dkl_sig, sl)
     kernel, sh = m.kernel, m._sh
     kp = param.params[kernel.name]

@@ -60,17 +60,20 @@ class Spherical:
         eigval = param.constants.get(self.name, {}).get("eigenvalues", np.zeros(len(levels)))
         return np.asarray(eigval)[levels]
 
-    # ---- spherical.py:214-249, 384-400: evaluated on the device ----
+    # ---- spherical.py:214-249, 384-400: evaluated on the device (ARD, scalar and [d, p] projection weights) ----
     def _weight_mode(self, param: Param) -> str:
         w = param.params[self.name]["weight_variances"]
-        if np.ndim(w) == 2:
-            raise _runtime.GpfyError("linear-projection weights [d, p] are not built yet (SURVEY.md §8f); use ARD or scalar weights")
-        return "scalar" if np.ndim(w) == 0 else "ard"
+        return "projection" if np.ndim(w) == 2 else ("scalar" if np.ndim(w) == 0 else "ard")
+
+    def _projection_dim(self, param: Param) -> int:
+        w = param.params[self.name]["weight_variances"]
+        return int(np.shape(w)[1]) if np.ndim(w) == 2 else 0
 
     def to_sphere(self, param: Param, X):
         kp = param.params[self.name]
         d = int(np.shape(X)[-1])
-        hp = _runtime.hot_path(d, [1], weight_mode=self._weight_mode(param), kernel_order=self.order)
+        hp = _runtime.hot_path(d, [1], weight_mode=self._weight_mode(param), kernel_order=self.order,
+                               projection_dim=self._projection_dim(param))
         return hp.to_sphere(X, kp["weight_variances"], kp["bias_variance"])
 
     def K_diag(self, param: Param, X):

@@ -137,7 +137,8 @@ class SphericalHarmonics:
     def _features(self, param: Param, kernel, x, degree_scale):
         vhat, lcat, m = self._cat(param)
         kp = param.params[kernel.name]
-        hp = _runtime.hot_path(int(np.shape(x)[-1]), m, weight_mode=kernel._weight_mode(param), kernel_order=kernel.order)
+        hp = _runtime.hot_path(int(np.shape(x)[-1]), m, weight_mode=kernel._weight_mode(param), kernel_order=kernel.order,
+                               projection_dim=kernel._projection_dim(param))
         return hp.features(x, vhat, lcat, w=kp["weight_variances"], b=kp["bias_variance"], degree_scale=degree_scale, mul_r=True)[0]
 
     def Kuf(self, param: Param, kernel, x):

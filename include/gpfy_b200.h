@@ -50,7 +50,7 @@ enum {
 
 enum { GPFY_LIK_GAUSSIAN = 0, GPFY_LIK_BERNOULLI = 1 };
 enum { GPFY_Q_TRIL = 0, GPFY_Q_FULLCOV = 1 };
-enum { GPFY_W_ARD = 0, GPFY_W_SCALAR = 1 };
+enum { GPFY_W_ARD = 0, GPFY_W_SCALAR = 1, GPFY_W_PROJECTION = 2 };
 
 /* POD, versioned.  Mirrors the static (non-pytree) fields the reference keeps on its dataclasses:
  * SphericalHarmonics.num_frequencies / phase_truncation (spherical_harmonics.py:75-76, via m[]),
@@ -58,7 +58,8 @@ enum { GPFY_W_ARD = 0, GPFY_W_SCALAR = 1 };
 typedef struct GpfyDesc {
   uint32_t struct_size; /* sizeof(GpfyDesc) */
   uint32_t abi_version; /* GPFY_ABI_VERSION */
-  int32_t input_dim;    /* d = X.shape[-1]; ambient dim = d + 1 (bias always appended, spherical.py:243-249) */
+  int32_t input_dim;    /* d = X.shape[-1]; ambient dim = sphere_dim + 1 (bias always appended, spherical.py:243-249),
+                           sphere_dim = projection_dim if > 0 else d */
   int32_t num_degrees;  /* F; degrees are 0..F-1 (spherical_harmonics.py:78-80) */
   int32_t m[GPFY_MAX_DEGREES]; /* rows of V_l = min(phase_truncation, N(dim, l)); M = sum m[l] */
   int32_t num_outputs;  /* P = num_independent_processes (variational.py:86) */
@@ -66,9 +67,10 @@ typedef struct GpfyDesc {
   int32_t likelihood;   /* GPFY_LIK_* (likelihoods.py:188-220 / :254-278) */
   int32_t q_kind;       /* GPFY_Q_TRIL: Sigma holds L, q = N(mu, L L^T) (variational.py:243-351);
                            GPFY_Q_FULLCOV: Sigma is the covariance (variational.py:354-464) */
-  int32_t weight_mode;  /* GPFY_W_ARD: weight_variances [d]; GPFY_W_SCALAR: one value (spherical.py:110-114) */
-  int32_t reserved;
-  double alpha;         /* (dim - 2) / 2 (spherical_harmonics.py:149) */
+  int32_t weight_mode;  /* GPFY_W_ARD: weight_variances [d]; GPFY_W_SCALAR: one value (spherical.py:110-114);
+                           GPFY_W_PROJECTION: a [d, p] linear projection X @ W, identity bijector (spherical.py:110-117,225-226) */
+  int32_t projection_dim; /* p for GPFY_W_PROJECTION, else 0 */
+  double alpha;         /* (ambient dim - 2) / 2 (spherical_harmonics.py:149) */
 } GpfyDesc;
 
 /* Which scratch size to ask for. */
@@ -85,7 +87,7 @@ typedef struct GpfyElboLayout {
   int64_t d_eig;     /* [F]   w.r.t. kernel.eigenvalues lambda_l      (spherical_harmonics.py:335,385) */
   int64_t d_vhat;    /* [M, dim]                                      (spherical_harmonics.py:308) */
   int64_t d_lcat;    /* [sum m_l^2], lower triangles valid            (spherical_harmonics.py:316) */
-  int64_t d_w;       /* [d] or [1]                                    (spherical.py:228) */
+  int64_t d_w;       /* [d], [1] or [d, p]                            (spherical.py:225-228) */
   int64_t d_b;       /* [1] bias_variance                             (spherical.py:245-246) */
   int64_t d_v;       /* [1] kernel variance                           (spherical_harmonics.py:362, spherical.py:400) */
   int64_t d_sigma2;  /* [1] Gaussian noise variance; 0 for Bernoulli  (likelihoods.py:210-218) */

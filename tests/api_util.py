@@ -21,7 +21,8 @@ def objects_from_golden(g):
     q = VariationalDistributionTriL() if str(g["meta_q"]).endswith("TriL") else VariationalDistributionFullCovariance()
     sh = SphericalHarmonics(F, phase_truncation=T)
     m = GP(kernel).conditional(sh, q)
-    param = m.init(0, input_dim=d, num_independent_processes=P, likelihood=lik, sh_features=sh, variational_dist=q)
+    proj = int(g["meta_projection_dim"]) or None
+    param = m.init(0, input_dim=d, num_independent_processes=P, projection_dim=proj, likelihood=lik, sh_features=sh, variational_dist=q)
     p = {k: (dict(v) if isinstance(v, dict) else v) for k, v in param.params.items()}
     kp = dict(p[kernel.name])
     for k in list(kp):
@@ -38,5 +39,5 @@ def objects_from_golden(g):
     if "const_eigenvalues" in g:
         consts[kernel.name] = {"eigenvalues": np.array(g["const_eigenvalues"])}
     param = param.replace(params=p, constants=consts)
-    return dict(kernel=kernel, lik=lik, q=q, sh=sh, m=m, param=param, init_param=m.init(0, input_dim=d, num_independent_processes=P,
+    return dict(kernel=kernel, lik=lik, q=q, sh=sh, m=m, param=param, init_param=m.init(0, input_dim=d, num_independent_processes=P, projection_dim=proj,
                                                                                        likelihood=lik, sh_features=sh, variational_dist=q))

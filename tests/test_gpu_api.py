@@ -13,7 +13,7 @@ from tests.golden_util import CASES, golden_pack, load, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-API_CASES = [c for c in CASES if c != "d6_proj3_arccos"]
+API_CASES = list(CASES)
 
 
 def _np(t):

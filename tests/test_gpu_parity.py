@@ -13,7 +13,7 @@ from tests.golden_util import CASES, golden_pack, load, rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
-ARD_CASES = [c for c in CASES if c != "d6_proj3_arccos"]  # [d, p] projection weights: host pre-multiply (next row)
+ARD_CASES = list(CASES)  # ARD, scalar and [d, p] projection weights (spherical.py:110-117, 225-228)
 
 
 def _resolved(name):
@@ -31,7 +31,8 @@ def _hot(pack, g):
     m = [v.shape[0] for v in pack["V"]]
     return HotPath(int(g["meta_input_dim"]), m, num_outputs=pack["mu"].shape[1], kernel_order=pack["order"],
                    likelihood=pack["lik"], q_kind="tril" if "Lq" in pack else "fullcov",
-                   weight_mode="scalar" if np.ndim(pack["w"]) == 0 else "ard")
+                   weight_mode={0: "scalar", 1: "ard", 2: "projection"}[np.ndim(pack["w"])],
+                   projection_dim=pack["w"].shape[1] if np.ndim(pack["w"]) == 2 else 0)
 
 
 def _cat(pack):
@@ -86,7 +87,7 @@ def test_elbo_value_and_gradients_match_oracle(name):
     assert rel_err(out["mu"], og["mu"]) < TOL
     assert rel_err(out["sigma"], og["Lq"] if "Lq" in og else og["Sigma"]) < TOL
     assert rel_err(out["eig"], og["eig"]) < TOL
-    assert rel_err(out["w"], np.atleast_1d(og["w"])) < TOL
+    assert rel_err(out["w"], np.atleast_1d(og["w"]).ravel()) < TOL
     assert rel_err(out["b"], og["b"]) < TOL
     assert rel_err(out["v"], og["v"]) < TOL
     if "sigma2" in og:
