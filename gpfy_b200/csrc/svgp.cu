@@ -506,6 +506,7 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
     ZonalFwd2Args fa;
     fa.z = a;
     fa.mt = make_monic(0.5 * a.rc.two_alpha);
+    { const char* e = getenv("GPFY_ZF_DBG"); fa.dbg = e ? atoi(e) : 0; }
     const int pmax = a.P == 1 ? 1 : (a.P == 2 ? 2 : 4);
     const int smem = zf2_smem_bytes(a.Mp, DIMP, a.P, a.mz != nullptr, pmax);
     const unsigned pgrid = std::min(grid, (unsigned)(2 * device_sms()));  // persistent: two CTAs per SM

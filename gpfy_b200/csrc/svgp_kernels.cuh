@@ -78,8 +78,9 @@ __device__ __forceinline__ double load_point(const double* __restrict__ X, int x
       }
     }
     r = sqrt(ss);                             // spherical.py:248
+    const double rinv = 1.0 / r;              // spherical.py:249 (one reciprocal: <= 1 ulp from the division)
 #pragma unroll
-    for (int c = 0; c < DIMP; ++c) xh[c] = xh[c] / r;  // spherical.py:249
+    for (int c = 0; c < DIMP; ++c) xh[c] = xh[c] * rinv;
   } else {
 #pragma unroll
     for (int c = 0; c < DIMP; ++c) xh[c] = (c < dim) ? x[c] : 0.0;

@@ -51,25 +51,26 @@ __device__ __forceinline__ void monic_uniform(const double* beta, int l, const d
 #pragma unroll
   for (int u = 0; u < NV; ++u) { a[u] = 1.0; b[u] = t[u]; }
   const int nd = (l - 2 - (l & 1)) >> 1;
+  double b0 = beta[2], b1 = beta[3];   // coefficients are fetched one trip ahead of their use
 #pragma unroll 1
   for (int j = 0; j < nd; ++j) {
-    const double b0 = beta[2 * j + 2], b1 = beta[2 * j + 3];
+    const double nb0 = beta[2 * j + 4], nb1 = beta[2 * j + 5];
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       a[u] = fma(t[u], b[u], -b0 * a[u]);
       b[u] = fma(t[u], a[u], -b1 * b[u]);
     }
+    b0 = nb0;
+    b1 = nb1;
   }
-  if (l & 1) {
-    const double b0 = beta[l - 1], b1 = beta[l];
+  if (l & 1) {   // after nd trips (b0, b1) = (beta[l - 1], beta[l])
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       p2[u] = b[u];
       p1[u] = fma(t[u], b[u], -b0 * a[u]);
       p[u] = fma(t[u], p1[u], -b1 * b[u]);
     }
-  } else {
-    const double b0 = beta[l];
+  } else {       // (b0, b1) = (beta[l], beta[l + 1])
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       p2[u] = a[u];

@@ -9,13 +9,16 @@
 
 namespace gpfy {
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 struct ZonalFwd2Args {
   ZonalArgs z;
   MonicTab mt;  // parameter alpha
+  int dbg;      // development: 1 = skip the Z stores
 };
 
 static inline int zf2_smem_bytes(int Mp, int dimp, int P, bool with_mz, int pmax) {
-  int dbl = Mp * dimp + (with_mz ? P * Mp : 0) + 2 * 32 * dimp + 2 * 8 * pmax * 32 + 2 * 32 + GPFY_MAX_DEGREES + 2;
+  int dbl = Mp * dimp + (with_mz ? P * Mp : 0) + 2 * 32 * dimp + 2 * 8 * pmax * 32 + 2 * 32 + 2 * GPFY_MAX_DEGREES + 8;
   return dbl * 8 + Mp * 4 + 16;
 }
 
@@ -36,7 +39,8 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
   double* red = xs + 2 * 32 * DIMP;                    // [2][8][PMAX][32]
   double* rs = red + 2 * 8 * PMAX * 32;                // [2][32] radii of the tile's points
   double* leads = rs + 2 * 32;                         // [MAX_DEGREES + 2]
-  int* rowdeg = reinterpret_cast<int*>(leads + GPFY_MAX_DEGREES + 2);  // [Mp]
+  double* betas = leads + GPFY_MAX_DEGREES + 2;        // [MAX_DEGREES + 6] recurrence coefficients (read ahead)
+  int* rowdeg = reinterpret_cast<int*>(betas + GPFY_MAX_DEGREES + 6);  // [Mp]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -54,6 +58,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
     rowdeg[i] = l;
   }
   for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) leads[i] = args.mt.lead[i];
+  for (int i = tid; i < GPFY_MAX_DEGREES + 6; i += 256) betas[i] = i < GPFY_MAX_DEGREES + 2 ? args.mt.beta[i] : 0.0;
 
   // warp 0, lane = point: onto the sphere (spherical.py:214-249); coordinates to shared memory, r and xhat to HBM
   auto project_tile = [&](int it) {
@@ -110,6 +115,14 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
   for (int it = 0; it < n_my; ++it) {
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
     const double* x = xs + (it & 1) * 32 * DIMP;
+    if (warp == 0 && it + 1 < n_my) {  // the next tile's rows are on their way to L2 while this tile is computed
+      const int64_t nn = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 32 + lane;
+      if (nn < a.npts) {
+        prefetch_l2(a.X + nn * a.xcols);
+        prefetch_l2(a.X + nn * a.xcols + a.xcols - 1);
+        if (a.Yg) prefetch_l2(a.Yg + nn);
+      }
+    }
     double xb[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
@@ -122,7 +135,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
 #pragma unroll
       for (int u = 0; u < 8; ++u) mzacc[p][u] = 0.0;
 
-    for (int rt = warp; rt < ntile; rt += 8) {
+    for (int rt = 7 - warp; rt < ntile; rt += 8) {  // warp 0 (which also projects the points) gets the short end
       const int row = rt * 8 + g;
       double t[8];
 #pragma unroll
@@ -137,18 +150,19 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
       const int lo = rowdeg[rt * 8], hi = rowdeg[rt * 8 + 7];
       double p[8], p1[8], p2[8], z[8];
       if (lo == hi && lo >= 1) {
-        monic_uniform<8>(args.mt.beta, lo, t, p, p1, p2);
+        monic_uniform<8>(betas, lo, t, p, p1, p2);
         const double ld = leads[lo];
 #pragma unroll
         for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
       } else {
         const int lmax = __reduce_max_sync(0xffffffffu, l);
-        monic_mixed<8>(args.mt.beta, l, lmax, t, p, p1, p2);
+        monic_mixed<8>(betas, l, lmax, t, p, p1, p2);
         const double ld = l >= 1 ? leads[l] : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
       }
       if (row < a.M) {
+        if (!(args.dbg & 1))
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int64_t n0 = p0 + 8 * nt + 2 * t4;
@@ -216,7 +230,7 @@ constexpr int FT_LD = 32;
 __device__ __forceinline__ int ft_at(int row, int pt) { return row * FT_LD + (pt ^ ((row & 3) << 2)); }
 
 static inline int ft_smem_bytes(int Mp, int dimp) {
-  int dbl = Mp * dimp + Mp * FT_LD + 2 * 32 * dimp + 2 * 32 + 2 * (GPFY_MAX_DEGREES + 2);
+  int dbl = Mp * dimp + Mp * FT_LD + 2 * 32 * dimp + 2 * 32 + 3 * (GPFY_MAX_DEGREES + 2) + 4;
   return dbl * 8 + Mp * 4 + (GPFY_MAX_DEGREES + 1) * 4 + 16;
 }
 
@@ -233,7 +247,8 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
   double* rs = xs + 2 * 32 * DIMP;            // [2][32]
   double* leads = rs + 2 * 32;                // [MAX_DEGREES + 2]
   double* scl = leads + GPFY_MAX_DEGREES + 2; // [MAX_DEGREES + 2] per-degree output scale
-  int* rowdeg = reinterpret_cast<int*>(scl + GPFY_MAX_DEGREES + 2);  // [Mp]
+  double* betas = scl + GPFY_MAX_DEGREES + 2; // [MAX_DEGREES + 6]
+  int* rowdeg = reinterpret_cast<int*>(betas + GPFY_MAX_DEGREES + 6);  // [Mp]
   int* offs = rowdeg + Mp;                    // [F + 1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -256,6 +271,7 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
     leads[i] = args.mt.lead[i];
     scl[i] = (i < F && args.scale) ? args.scale[i] : 1.0;
   }
+  for (int i = tid; i < GPFY_MAX_DEGREES + 6; i += 256) betas[i] = i < GPFY_MAX_DEGREES + 2 ? args.mt.beta[i] : 0.0;
   if (tid == 0) {
     int o = 0;
     for (int l = 0; l < F; ++l) { offs[l] = o; o += a.deg.m[l]; }
@@ -287,6 +303,13 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
   for (int it = 0; it < n_my; ++it) {
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
     const double* x = xs + (it & 1) * 32 * DIMP;
+    if (warp == 0 && it + 1 < n_my) {
+      const int64_t nn = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 32 + lane;
+      if (nn < a.npts) {
+        prefetch_l2(a.X + nn * a.xcols);
+        prefetch_l2(a.X + nn * a.xcols + a.xcols - 1);
+      }
+    }
     // ---- phase A: zonal values of the tile into shared memory ----
     {
       double xb[KS][4];
@@ -294,7 +317,7 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
       for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) xb[ks][nt] = x[(8 * nt + g) * DIMP + 4 * ks + t4];
-      for (int rt = warp; rt < ntile; rt += 8) {
+      for (int rt = 7 - warp; rt < ntile; rt += 8) {
         const int row = rt * 8 + g;
         double t[8];
 #pragma unroll
@@ -309,13 +332,13 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
         const int lo = rowdeg[rt * 8], hi = rowdeg[rt * 8 + 7];
         double p[8], p1[8], p2[8], z[8];
         if (lo == hi && lo >= 1) {
-          monic_uniform<8>(args.mt.beta, lo, t, p, p1, p2);
+          monic_uniform<8>(betas, lo, t, p, p1, p2);
           const double ld = leads[lo];
 #pragma unroll
           for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
         } else {
           const int lmax = __reduce_max_sync(0xffffffffu, l);
-          monic_mixed<8>(args.mt.beta, l, lmax, t, p, p1, p2);
+          monic_mixed<8>(betas, l, lmax, t, p, p1, p2);
           const double ld = l >= 1 ? leads[l] : 0.0;
 #pragma unroll
           for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
