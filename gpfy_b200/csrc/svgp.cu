@@ -310,22 +310,26 @@ struct FinalArgs {
   double* packed;
   GpfyElboLayout lay;
 };
-// single block: deterministic tree over the per-block partials, then the scalar chain rules
-__global__ void finalize_kernel(FinalArgs a) {
-  extern __shared__ double sums[];  // [npart]
+// column k of the per-block partials, one block per k: deterministic tree
+__global__ void __launch_bounds__(256) partial_sums_kernel(const double* partials, int nblocks, int npart, double* out) {
   __shared__ double red[256];
-  for (int k = 0; k < a.npart; ++k) {
-    double s = 0.0;
-    for (int bI = threadIdx.x; bI < a.nblocks; bI += blockDim.x) s += a.partials[(int64_t)bI * a.npart + k];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) sums[k] = red[0];
+  const int k = blockIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  int bI = threadIdx.x;
+  for (; bI + 256 < nblocks; bI += 512) { s0 += partials[(int64_t)bI * npart + k]; s1 += partials[(int64_t)(bI + 256) * npart + k]; }
+  if (bI < nblocks) s0 += partials[(int64_t)bI * npart + k];
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
+  if (threadIdx.x == 0) out[k] = red[0];
+}
+
+// the scalar chain rules on the summed partials (a.partials = [npart] sums)
+__global__ void finalize_kernel(FinalArgs a) {
+  const double* sums = a.partials;
   if (threadIdx.x == 0) {
     a.packed[a.lay.data_term] = sums[PART_E];
     a.packed[a.lay.d_sigma2] = sums[PART_DS2];
@@ -613,13 +617,60 @@ static int launch_zonal_bwd3(cudaStream_t st, const ZonalBwd3Args& a, bool fuse_
   }
 }
 
+// C [Mp, Mp] = alpha A B + beta C for the O(M^3) parameter algebra of a step (7 products).  The big-tile GEMM
+// would put these on 6 CTAs (54 us each); here every CTA owns a 32 x 32 tile (4 warps x 16 x 16, DMMA fragments
+// straight from L2-resident operands), so an Mp = 288 product spreads over 81 CTAs.
+__global__ void __launch_bounds__(256) gemm_small_kernel(const double* __restrict__ A, const double* __restrict__ B, double* C, int Mp,
+                                                         double alpha, double beta) {
+  __shared__ double part[4][32][8];  // second K half of each 16 x 16 warp tile, added in a fixed order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const int wt = warp & 3, kh = warp >> 2;
+  const int row0 = blockIdx.y * 32 + (wt >> 1) * 16, col0 = blockIdx.x * 32 + (wt & 1) * 16;
+  const int kb = kh * (Mp / 2), ke = kb + Mp / 2;  // Mp is a multiple of 32
+  double acc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const double* a0 = A + (int64_t)(row0 + g) * Mp + t4;
+  const double* a1 = a0 + 8 * (int64_t)Mp;
+  const double* b0 = B + (int64_t)t4 * Mp + col0 + g;
+#pragma unroll 8
+  for (int k = kb; k < ke; k += 4) {
+    const double af0 = __ldg(a0 + k), af1 = __ldg(a1 + k);
+    const double bf0 = __ldg(b0 + (int64_t)k * Mp), bf1 = __ldg(b0 + (int64_t)k * Mp + 8);
+    dmma884(acc[0][0][0], acc[0][0][1], af0, bf0);
+    dmma884(acc[0][1][0], acc[0][1][1], af0, bf1);
+    dmma884(acc[1][0][0], acc[1][0][1], af1, bf0);
+    dmma884(acc[1][1][0], acc[1][1][1], af1, bf1);
+  }
+  if (kh == 1) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { part[wt][lane][4 * i + 2 * j] = acc[i][j][0]; part[wt][lane][4 * i + 2 * j + 1] = acc[i][j][1]; }
+  }
+  __syncthreads();
+  if (kh == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double2* dst = reinterpret_cast<double2*>(C + (int64_t)(row0 + 8 * i + g) * Mp + col0 + 8 * j + 2 * t4);
+        double2 v = make_double2(alpha * (acc[i][j][0] + part[wt][lane][4 * i + 2 * j]), alpha * (acc[i][j][1] + part[wt][lane][4 * i + 2 * j + 1]));
+        if (beta != 0.0) { const double2 o = *dst; v.x += beta * o.x; v.y += beta * o.y; }
+        *dst = v;
+      }
+  }
+}
+
 static int gemm_sq(cudaStream_t st, const double* A, const double* B, double* C, int Mp, double alpha, double beta, int sms) {
-  GemmArgs g;
-  g.A = A; g.lda = Mp; g.B = B; g.ldb = Mp; g.C = C; g.ldc = Mp;
-  g.m = g.n = g.k = Mp;
-  g.alpha = alpha; g.beta = beta;
-  g.psi_out = nullptr; g.ld_psi = 0;
-  return launch_gemm(st, g, sms);
+  (void)sms;
+  dim3 grid(Mp / 32, Mp / 32);
+  gemm_small_kernel<<<grid, 256, 0, st>>>(A, B, C, Mp, alpha, beta);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
 }
 
 #define GPFY_K(kernel, grid, block, smem, st, ...)    \
@@ -985,10 +1036,11 @@ int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity
   GPFY_K(dl_step2_kernel, s.F, 256, 0, st, ws + p.o_tmp1, ws + p.o_linv, packed + lay.d_lcat, Mp, deg);
   GPFY_K(reduce_dv_kernel, (8 * s.M * s.dim + 255) / 256, 256, 0, st, ws + p.o_dVpart, packed + lay.d_vhat, s.M, Mp, s.dim, s.dimp, p.KSV);
   FinalArgs fa;
-  fa.partials = ws + p.o_partials; fa.nblocks = (int)p.nblocks_c; fa.npart = p.npart;
+  GPFY_K(partial_sums_kernel, p.npart, 256, 0, st, ws + p.o_partials, (int)p.nblocks_c, p.npart, ws + p.o_tmp3);
+  fa.partials = ws + p.o_tmp3; fa.nblocks = (int)p.nblocks_c; fa.npart = p.npart;
   fa.dd = ws + p.o_dd; fa.dvec = ws + p.o_dvec; fa.eig = eig; fa.w = w; fa.b = b; fa.v = variance;
   fa.M = s.M; fa.d = s.d; fa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; fa.proj = s.proj; fa.nw = s.nw; fa.deg = deg; fa.packed = packed; fa.lay = lay;
-  GPFY_K(finalize_kernel, 1, 256, p.npart * 8, st, fa);
+  GPFY_K(finalize_kernel, 1, 32, 0, st, fa);
   return GPFY_OK;
 }
 
