@@ -152,3 +152,37 @@ def test_headline_shapes_match_oracle_on_a_sample(T, P, lik):
     fmu, fvar = hp.predict_diag(*[args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)])
     ofmu, ofvar = O.predict_diag(O.pack_to_torch(pack), O.T(args[0].cpu().numpy()))
     assert rel_err(fmu.cpu().numpy(), ofmu.numpy()) < TOL and rel_err(fvar.cpu().numpy(), ofvar.numpy()) < TOL
+
+
+@pytest.mark.parametrize("N,T,P,lik,d,F", [(1000, 30, 1, "gaussian", 8, 11), (333, 12, 2, "bernoulli", 5, 5),
+                                             (65, 30, 1, "gaussian", 8, 11), (257, 8, 1, "gaussian", 2, 6)])
+def test_results_do_not_depend_on_workspace_contents(N, T, P, lik, d, F):
+    """compute-sanitizer is closed on this pool, so uninitialised reads are hunted the other way round: the
+    caller-provided scratch is poisoned with NaN before every call; every output must stay finite and bit-identical
+    to the run on a zeroed workspace (ragged sizes, every entry point that takes scratch)."""
+    from gpfy_b200 import _lib
+    from gpfy_b200.synthetic import headline_problem
+    prob = headline_problem(N, d=d, F=F, T=T, P=P, likelihood=lik, device="cuda")
+    hp, args = prob["hot"], prob["args"]
+    X, Y, w, b, v, eig, vhat, lcat, mu, sg, s2 = args
+
+    def run_all():
+        out = hp.elbo_valgrad_packed(*args).clone()
+        fmu, fvar = hp.predict_diag(X, w, b, v, eig, vhat, lcat, mu, sg)
+        A, r = hp.features(X, vhat, lcat, w=w, b=b, degree_scale=torch.sqrt(eig * v), mul_r=True)
+        pm, pv = hp.project_q(A, mu, sg)
+        return [out, fmu.clone(), fvar.clone(), A.clone(), r.clone(), pm.clone(), pv.clone()]
+
+    def poison(val):
+        for op in (_lib.OP_FEATURES, _lib.OP_ELBO, _lib.OP_PREDICT):
+            ws = hp.workspace(N, op)
+            ws.view(torch.float64).fill_(val)
+
+    run_all()               # allocates the scratch buffers
+    poison(0.0)
+    ref = run_all()
+    poison(float("nan"))
+    got = run_all()
+    for a, b_ in zip(got, ref):
+        assert bool(torch.isfinite(a).all())
+        assert torch.equal(a, b_)
