@@ -3,8 +3,8 @@
 //
 // One persistent CTA per SM (12 warps) walks 32-point tiles of the chunk.  Per tile:
 //   load   : the [Mp x 32] slice of C = W2 Z plus the tile's xhat rows and per-point weights arrive in shared
-//            memory by cp.async + mbarrier (the GEMM stores C tile by tile, pre-swizzled: GemmArgs::c_blocked, so a tile
-//            is one contiguous slab), two tiles in flight; the replicated Vhat / mu2 panel is staged once by TMA
+//            memory by a handful of TMA bulk copies (cp.async.bulk + mbarrier complete_tx; the GEMM stores C tile by
+//            tile, pre-swizzled: GemmArgs::c_blocked, so a tile is one contiguous slab), two tiles in flight
 //   phase 1: lane = point; every warp owns three 8-row tiles (dealt on the host so that the recurrence lengths
 //            balance): t = Vhat xhat, then the monic (alpha + 1) recurrence gives BOTH
 //            d/dt C_l^alpha = 2 alpha C_{l-1}^{alpha+1} (gegenbauer.py:73-81) and, through
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
     prow[tid] = t == 255 ? -1 : (int)t * 8;
   }
   if (tid == 0) {
-    mbar_init(&bar_full[0], 32);
-    mbar_init(&bar_full[1], 32);
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
     mbar_init(&bar_done[0], ZB_WARPS);
     mbar_init(&bar_done[1], ZB_WARPS);
   }
@@ -189,16 +189,18 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
     double* cb = cbuf + buf * Mp * ZB_LD;
     double* hb = hdr + buf * HDR;
-    // The tile's [Mp][32] slab is contiguous in C: 16-byte cp.async (LDGSTS) requests from the 32 lanes of the
-    // producing warp, completion counted on bar_full (TMA bulk copies measured the same on B200).
-    const int nchunk = Mp * 16;
-    const double* src = a.C + (p0 >> 5) * (int64_t)Mp * 32;
-    for (int q = lane; q < nchunk; q += 32) cp_async16(cb + 2 * q, src + 2 * q, true);
-    for (int q = lane; q < HDR / 2; q += 32) {
-      const double* g = q < 16 ? a.wp + p0 + 2 * q : (q < 32 ? a.cq + p0 + 2 * (q - 16) : a.XH + p0 * DIMP + 2 * (q - 32));
-      cp_async16(hb + 2 * q, g, true);
-    }
-    cp_async_mbar_arrive(&bar_full[buf]);
+    // The tile's [Mp][32] slab is contiguous in C: a few TMA bulk copies (<= 32 KB each) + the header pieces, all
+    // completing on bar_full[buf].  Issuing them costs the producing (tail) warp a handful of instructions, which
+    // matters because the refill sits on the per-tile critical path (150 LDGSTS per lane cost ~5 k cycles).
+    if (lane == 0) mbar_expect_tx(&bar_full[buf], (unsigned)(Mp * 256 + HDR * 8));
+    __syncwarp();
+    const unsigned slab = (unsigned)Mp * 256u;
+    const char* src = reinterpret_cast<const char*>(a.C + (p0 >> 5) * (int64_t)Mp * 32);
+    for (unsigned off = (unsigned)lane * 16384u; off < slab; off += 32u * 16384u)
+      tma_bulk_g2s(reinterpret_cast<char*>(cb) + off, src + off, min(16384u, slab - off), &bar_full[buf]);
+    if (lane == 29) tma_bulk_g2s(hb, a.wp + p0, 256, &bar_full[buf]);
+    if (lane == 30) tma_bulk_g2s(hb + 32, a.cq + p0, 256, &bar_full[buf]);
+    if (lane == 31) tma_bulk_g2s(hb + 64, a.XH + p0 * DIMP, 32 * DIMP * 8, &bar_full[buf]);
   };
   if (warp == 0) {
     if (n_my > 0) issue_tile(0);
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(ZB_THREADS, 1) zonal_bwd3_kernel(const __grid_
       }
       __syncwarp();
       if (it + 2 < n_my) {
+        fence_proxy_async();  // generic-proxy accesses to this buffer are ordered before the async-proxy refill
         issue_tile(it + 2);
       }
       ZB_CLK(5);
