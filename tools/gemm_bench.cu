@@ -30,8 +30,9 @@ int main() {
   double t;
   t = run<0>(a, 5); printf("full              %8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
   t = run<4>(a, 5); printf("no psi            %8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
-  t = run<2>(a, 5); printf("no epilogue       %8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
+  t = run<12>(a, 5); printf("no psi, no stores %8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
+  a.c_blocked = 1; t = run<4>(a, 5); printf("no psi, blocked C %8.1f us  %5.2f TF\n", t, fl / t * 1e-6); a.c_blocked = 0;
   t = run<1>(a, 5); printf("no loads          %8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
-  t = run<3>(a, 5); printf("no loads no epi   %8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
+  t = run<13>(a, 5); printf("no loads no stores%8.1f us  %5.2f TF\n", t, fl / t * 1e-6);
   return 0;
 }
