@@ -51,30 +51,34 @@ class FillTriangular(Bijector):
     """TFP FillTriangular(upper=False) (variational.py:260): vector n(n+1)/2 -> lower [n, n] by
     concat([x[n:], reverse(x)]) reshaped [n, n] and masked to the lower band."""
 
-    @staticmethod
-    def _index_map(n):
-        m = n * (n + 1) // 2
-        x = np.arange(1, m + 1)
-        xc = np.concatenate([x[n:], x[::-1]])
-        return np.tril(xc.reshape(n, n))
+    _maps = {}
+
+    @classmethod
+    def _index_map(cls, n):
+        """(flat position in the [n, n] matrix, position in the vector) of every lower-triangular entry, cached."""
+        if n not in cls._maps:
+            m = n * (n + 1) // 2
+            x = np.arange(1, m + 1)
+            xc = np.tril(np.concatenate([x[n:], x[::-1]]).reshape(n, n))
+            ii, jj = np.nonzero(xc)
+            cls._maps[n] = (ii * n + jj, xc[ii, jj] - 1)
+        return cls._maps[n]
 
     def forward(self, x):
         x = np.asarray(x)
         m = x.shape[-1]
         n = int(round((math.sqrt(1 + 8 * m) - 1) / 2))
-        idx = self._index_map(n)
-        out = np.zeros(x.shape[:-1] + (n, n), dtype=x.dtype)
-        ii, jj = np.nonzero(idx)
-        out[..., ii, jj] = x[..., idx[ii, jj] - 1]
-        return out
+        flat, src = self._index_map(n)
+        out = np.zeros(x.shape[:-1] + (n * n,), dtype=x.dtype)
+        out[..., flat] = x[..., src]
+        return out.reshape(x.shape[:-1] + (n, n))
 
     def inverse(self, y):
         y = np.asarray(y)
         n = y.shape[-1]
-        idx = self._index_map(n)
+        flat, src = self._index_map(n)
         out = np.zeros(y.shape[:-2] + (n * (n + 1) // 2,), dtype=y.dtype)
-        ii, jj = np.nonzero(idx)
-        out[..., idx[ii, jj] - 1] = y[..., ii, jj]
+        out[..., src] = y.reshape(y.shape[:-2] + (n * n,))[..., flat]
         return out
 
     def forward_vjp(self, x, g):
