@@ -56,6 +56,8 @@ _SIGNATURES = {
     "gpfy_svgp_elbo_rows": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, ctypes.c_int64] + [_P] * 4 +
                             [_P, ctypes.c_size_t]),
     "gpfy_svgp_elbo_finish": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 6 + [_P, ctypes.c_size_t]),
+    "gpfy_inducing_basis_fwd": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, ctypes.c_int, _P, _P]),
+    "gpfy_inducing_basis_vjp": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, ctypes.c_int, _P, _P, _P]),
     "gpfy_prior_kl_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, _P]),
     "gpfy_predict_diag": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 11 + [_P, ctypes.c_size_t]),
     "gpfy_allreduce_packed": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),

@@ -23,3 +23,8 @@ def as_rng(key):
     if isinstance(key, np.random.Generator):
         return key
     return np.random.default_rng([int(k) for k in np.atleast_1d(np.asarray(key)).ravel()])
+
+
+def cuda_available():
+    import torch
+    return torch.cuda.is_available()

@@ -10,6 +10,7 @@
 #include "svgp_kernels.cuh"
 #include "zonal_bwd3.cuh"
 #include "zonal_fwd2.cuh"
+#include "basis.cuh"
 
 namespace gpfy {
 
@@ -1057,6 +1058,32 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
   GPFY_TRY(gpfy_svgp_elbo_begin(stream, desc, n, w, b, variance, eig, vhat, lcat, mu, sigma, workspace, workspace_bytes));
   GPFY_TRY(gpfy_svgp_elbo_rows(stream, desc, n, n, X, Y, variance, sigma2, workspace, workspace_bytes));
   return gpfy_svgp_elbo_finish(stream, desc, n, w, b, variance, eig, mu, packed, workspace, workspace_bytes);
+}
+
+static int basis_launch(void* stream, const GpfyDesc* desc, BasisArgs& ba) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (s.mmax > BASIS_MAX_M) { set_error("inducing-basis kernels are built for m_l <= %d (got %d): keep this degree's algebra on the host", BASIS_MAX_M, s.mmax); return GPFY_EUNSUPPORTED; }
+  ba.dim = s.dim; ba.alpha = desc->alpha; ba.deg = degree_table(desc); ba.rc = make_rec_coef(desc->alpha);
+  const int smem = basis_smem_bytes(s.mmax, s.dim);
+  GPFY_TRY(set_smem(inducing_basis_kernel, smem));
+  GPFY_K(inducing_basis_kernel, s.F, 256, smem, (cudaStream_t)stream, ba);
+  return GPFY_OK;
+}
+
+int gpfy_inducing_basis_fwd(void* stream, const GpfyDesc* desc, const double* V, int normalise, double* vhat, double* lcat) {
+  BasisArgs ba;
+  ba.V = V; ba.vhat = vhat; ba.lcat = lcat; ba.dvhat = nullptr; ba.dlcat = nullptr; ba.dV = nullptr;
+  ba.normalise = normalise; ba.vjp = 0;
+  return basis_launch(stream, desc, ba);
+}
+
+int gpfy_inducing_basis_vjp(void* stream, const GpfyDesc* desc, const double* V, const double* lcat, int normalise,
+                            const double* dvhat, const double* dlcat, double* dV) {
+  BasisArgs ba;
+  ba.V = V; ba.vhat = nullptr; ba.lcat = const_cast<double*>(lcat); ba.dvhat = dvhat; ba.dlcat = dlcat; ba.dV = dV;
+  ba.normalise = normalise; ba.vjp = 1;
+  return basis_launch(stream, desc, ba);
 }
 
 int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out) {

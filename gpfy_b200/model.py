@@ -71,7 +71,7 @@ class GP:
         vhat, lcat, m = sh._cat(param)
         P = q.mu(param).shape[1]
         wv = kp["weight_variances"]
-        input_dim = int(np.shape(wv)[0]) if np.ndim(wv) >= 1 else vhat.shape[1] - 1
+        input_dim = int(np.shape(wv)[0]) if np.ndim(wv) >= 1 else int(vhat.shape[1]) - 1
         hp = _runtime.hot_path(input_dim, m, num_outputs=P, kernel_order=kernel.order,
                                likelihood=lik._kind if lik is not None else "gaussian", q_kind=q._q_kind,
                                weight_mode=kernel._weight_mode(param), projection_dim=kernel._projection_dim(param))

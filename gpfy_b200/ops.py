@@ -244,6 +244,23 @@ class HotPath:
                                            _ptr(mean), _ptr(var), _ptr(ws), ws.numel()))
         return mean, var
 
+    def inducing_basis(self, V, normalise=True):
+        """(vhat [M, dim], lcat [sum m_l^2]) from the raw fundamental points — spherical_harmonics.py:194-239, 265-288."""
+        V = self._dev(V)
+        vhat = torch.empty((self.M, self.dim), dtype=torch.float64, device=self.device)
+        lcat = torch.empty((self.lsize,), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gpfy_inducing_basis_fwd(_stream(self.device), ctypes.byref(self.desc), _ptr(V), int(bool(normalise)),
+                                                    _ptr(vhat), _ptr(lcat)))
+        return vhat, lcat
+
+    def inducing_basis_vjp(self, V, lcat, dvhat, dlcat, normalise=True):
+        """dV [M, dim] from the cotangents of (vhat, lcat) — the reverse pass of `inducing_basis`."""
+        V, lcat, dvhat, dlcat = self._dev(V), self._dev(lcat), self._dev(dvhat), self._dev(dlcat)
+        dV = torch.empty((self.M, self.dim), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gpfy_inducing_basis_vjp(_stream(self.device), ctypes.byref(self.desc), _ptr(V), _ptr(lcat),
+                                                    int(bool(normalise)), _ptr(dvhat), _ptr(dlcat), _ptr(dV)))
+        return dV
+
     def prior_kl_valgrad(self, mu, sigma):
         """KL(q || N(0, I)), dKL/dmu [M, P], dKL/dSigma [P, M, M] (TriL) — variational.py:225-240."""
         mu, sigma = self._dev(mu), self._dev(sigma)

@@ -16,6 +16,7 @@ from .param import Param, tree_map
 def _packed(param, m, q, lik, train_data, allreduce):
     X, Y = train_data
     hp, args = m.hot_args(param, lik)
+    lcat = args[5]
     s2 = lik._sigma2(param)
     if torch.is_tensor(X) and not X.is_cuda and X.is_pinned():
         Yh = Y if torch.is_tensor(Y) else torch.as_tensor(np.asarray(Y, dtype=np.float64))
@@ -33,7 +34,7 @@ def _packed(param, m, q, lik, train_data, allreduce):
                 summed = allreduce(packed.cpu()).numpy()
         else:
             summed = packed.cpu().numpy()
-    return hp, summed
+    return hp, summed, (lcat if torch.is_tensor(lcat) else None)
 
 
 def _chol_vjp(L, dL):
@@ -45,13 +46,22 @@ def _chol_vjp(L, dL):
     return 0.5 * (S + S.T)
 
 
-def _inducing_chain(sh, param, dvhat, dlcat):
+def _inducing_chain(sh, param, dvhat, dlcat, device_basis=None):
     """d/dV_l from (dVhat_l, dL_l): V -> V / |V| -> c_l C_l(Vhat Vhat^T) + 1e-16 I -> chol
-    (spherical_harmonics.py:209-217, 265-288; gegenbauer.py:73-81).  Fixed bases: dV = dVhat."""
+    (spherical_harmonics.py:209-217, 265-288; gegenbauer.py:73-81).  Fixed bases: dV = dVhat.
+    `device_basis` = (HotPath, lcat on the device): the chain runs in `gpfy_inducing_basis_vjp`."""
     raw = [v for _, v in sorted(param.params["variational"]["inducing_features"].items())]
     names = sorted(param.params["variational"]["inducing_features"])
     alpha = param.constants["sphere"]["alpha"]
     learned = sh._learned(param)
+    if learned and device_basis is not None:
+        hp, lcat_dev = device_basis
+        dV = hp.inducing_basis_vjp(np.concatenate(raw, 0), lcat_dev, dvhat, dlcat, normalise=True).cpu().numpy()
+        out, o = {}, 0
+        for name, V in zip(names, raw):
+            out[name] = dV[o:o + V.shape[0]].copy()
+            o += V.shape[0]
+        return out
     out, o, lo = {}, 0, 0
     Ls = sh.Ls(param) if learned else None
     for n, (name, V) in enumerate(zip(names, raw)):
@@ -80,7 +90,7 @@ def elbo_value_and_grad(param: Param, m, q, lik, train_data, dataset_size: int =
     (distributed.PackedAllReduce) and the global row count `n_total`."""
     if not param._constrained:
         raise ValueError("elbo expects constrained parameters (call param.constrained())")
-    hp, summed = _packed(param, m, q, lik, train_data, allreduce)
+    hp, summed, lcat_dev = _packed(param, m, q, lik, train_data, allreduce)
     n_local = int(np.shape(train_data[0])[0])
     n_total = int(n_total) if n_total is not None else n_local
     kl, dkl_mu, dkl_sig = q.prior_KL_and_grad(param)
@@ -100,7 +110,8 @@ def elbo_value_and_grad(param: Param, m, q, lik, train_data, dataset_size: int =
     gv = grads["variational"]
     gv[q.name]["mu"] = g["mu"].reshape(hp.M, hp.P)
     gv[q.name]["Sigma"] = g["sigma"].reshape(hp.P, hp.M, hp.M)
-    gv["inducing_features"] = _inducing_chain(sh, param, g["vhat"].reshape(hp.M, hp.dim), g["lcat"])
+    gv["inducing_features"] = _inducing_chain(sh, param, g["vhat"].reshape(hp.M, hp.dim), g["lcat"],
+                                              device_basis=(hp, lcat_dev) if lcat_dev is not None else None)
     return value, grads
 
 

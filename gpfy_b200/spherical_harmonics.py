@@ -116,13 +116,23 @@ class SphericalHarmonics:
 
     # ---- device side ----
     def _cat(self, param: Param):
+        """(vhat [M, dim], lcat [sum m_l^2], m) as the kernels consume them.  In learned mode (phase truncation) the
+        normalisation, the Gram matrices and their Cholesky factors are rebuilt on the device every call
+        (`gpfy_inducing_basis_fwd`) when every m_l <= 64; otherwise it is host numpy, as in fixed mode where the
+        factors are constants."""
+        raw = [v for _, v in sorted(param.params["variational"]["inducing_features"].items())]
+        m = [int(v.shape[0]) for v in raw]
+        if self._learned(param) and max(m) <= 64 and _runtime.cuda_available():
+            hp = _runtime.hot_path(raw[0].shape[1] - 1, m)
+            vhat, lcat = hp.inducing_basis(np.concatenate(raw, 0), normalise=True)
+            return vhat, lcat, m
         Vs, Ls = self.Vs(param), self.Ls(param)
-        return np.concatenate(Vs, 0), np.concatenate([l.ravel() for l in Ls]), [v.shape[0] for v in Vs]
+        return np.concatenate(Vs, 0), np.concatenate([l.ravel() for l in Ls]), m
 
     def polynomial_expansion(self, param: Param, X):
         """[M, N] harmonics of points X [N, dim] that already lie on the sphere (spherical_harmonics.py:290-320)."""
         vhat, lcat, m = self._cat(param)
-        dim = vhat.shape[1]
+        dim = int(vhat.shape[1])
         if int(np.shape(X)[-1]) != dim:
             raise ValueError(f"X has {np.shape(X)[-1]} columns, the harmonics live in dimension {dim}")
         hp = _runtime.hot_path(dim - 1, m)

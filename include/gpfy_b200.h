@@ -148,6 +148,16 @@ GPFY_API int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n
                           const double* variance, const double* eig, const double* mu, double* packed, void* workspace,
                           size_t workspace_bytes);
 
+/* Inducing-basis algebra of the learned (phase-truncated) mode, N-independent, one call per step each way
+ * (replaces spherical_harmonics.py:194-217 `Vs`, :219-239 `Ls`, :265-288 `orthogonalise_basis` and their reverse
+ * pass).  V [M, dim] are the raw `V_l` parameters concatenated over degrees.
+ *   fwd: vhat = rows of V normalised (normalise != 0), lcat = chol(alpha/(alpha+l) C_l^alpha(vhat vhat^T) + 1e-16 I)
+ *   vjp: dV from the cotangents of (vhat, lcat) as gpfy_svgp_elbo_valgrad returns them (d_vhat, d_lcat).
+ * Built for m_l <= 64; GPFY_EUNSUPPORTED otherwise (the host framework keeps that algebra). */
+GPFY_API int gpfy_inducing_basis_fwd(void* stream, const GpfyDesc* desc, const double* V, int normalise, double* vhat, double* lcat);
+GPFY_API int gpfy_inducing_basis_vjp(void* stream, const GpfyDesc* desc, const double* V, const double* lcat, int normalise,
+                            const double* dvhat, const double* dlcat, double* dV);
+
 /* KL(q || N(0, I)) and its gradients (replaces variational.py:225-240 with :262-286 / :375-399).
  * out: [1 + M*P + P*M*M] = KL, dKL/dmu, dKL/dSigma.  TriL only reads diag/all of L; full covariance
  * needs a Cholesky of Sigma and is left to the host framework (returns GPFY_EUNSUPPORTED). */

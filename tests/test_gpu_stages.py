@@ -186,3 +186,29 @@ def test_results_do_not_depend_on_workspace_contents(N, T, P, lik, d, F):
     for a, b_ in zip(got, ref):
         assert bool(torch.isfinite(a).all())
         assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("name", ["d8_F6_T12", "d8_F11_T30", "d32_F4_T16_bernoulli", "d5_ntk3_P2"])
+def test_inducing_basis_on_device_matches_reference_and_autograd(name):
+    """gpfy_inducing_basis_fwd / _vjp against the reference's Vs / Ls outputs and against
+    torch.autograd through normalise -> Gram -> Cholesky of the oracle."""
+    from gpfy_b200.ops import HotPath
+    g = load(name)
+    F = int(g["meta_F"])
+    alpha = float(g["meta_alpha"])
+    V = [g[f"p_V_{n:02d}"] for n in range(F)]
+    m = [v.shape[0] for v in V]
+    hp = HotPath(V[0].shape[1] - 1, m)
+    vhat, lcat = hp.inducing_basis(np.concatenate(V, 0), normalise=True)
+    assert rel_err(vhat.cpu().numpy(), np.concatenate([g[f"o_Vs_{n:02d}"] for n in range(F)], 0)) < 1e-14
+    assert rel_err(lcat.cpu().numpy(), np.concatenate([np.tril(g[f"o_Ls_{n:02d}"]).ravel() for n in range(F)])) < 1e-10
+    rng = np.random.default_rng(3)
+    Vt = [O.T(v).requires_grad_(True) for v in V]
+    Vh = O.normalise_V(Vt)
+    Ls = O.orthogonalise_basis(Vh, alpha)
+    dvh = [rng.standard_normal(v.shape) for v in V]
+    dL = [np.tril(rng.standard_normal((k, k))) for k in m]
+    s = sum((v * O.T(d)).sum() for v, d in zip(Vh, dvh)) + sum((l * O.T(d)).sum() for l, d in zip(Ls, dL))
+    grads = torch.autograd.grad(s, Vt)
+    dV = hp.inducing_basis_vjp(np.concatenate(V, 0), lcat, np.concatenate(dvh, 0), np.concatenate([d.ravel() for d in dL]), normalise=True)
+    assert rel_err(dV.cpu().numpy(), np.concatenate([x.numpy() for x in grads], 0)) < 1e-9
