@@ -168,6 +168,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
     N = int(a.n)
     prob = synthetic.headline_problem(N, T=a.T, device=dev, rank=rank, world=world)
