@@ -311,14 +311,17 @@ def run_ours(a):
     # ---- BASELINE.json configs[1]: Phi(X) only (projection A = sqrt(lambda v) r Phi), device resident ----
     phi = None
     if world == 1:
-        nphi = min(n_local, 2_000_000)
+        nphi = n_local  # the full N = 10 M: Phi is 8 M N = 22.4 GB of the 180 GB
         ds = torch.sqrt(args[5] * args[4])
         f = lambda: hp.features(X[:nphi], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)
-        f(); torch.cuda.synchronize()
+        out_phi = f(); torch.cuda.synchronize()
+        del out_phi
         e0.record()
         for _ in range(3):
-            f()
+            out_phi = f()
         e1.record(); torch.cuda.synchronize()
+        del out_phi
+        torch.cuda.empty_cache()
         pms = e0.elapsed_time(e1) / 3
         hbm_peak = 6549.8
         try:
