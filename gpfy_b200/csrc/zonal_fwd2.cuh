@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
           const int kend = min(ml, 8 * i + 8);        // lower triangular: columns 0 .. 8 i + 7
           const bool rok = rloc < ml;
           const double* Lrow = args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off;
+#pragma unroll 4
           for (int k0 = 0; k0 < kend; k0 += 4) {
             const int kc = k0 + t4;
             const double av = (rok && kc < ml) ? __ldg(Lrow + kc) : 0.0;
