@@ -9,8 +9,6 @@
 
 namespace gpfy {
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
-
 struct ZonalFwd2Args {
   ZonalArgs z;
   MonicTab mt;  // parameter alpha
@@ -23,8 +21,8 @@ static inline int zf2_smem_bytes(int Mp, int dimp, int P, bool with_mz, int pmax
 }
 
 // Persistent: every CTA stages Vhat / mu2 once (TMA bulk copy) and then walks 32-point tiles
-// blockIdx, blockIdx + gridDim, ...  Per tile there is ONE CTA barrier: warp 0 loads and projects the NEXT tile's
-// points while all warps work on the current one (coordinates and the mu2 . z partial sums are double-buffered in
+// blockIdx, blockIdx + gridDim, ...  Per tile there is ONE CTA barrier: warp 0 (helper) loads and projects the NEXT
+// tile's points while the seven compute warps work on the current one (coordinates and the mu2 . z partial sums are double-buffered in
 // shared memory), and finishes the previous tile's per-point outputs right after the barrier.
 template <int DIMP, int PMAX>
 __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constant__ ZonalFwd2Args args) {
@@ -92,7 +90,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
       if (pp < a.P) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += rd[(w * PMAX + pp) * 32 + lane];
+        for (int w = 1; w < 8; ++w) s += rd[(w * PMAX + pp) * 32 + lane];
         if (valid) {
           a.mz[(int64_t)pp * a.ldz + n] = s;
           if (a.Yg) {
@@ -113,16 +111,14 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
 
   const int ntile = (a.M + 7) / 8;
   for (int it = 0; it < n_my; ++it) {
+    if (warp == 0) {  // helper warp: the next tile's points while the seven compute warps work, then this tile's outputs
+      if (it + 1 < n_my) project_tile(it + 1);
+      __syncthreads();
+      if (a.mz) finish_tile(it);
+      continue;
+    }
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
     const double* x = xs + (it & 1) * 32 * DIMP;
-    if (warp == 0 && it + 1 < n_my) {  // the next tile's rows are on their way to L2 while this tile is computed
-      const int64_t nn = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 32 + lane;
-      if (nn < a.npts) {
-        prefetch_l2(a.X + nn * a.xcols);
-        prefetch_l2(a.X + nn * a.xcols + a.xcols - 1);
-        if (a.Yg) prefetch_l2(a.Yg + nn);
-      }
-    }
     double xb[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
@@ -135,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
 #pragma unroll
       for (int u = 0; u < 8; ++u) mzacc[p][u] = 0.0;
 
-    for (int rt = 7 - warp; rt < ntile; rt += 8) {  // warp 0 (which also projects the points) gets the short end
+    for (int rt = warp - 1; rt < ntile; rt += 7) {  // seven compute warps: 35 row tiles at M = 280 = 5 each
       const int row = rt * 8 + g;
       double t[8];
 #pragma unroll
@@ -197,9 +193,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
           if (g == 0) rd[(warp * PMAX + pp) * 32 + 8 * (u >> 1) + 2 * t4 + (u & 1)] = v;
         }
     }
-    if (warp == 0 && it + 1 < n_my) project_tile(it + 1);
     __syncthreads();
-    if (warp == 0 && a.mz) finish_tile(it);
   }
 }
 
@@ -303,21 +297,17 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
   for (int it = 0; it < n_my; ++it) {
     const int64_t p0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 32;
     const double* x = xs + (it & 1) * 32 * DIMP;
-    if (warp == 0 && it + 1 < n_my) {
-      const int64_t nn = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 32 + lane;
-      if (nn < a.npts) {
-        prefetch_l2(a.X + nn * a.xcols);
-        prefetch_l2(a.X + nn * a.xcols + a.xcols - 1);
-      }
-    }
-    // ---- phase A: zonal values of the tile into shared memory ----
-    {
+    // ---- phase A: zonal values of the tile into shared memory (seven compute warps; warp 0 projects the next
+    // tile's points meanwhile) ----
+    if (warp == 0) {
+      if (it + 1 < n_my) project_tile(it + 1);
+    } else {
       double xb[KS][4];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) xb[ks][nt] = x[(8 * nt + g) * DIMP + 4 * ks + t4];
-      for (int rt = 7 - warp; rt < ntile; rt += 8) {
+      for (int rt = warp - 1; rt < ntile; rt += 7) {
         const int row = rt * 8 + g;
         double t[8];
 #pragma unroll
@@ -349,7 +339,6 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
         }
       }
     }
-    if (warp == 0 && it + 1 < n_my) project_tile(it + 1);
     __syncthreads();
 
     // ---- phase B: whitening, work item = (degree, 8-row tile of that degree) dealt round-robin to the warps ----
