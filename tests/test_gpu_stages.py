@@ -152,6 +152,10 @@ def test_headline_shapes_match_oracle_on_a_sample(T, P, lik):
     fmu, fvar = hp.predict_diag(*[args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)])
     ofmu, ofvar = O.predict_diag(O.pack_to_torch(pack), O.T(args[0].cpu().numpy()))
     assert rel_err(fmu.cpu().numpy(), ofmu.numpy()) < TOL and rel_err(fvar.cpu().numpy(), ofvar.numpy()) < TOL
+    # the explicit projection A = sqrt(lambda v) r Phi on the same ragged rows (odd N: unaligned output rows)
+    A, r = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=torch.sqrt(args[5] * args[4]), mul_r=True)
+    oA = O.projection(O.pack_to_torch(pack), O.T(args[0].cpu().numpy()))
+    assert rel_err(A.cpu().numpy(), oA.numpy()) < TOL
 
 
 @pytest.mark.parametrize("N,T,P,lik,d,F", [(1000, 30, 1, "gaussian", 8, 11), (333, 12, 2, "bernoulli", 5, 5),
