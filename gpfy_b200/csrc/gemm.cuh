@@ -19,7 +19,7 @@ struct GemmArgs {
   int64_t lda;
   const double* B;
   int64_t ldb;
-  double* C;
+  double* C;    // may be null when only the psi epilogue is wanted (predict_diag): the product is not stored
   int64_t ldc;
   int m, n, k;  // k must be a multiple of 16 (operands zero padded); n even; lda, ldb, ldc even
   double alpha, beta;

@@ -1131,7 +1131,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
       GemmArgs g;
       g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
       g.B = ws + p.o_Z; g.ldb = p.nc;
-      g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
+      g.C = nullptr; g.ldc = p.nc;  // only psi = z . (W2 z) is needed (model.py:136): the product is never stored
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
@@ -1203,7 +1203,7 @@ int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* 
       GemmArgs g;
       g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
       g.B = ws + p.o_Z; g.ldb = p.nc;
-      g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
+      g.C = nullptr; g.ldc = p.nc;  // only psi = z . (W2 z) is needed (model.py:136): the product is never stored
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
