@@ -34,6 +34,12 @@ class GpfyElboLayout(ctypes.Structure):
                 ("total", "data_term", "d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2")]
 
 
+class GpfyStepLayout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("kernel_kind", "truncation_level", "w_identity", "n_w")] + \
+               [(n, ctypes.c_int64) for n in ("th_w", "th_b", "th_v", "th_beta", "th_s2", "th_mu", "th_sig", "th_V", "th_total",
+                                              "c_w", "c_b", "c_v", "c_beta", "c_eig", "c_deig", "c_s2", "c_mu", "c_sig", "c_V", "c_total")]
+
+
 class GpfyError(RuntimeError):
     pass
 
@@ -58,6 +64,9 @@ _SIGNATURES = {
     "gpfy_svgp_elbo_finish": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 6 + [_P, ctypes.c_size_t]),
     "gpfy_inducing_basis_fwd": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, ctypes.c_int, _P, _P]),
     "gpfy_inducing_basis_vjp": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, ctypes.c_int, _P, _P, _P]),
+    "gpfy_step_constrain": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyStepLayout), _P, _P, _P, _P]),
+    "gpfy_step_grad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyStepLayout), _P, _P, _P, _P, _P, ctypes.c_double, _P, _P]),
+    "gpfy_step_adam": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P, _P, _P] + [ctypes.c_double] * 4 + [ctypes.c_int64]),
     "gpfy_prior_kl_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, _P]),
     "gpfy_predict_diag": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 11 + [_P, ctypes.c_size_t]),
     "gpfy_allreduce_packed": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),

@@ -1,0 +1,158 @@
+// Device-side step driver: everything around the hot path that the reference does in
+// host JAX every step - bijector forward (param.py:255), PolynomialDecay eigenvalues (spherical.py:563-587), the
+// bijector / eigenvalue chain rules, the scale / N and KL bookkeeping of optimization.py:151-156 and the Adam
+// update of training.py:78-86 - as a few tiny kernels on flat device vectors, so that a training step needs no
+// host round trip (and can be captured in a CUDA graph).  O(#parameters) work; not on the N-dependent path.
+#include "common.cuh"
+
+namespace gpfy {
+
+__global__ void step_constrain_kernel(GpfyStepLayout L, const double* __restrict__ theta, const int* __restrict__ tri_map,
+                                      const double* __restrict__ cf, double* __restrict__ cons, int M, int P, int F, int fullcov) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  // weights: Exp (ARD / scalar) or Identity (projection)
+  for (int64_t i = tid; i < L.n_w; i += nth) cons[L.c_w + i] = L.w_identity ? theta[L.th_w + i] : exp(theta[L.th_w + i]);
+  if (tid == 0) {
+    cons[L.c_b] = exp(theta[L.th_b]);
+    cons[L.c_v] = exp(theta[L.th_v]);
+    if (L.th_s2 >= 0) cons[L.c_s2] = exp(theta[L.th_s2]);
+    if (L.kernel_kind == 1) {
+      // lambda_n = (1 + n)^-beta cf_n / sum_k (1 + k)^-beta, levels clipped to truncation_level - 1 (spherical.py:579-587)
+      const double beta = exp(theta[L.th_beta]);
+      double S = 0.0, dS = 0.0;
+      for (int k = 0; k < L.truncation_level; ++k) {
+        const double dk = pow(1.0 + k, -beta);
+        S += dk;
+        dS += -log1p((double)k) * dk;
+      }
+      for (int l = 0; l < F; ++l) {
+        const int n = l < L.truncation_level ? l : L.truncation_level - 1;
+        const double dn = pow(1.0 + n, -beta), ddn = -log1p((double)n) * dn;
+        cons[L.c_eig + l] = dn * cf[n] / S;
+        cons[L.c_deig + l] = ddn * cf[n] / S - dn * cf[n] * dS / (S * S);
+      }
+      cons[L.c_beta] = beta;
+    } else {
+      for (int l = 0; l < F; ++l) { cons[L.c_eig + l] = cf[l]; cons[L.c_deig + l] = 0.0; }
+    }
+  }
+  for (int64_t i = tid; i < (int64_t)M * P; i += nth) cons[L.c_mu + i] = theta[L.th_mu + i];
+  const int64_t nV = L.th_total - L.th_V;
+  for (int64_t i = tid; i < nV; i += nth) cons[L.c_V + i] = theta[L.th_V + i];
+  if (fullcov) {
+    for (int64_t i = tid; i < (int64_t)P * M * M; i += nth) cons[L.c_sig + i] = theta[L.th_sig + i];
+  } else {
+    // FillTriangular (variational.py:260): zero the dense matrices here, step_fill_tril_kernel scatters the vector
+    for (int64_t i = tid; i < (int64_t)P * M * M; i += nth) cons[L.c_sig + i] = 0.0;
+  }
+}
+
+__global__ void step_fill_tril_kernel(GpfyStepLayout L, const double* __restrict__ theta, const int* __restrict__ tri_map,
+                                      double* __restrict__ cons, int M, int P) {
+  const int64_t ntri = (int64_t)M * (M + 1) / 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * ntri) return;
+  const int64_t p = i / ntri, k = i % ntri;
+  cons[L.c_sig + p * M * M + tri_map[k]] = theta[L.th_sig + i];
+}
+
+// gradient of the loss (-ELBO) w.r.t. the unconstrained vector, and the loss itself
+__global__ void step_grad_kernel(GpfyStepLayout L, GpfyElboLayout E, const double* __restrict__ cons, const double* __restrict__ packed,
+                                 const double* __restrict__ kl, const double* __restrict__ dV, const int* __restrict__ tri_map,
+                                 double c, double* __restrict__ grad, double* __restrict__ loss_out, int M, int P, int F, int fullcov) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nmu = (int64_t)M * P, nsig = (int64_t)P * M * M;
+  for (int64_t i = tid; i < L.n_w; i += nth) {
+    const double g = c * packed[E.d_w + i];
+    grad[L.th_w + i] = -(L.w_identity ? g : g * cons[L.c_w + i]);   // Exp: d exp(x) / dx = exp(x)
+  }
+  if (tid == 0) {
+    grad[L.th_b] = -c * packed[E.d_b] * cons[L.c_b];
+    grad[L.th_v] = -c * packed[E.d_v] * cons[L.c_v];
+    if (L.th_s2 >= 0) grad[L.th_s2] = -c * packed[E.d_sigma2] * cons[L.c_s2];
+    if (L.kernel_kind == 1) {
+      double s = 0.0;
+      for (int l = 0; l < F; ++l) s += c * packed[E.d_eig + l] * cons[L.c_deig + l];
+      grad[L.th_beta] = -s * cons[L.c_beta];
+    }
+    loss_out[0] = -(c * packed[E.data_term] - kl[0]);   // optimization.py:154-156
+  }
+  for (int64_t i = tid; i < nmu; i += nth) grad[L.th_mu + i] = -(c * packed[E.d_mu + i] - kl[1 + i]);
+  if (fullcov) {
+    for (int64_t i = tid; i < nsig; i += nth) grad[L.th_sig + i] = -(c * packed[E.d_sigma + i] - kl[1 + nmu + i]);
+  } else {
+    const int64_t ntri = (int64_t)M * (M + 1) / 2;
+    for (int64_t i = tid; i < P * ntri; i += nth) {
+      const int64_t p = i / ntri, k = i % ntri;
+      const int64_t e = p * M * M + tri_map[k];
+      grad[L.th_sig + i] = -(c * packed[E.d_sigma + e] - kl[1 + nmu + e]);   // FillTriangular's VJP: gather
+    }
+  }
+  const int64_t nV = L.th_total - L.th_V;
+  for (int64_t i = tid; i < nV; i += nth) grad[L.th_V + i] = -c * dV[i];
+}
+
+// optax.adam + masked set_to_zero (model.py:288-289, training.py:78-86)
+__global__ void step_adam_kernel(int64_t n, double* __restrict__ theta, const double* __restrict__ grad, double* __restrict__ m1,
+                                 double* __restrict__ m2, const unsigned char* __restrict__ mask, double lr, double b1, double b2,
+                                 double eps, double bc1, double bc2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double g = grad[i];
+  const double a = b1 * m1[i] + (1.0 - b1) * g;
+  const double v = b2 * m2[i] + (1.0 - b2) * g * g;
+  m1[i] = a;
+  m2[i] = v;
+  if (mask[i]) theta[i] += -lr * (a / bc1) / (sqrt(v / bc2) + eps);
+}
+
+}  // namespace gpfy
+
+using namespace gpfy;
+
+#define STEP_K(kernel, grid, block, st, ...)                 \
+  do {                                                       \
+    kernel<<<grid, block, 0, st>>>(__VA_ARGS__);             \
+    GPFY_COUNT_LAUNCH();                                     \
+    GPFY_LAUNCH_OK();                                        \
+  } while (0)
+
+extern "C" {
+
+int gpfy_step_constrain(void* stream, const GpfyDesc* desc, const GpfyStepLayout* lay, const double* theta, const int* tri_map,
+                        const double* cf, double* cons) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (!lay || !theta || !cons) { set_error("null argument"); return GPFY_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int fullcov = desc->q_kind == GPFY_Q_FULLCOV;
+  STEP_K(step_constrain_kernel, 64, 256, st, *lay, theta, tri_map, cf, cons, s.M, s.P, s.F, fullcov);
+  if (!fullcov) {
+    const int64_t n = (int64_t)s.P * s.M * (s.M + 1) / 2;
+    STEP_K(step_fill_tril_kernel, (unsigned)((n + 255) / 256), 256, st, *lay, theta, tri_map, cons, s.M, s.P);
+  }
+  return GPFY_OK;
+}
+
+int gpfy_step_grad(void* stream, const GpfyDesc* desc, const GpfyStepLayout* lay, const double* cons, const double* packed,
+                   const double* kl, const double* dV, const int* tri_map, double scale_over_n, double* grad, double* loss_out) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  GpfyElboLayout E;
+  GPFY_TRY(gpfy_elbo_packed_layout(desc, &E));
+  STEP_K(step_grad_kernel, 128, 256, (cudaStream_t)stream, *lay, E, cons, packed, kl, dV, tri_map, scale_over_n, grad, loss_out, s.M,
+         s.P, s.F, desc->q_kind == GPFY_Q_FULLCOV);
+  return GPFY_OK;
+}
+
+int gpfy_step_adam(void* stream, int64_t n, double* theta, const double* grad, double* m1, double* m2, const unsigned char* mask,
+                   double lr, double b1, double b2, double eps, int64_t step_count) {
+  if (n <= 0) return GPFY_OK;
+  const double bc1 = 1.0 - pow(b1, (double)step_count), bc2 = 1.0 - pow(b2, (double)step_count);
+  STEP_K(step_adam_kernel, (unsigned)((n + 255) / 256), 256, (cudaStream_t)stream, n, theta, grad, m1, m2, mask, lr, b1, b2, eps, bc1, bc2);
+  return GPFY_OK;
+}
+
+}  // extern "C"

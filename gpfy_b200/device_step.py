@@ -1,0 +1,185 @@
+"""Training step driver on the device.
+
+The reference's `train_step` (optimization.py:107-120) applies the bijectors, evaluates the ELBO and its gradient,
+and lets optax update the unconstrained parameters - all inside one jitted XLA program.  `DeviceTrainer` is the
+equivalent around the CUDA hot path: the unconstrained parameters live in ONE flat device vector, and a step is a
+fixed sequence of stream-ordered C-ABI calls (constrain -> inducing basis -> ELBO + gradient -> all-reduce -> KL ->
+basis VJP -> gradient assembly -> Adam) without a single host synchronisation, so it can be replayed from a CUDA
+graph.  Supports the TriL variational distribution with Gaussian or Bernoulli likelihood and every kernel of
+gpfy_b200.spherical; m_l <= 64 in learned-basis mode.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _ptr, _stream
+from .param import FillTriangular, Param, tree_map
+from .spherical import PolynomialDecay
+
+
+class DeviceTrainer:
+    def __init__(self, param: Param, m, q, lik, learning_rate=5e-2, b1=0.9, b2=0.999, eps=1e-8, dataset_size=-1,
+                 allreduce=None, n_total=None):
+        if q._q_kind != "tril":
+            raise _lib.GpfyError("DeviceTrainer supports VariationalDistributionTriL (the full-covariance KL needs a host Cholesky)")
+        self.m, self.q, self.lik, self.kernel, self.sh = m, q, lik, m.kernel, m._sh
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(b1), float(b2), float(eps)
+        self.dataset_size, self.allreduce, self.n_total = dataset_size, allreduce, n_total
+        self.template = param if param._constrained else param.constrained()
+        con = self.template
+        self.hp, _ = m.hot_args(con, lik)
+        hp, dev = self.hp, self.hp.device
+        kname = self.kernel.name
+        kp = con.params[kname]
+        self.learned = self.sh._learned(con)
+        if self.learned and max(hp.m) > 64:
+            raise _lib.GpfyError("DeviceTrainer needs m_l <= 64 in learned-basis mode")
+        self.vnames = sorted(con.params["variational"]["inducing_features"])
+        M, P, F, dim = hp.M, hp.P, hp.F, hp.dim
+        ntri = M * (M + 1) // 2
+        L = _lib.GpfyStepLayout()
+        L.kernel_kind = 1 if isinstance(self.kernel, PolynomialDecay) else 0
+        L.truncation_level = getattr(self.kernel, "truncation_level", 0)
+        L.w_identity = 1 if hp.projection_dim else 0
+        L.n_w = hp.nw
+        o = 0
+        def take(n):
+            nonlocal o
+            r = o
+            o += n
+            return r
+        L.th_w, L.th_b, L.th_v = take(hp.nw), take(1), take(1)
+        L.th_beta = take(1) if "beta" in kp else -1
+        self.has_s2 = lik._sigma2(con) is not None
+        L.th_s2 = take(1) if self.has_s2 else -1
+        L.th_mu, L.th_sig, L.th_V = take(M * P), take(P * ntri), take(M * dim)
+        L.th_total = o
+        o = 0
+        L.c_w, L.c_b, L.c_v, L.c_beta, L.c_eig, L.c_deig, L.c_s2 = take(hp.nw), take(1), take(1), take(1), take(F), take(F), take(1)
+        L.c_mu, L.c_sig, L.c_V = take(M * P), take(P * M * M), take(M * dim)
+        L.c_total = o
+        self.L = L
+        # flat unconstrained vector + trainable mask from the Param
+        free = con.unconstrained()
+        fk, tk = free.params[kname], con._trainables[kname]
+        theta = np.zeros(L.th_total)
+        mask = np.zeros(L.th_total, dtype=np.uint8)
+        def put(off, val, tr):
+            val = np.asarray(val, dtype=np.float64).ravel()
+            theta[off:off + val.size] = val
+            mask[off:off + val.size] = 1 if tr else 0
+        put(L.th_w, fk["weight_variances"], tk["weight_variances"])
+        put(L.th_b, fk["bias_variance"], tk["bias_variance"])
+        put(L.th_v, fk["variance"], tk["variance"])
+        if L.th_beta >= 0:
+            put(L.th_beta, fk["beta"], tk["beta"])
+        if self.has_s2:
+            put(L.th_s2, free.params["likelihood"][lik.name]["variance"], con._trainables["likelihood"][lik.name]["variance"])
+        fq, tq = free.params["variational"][q.name], con._trainables["variational"][q.name]
+        put(L.th_mu, fq["mu"], tq["mu"])
+        put(L.th_sig, fq["Sigma"], tq["Sigma"])
+        off = L.th_V
+        for name in self.vnames:
+            v = free.params["variational"]["inducing_features"][name]
+            put(off, v, con._trainables["variational"]["inducing_features"][name])
+            off += v.size
+        t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dt)
+        self.theta, self.mask = t(theta), torch.as_tensor(mask, device=dev)
+        self.m1, self.m2 = torch.zeros_like(self.theta), torch.zeros_like(self.theta)
+        self.grad = torch.zeros_like(self.theta)
+        self.cons = torch.zeros(L.c_total, dtype=torch.float64, device=dev)
+        flat, src = FillTriangular._index_map(M)
+        tri = np.zeros(ntri, dtype=np.int32)
+        tri[src] = flat
+        self.tri_map = torch.as_tensor(tri, device=dev)
+        if L.kernel_kind == 1:
+            cf = self.kernel._compute_eigvals(con.constants["sphere"]["sphere_dim"],
+                                              gegenbauer_lookup_table=con.constants["sphere"]["gegenbauer_lookup_table"])
+        else:
+            cf = self.kernel.eigenvalues(con, self.sh.levels)
+        self.cf = t(cf)
+        self.packed = torch.zeros(hp.layout.total, dtype=torch.float64, device=dev)
+        self.kl = torch.zeros(1 + M * P + P * M * M, dtype=torch.float64, device=dev)
+        self.dV = torch.zeros(M * dim, dtype=torch.float64, device=dev)
+        if self.learned:
+            self.vhat = torch.zeros((M, dim), dtype=torch.float64, device=dev)
+            self.lcat = torch.zeros(hp.lsize, dtype=torch.float64, device=dev)
+        else:
+            self.lcat = t(np.concatenate([l.ravel() for l in self.sh.Ls(con)]))
+        self.loss_trace = []
+        self.count = 0
+        c = self.cons
+        sl = lambda a, n: c[a:a + n]
+        self.v_w, self.v_b, self.v_v, self.v_eig = sl(L.c_w, hp.nw), sl(L.c_b, 1), sl(L.c_v, 1), sl(L.c_eig, F)
+        self.v_s2, self.v_mu, self.v_sig, self.v_V = sl(L.c_s2, 1), sl(L.c_mu, M * P), sl(L.c_sig, P * M * M), sl(L.c_V, M * dim)
+
+    # ------------------------------------------------------------------
+    def step(self, X, Y):
+        """One Adam step on this rank's rows (device tensors); every call only enqueues work.  The loss (-ELBO) of the
+        step stays on the device in `loss_trace`."""
+        hp, L, lib = self.hp, self.L, self.hp.lib
+        st, d = _stream(hp.device), ctypes.byref(hp.desc)
+        _lib.check(lib.gpfy_step_constrain(st, d, ctypes.byref(L), _ptr(self.theta), _ptr(self.tri_map), _ptr(self.cf), _ptr(self.cons)))
+        if self.learned:
+            _lib.check(lib.gpfy_inducing_basis_fwd(st, d, _ptr(self.v_V), 1, _ptr(self.vhat), _ptr(self.lcat)))
+            vhat = self.vhat
+        else:
+            vhat = self.v_V
+        hp.elbo_valgrad_packed(X, Y, self.v_w, self.v_b, self.v_v, self.v_eig, vhat, self.lcat, self.v_mu, self.v_sig,
+                               self.v_s2 if self.has_s2 else None, out=self.packed)
+        n_local = X.shape[0]
+        if self.allreduce is not None and self.allreduce.world > 1:
+            self.allreduce(self.packed)
+        n_total = int(self.n_total) if self.n_total is not None else n_local
+        scale = float(self.dataset_size) if self.dataset_size > 0 else float(n_total)
+        _lib.check(lib.gpfy_prior_kl_valgrad(st, d, _ptr(self.v_mu), _ptr(self.v_sig), _ptr(self.kl)))
+        E = hp.layout
+        if self.learned:
+            _lib.check(lib.gpfy_inducing_basis_vjp(st, d, _ptr(self.v_V), _ptr(self.lcat), 1,
+                                                   ctypes.c_void_p(self.packed.data_ptr() + 8 * E.d_vhat),
+                                                   ctypes.c_void_p(self.packed.data_ptr() + 8 * E.d_lcat), _ptr(self.dV)))
+            dV = self.dV
+        else:
+            dV = self.packed[E.d_vhat:E.d_vhat + hp.M * hp.dim]
+        loss = torch.empty(1, dtype=torch.float64, device=hp.device)
+        _lib.check(lib.gpfy_step_grad(st, d, ctypes.byref(L), _ptr(self.cons), _ptr(self.packed), _ptr(self.kl), _ptr(dV),
+                                      _ptr(self.tri_map), scale / n_total, _ptr(self.grad), _ptr(loss)))
+        self.count += 1
+        _lib.check(lib.gpfy_step_adam(st, L.th_total, _ptr(self.theta), _ptr(self.grad), _ptr(self.m1), _ptr(self.m2), _ptr(self.mask),
+                                      self.lr, self.b1, self.b2, self.eps, self.count))
+        self.loss_trace.append(loss)
+        return loss
+
+    def losses(self):
+        return torch.cat(self.loss_trace).cpu().numpy() if self.loss_trace else np.zeros(0)
+
+    def param(self) -> Param:
+        """The current parameters as a constrained `Param` (one device -> host copy)."""
+        L, hp = self.L, self.hp
+        th = self.theta.cpu().numpy()
+        free = self.template.unconstrained()
+        p = tree_map(lambda x: x, free.params)
+        kname = self.kernel.name
+        kp = dict(p[kname])
+        kp["weight_variances"] = th[L.th_w:L.th_w + hp.nw].reshape(np.shape(kp["weight_variances"]))
+        kp["bias_variance"], kp["variance"] = th[L.th_b].reshape(()), th[L.th_v].reshape(())
+        if L.th_beta >= 0:
+            kp["beta"] = th[L.th_beta].reshape(())
+        p[kname] = kp
+        if self.has_s2:
+            p["likelihood"] = {self.lik.name: {"variance": th[L.th_s2].reshape(())}}
+        var = {k: (dict(v) if isinstance(v, dict) else v) for k, v in p["variational"].items()}
+        M, P = hp.M, hp.P
+        ntri = M * (M + 1) // 2
+        var[self.q.name] = {"mu": th[L.th_mu:L.th_mu + M * P].reshape(M, P), "Sigma": th[L.th_sig:L.th_sig + P * ntri].reshape(P, ntri)}
+        feats, off = {}, L.th_V
+        for name in self.vnames:
+            shp = np.shape(free.params["variational"]["inducing_features"][name])
+            n = int(np.prod(shp))
+            feats[name] = th[off:off + n].reshape(shp)
+            off += n
+        var["inducing_features"] = feats
+        p["variational"] = var
+        return free.replace(params=p).constrained()

@@ -186,6 +186,31 @@ GPFY_API int gpfy_variational_expectations(void* stream, const GpfyDesc* desc, i
 GPFY_API int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* A, const double* mu,
                    const double* sigma, double* mean, double* var, void* workspace, size_t workspace_bytes);
 
+/* ---- device-side step driver (replaces the host-JAX work around the hot path) ----
+ * theta is the flat UNCONSTRAINED parameter vector (what optax updates, model.py:285-295), `cons` the flat constrained
+ * buffer the hot-path calls read from; both are device memory, offsets in doubles. */
+typedef struct GpfyStepLayout {
+  int32_t kernel_kind;       /* 0: eigenvalues are constants (NTK / ArcCosine: cf = lambda_l [F]);
+                                1: PolynomialDecay (cf = alpha / (n + alpha) / C_n^alpha(1) [truncation_level], spherical.py:526-561) */
+  int32_t truncation_level;
+  int32_t w_identity;        /* 1: projection weights (Identity bijector), 0: Exp */
+  int32_t n_w;               /* number of weight entries */
+  int64_t th_w, th_b, th_v, th_beta, th_s2, th_mu, th_sig, th_V, th_total; /* theta; th_beta / th_s2 = -1 when absent */
+  int64_t c_w, c_b, c_v, c_beta, c_eig, c_deig, c_s2, c_mu, c_sig, c_V, c_total; /* cons; c_deig: d lambda_l / d beta */
+} GpfyStepLayout;
+
+/* cons = bijector.forward(theta) (param.py:255: Exp / Identity / FillTriangular through `tri_map`, the flat [M, M]
+ * position of every vector entry) plus kernel.eigenvalues (spherical.py:563-587) and its beta-derivative. */
+GPFY_API int gpfy_step_constrain(void* stream, const GpfyDesc* desc, const GpfyStepLayout* lay, const double* theta,
+                        const int* tri_map, const double* cf, double* cons);
+/* grad = d(-ELBO)/d theta from the all-reduced packed buffer, the KL triple of gpfy_prior_kl_valgrad and dV of
+ * gpfy_inducing_basis_vjp (un-scaled); scale_over_n = dataset_size / N (optimization.py:154-156); loss_out[0] = -ELBO. */
+GPFY_API int gpfy_step_grad(void* stream, const GpfyDesc* desc, const GpfyStepLayout* lay, const double* cons, const double* packed,
+                   const double* kl, const double* dV, const int* tri_map, double scale_over_n, double* grad, double* loss_out);
+/* optax.adam with the frozen leaves masked to zero updates (model.py:288-289, training.py:78-86); step_count >= 1. */
+GPFY_API int gpfy_step_adam(void* stream, int64_t n, double* theta, const double* grad, double* m1, double* m2,
+                   const unsigned char* mask, double lr, double b1, double b2, double eps, int64_t step_count);
+
 /* Sum of the packed buffers of all ranks, in place, on `stream` (the single exchange step).
  * `nccl_comm` is an ncclComm_t owned by the caller; NCCL is resolved at run time from the process
  * (the host framework's copy), so this library has no link-time NCCL dependency. */

@@ -36,3 +36,15 @@ for _ in range(3):
 torch.cuda.synchronize()
 dk = (time.perf_counter() - t0) / 3
 print(f"N={N}: API step {dt*1e3:.2f} ms ({N/dt*1e-6:.1f} M pts/s), packed C-ABI call {dk*1e3:.2f} ms; host-side share {100*(dt-dk)/dt:.1f}%  loss {loss:.6f}")
+
+from gpfy_b200.device_step import DeviceTrainer
+tr = DeviceTrainer(param, m, q, lik, learning_rate=1e-2)
+for _ in range(2):
+    tr.step(X, Y)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    tr.step(X, Y)
+torch.cuda.synchronize()
+dd = (time.perf_counter() - t0) / 5
+print(f"N={N}: DeviceTrainer step {dd*1e3:.2f} ms ({N/dd*1e-6:.1f} M pts/s) vs packed call {dk*1e3:.2f} ms: driver overhead {100*(dd-dk)/dd:.1f}%; loss {float(tr.loss_trace[-1]):.4f}")
