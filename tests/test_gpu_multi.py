@@ -48,3 +48,55 @@ def test_two_gpu_allreduce_matches_single_gpu():
         p.join(300)
         assert p.exitcode == 0
     assert all(ret.get(r, 1.0) < 1e-12 for r in range(world)), dict(ret)
+
+
+def _train_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch.distributed as dist
+    from gpfy_b200 import distributed as gd
+    from gpfy_b200.device_step import DeviceTrainer
+    from gpfy_b200.likelihoods import Gaussian
+    from gpfy_b200.model import GP
+    from gpfy_b200.param import tree_leaves
+    from gpfy_b200.spherical import PolynomialDecay
+    from gpfy_b200.spherical_harmonics import SphericalHarmonics
+    from gpfy_b200.variational import VariationalDistributionTriL
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        N, d = 50_001, 5
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        X = torch.randn((N, d), dtype=torch.float64, device=dev, generator=g)
+        Y = torch.sin(X[:, :1]) + 0.1 * torch.randn((N, 1), dtype=torch.float64, device=dev, generator=g)
+        sh, q, lik = SphericalHarmonics(5, phase_truncation=12), VariationalDistributionTriL(), Gaussian()
+        m = GP(PolynomialDecay()).conditional(sh, q)
+        param = m.init(0, input_dim=d, likelihood=lik, sh_features=sh, variational_dist=q)
+        single = DeviceTrainer(param, m, q, lik, learning_rate=2e-2)
+        lo, hi = gd.shard_bounds(N, rank, world)
+        sharded = DeviceTrainer(param, m, q, lik, learning_rate=2e-2, allreduce=gd.PackedAllReduce(), n_total=N)
+        Xs, Ys = X[lo:hi].contiguous(), Y[lo:hi].contiguous()
+        for _ in range(5):
+            single.step(X, Y)
+            sharded.step(Xs, Ys)
+        err = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+                  for a, b in zip(tree_leaves(sharded.param().params), tree_leaves(single.param().params)))
+        lerr = float(np.max(np.abs(sharded.losses() - single.losses()) / np.abs(single.losses())))
+        ret[rank] = max(err, lerr)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_device_trainer_matches_single_gpu_training():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert all(ret.get(r, 1.0) < 1e-9 for r in range(world)), dict(ret)
