@@ -171,6 +171,52 @@ def arccosine_shape_function(x: torch.Tensor, depth: int, order: int) -> torch.T
     return y
 
 
+def gegenbauer_from_lookup(level: int, alpha: float, x: torch.Tensor, grid_resolution: int = 100_000) -> torch.Tensor:
+    """gegenbauer.py:111-119,152-167: linear interpolation of C_level^alpha on linspace(-1, 1, grid_resolution)
+    (tfp.math.interp_regular_1d_grid: fractional index (x - lo) / (hi - lo) * (G - 1), clipped)."""
+    grid = _gegenbauer(level, alpha, torch.linspace(-1, 1, grid_resolution, dtype=DT))
+    xi = torch.clamp((x + 1.0) / 2.0 * (grid_resolution - 1), 0.0, grid_resolution - 1.0)
+    lo = torch.floor(xi)
+    hi = torch.clamp(lo + 1, max=grid_resolution - 1)
+    t = xi - lo
+    return (1 - t) * grid[lo.long()] + t * grid[hi.long()]
+
+
+def polydecay_shape_function(beta, alpha: float, truncation_level: int, x: torch.Tensor) -> torch.Tensor:
+    """spherical.py:589-611: sum_n eig_n (n + alpha) / alpha C_n^alpha(x), C from the lookup table."""
+    x = torch.clamp(x, -1.0, 1.0)
+    levels = list(range(truncation_level))
+    eig = polydecay_eigenvalues(beta, alpha, truncation_level, levels) * (torch.arange(truncation_level, dtype=DT) + alpha) / alpha
+    return sum(eig[n] * gegenbauer_from_lookup(n, alpha, x) for n in levels)
+
+
+def shape_function(pack, x: torch.Tensor) -> torch.Tensor:
+    """Dispatch on the kernel class of the pack (spherical.py:438-455, 479-500, 589-611)."""
+    kind = pack.get("kernel", "NTK")
+    if kind == "PolynomialDecay":
+        return polydecay_shape_function(pack["beta"], pack["alpha"], pack["truncation_level"], x)
+    if kind == "NTK":
+        return ntk_shape_function(x, pack["depth"])
+    return arccosine_shape_function(x, pack["depth"], pack["order"])
+
+
+def K(pack, X: torch.Tensor, X2: Optional[torch.Tensor] = None, unit_diagonal: bool = True) -> torch.Tensor:
+    """spherical.py:318-352 (`K`: the diagonal cosine is set to exactly 1 when X2 is None) and
+    :354-382 (`K2`: `unit_diagonal=False`, no such fix-up; X2 defaults to X)."""
+    xs, r1 = to_sphere(pack["w"], pack["b"], X)
+    if X2 is None:
+        xs2, r2 = xs, r1
+        c = xs @ xs2.T
+        if unit_diagonal:
+            c = c.clone()
+            c.fill_diagonal_(1.0)
+    else:
+        xs2, r2 = to_sphere(pack["w"], pack["b"], X2)
+        c = xs @ xs2.T
+    k = shape_function(pack, c)
+    return pack["v"] * k * (r1[:, None] * r2[None, :]) ** pack["order"]
+
+
 _LEG_X, _LEG_W = roots_legendre(1000)  # harmonics/utils.py:23-25
 
 
@@ -262,6 +308,17 @@ def project_diag_variance_full(S: torch.Tensor, A: torch.Tensor) -> torch.Tensor
     return torch.sum((S @ A[None]) * A[None], dim=-2).T
 
 
+def project_variance_tril(Lq: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """variational.py:330-351: (Lq^T A)^T (Lq^T A) -> [P, N, N]."""
+    tmp = Lq.transpose(-1, -2) @ A[None]
+    return tmp.transpose(-1, -2) @ tmp
+
+
+def project_variance_full(S: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """variational.py:443-464: A^T S A -> [P, N, N]."""
+    return A[None].transpose(-1, -2) @ (S @ A[None])
+
+
 def prior_KL(mu: torch.Tensor, cov: torch.Tensor, tril: bool = True) -> torch.Tensor:
     """variational.py:225-240 with logdet/trace of :262-286 (TriL) or :375-399 (full)."""
     KL = -0.5 * torch.tensor(float(mu.numel()), dtype=DT)
@@ -323,6 +380,19 @@ def predict_diag(pack, X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     else:
         qv = project_diag_variance_full(pack["Sigma"], A)
     return fmu, cond_var[..., None] + qv  # model.py:136-138
+
+
+def predict(pack, X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """model.py:231-259 with conditional() of :103-145: mean [N, P], covariance [P, N, N]
+    = K(X) - A^T A (spherical_harmonics.py:391-393) + the projected q covariance."""
+    A = projection(pack, X)
+    fmu = project_mean(pack["mu"], A)
+    cond_cov = K(pack, X) - A.T @ A
+    if "Lq" in pack:
+        qc = project_variance_tril(pack["Lq"], A)
+    else:
+        qc = project_variance_full(pack["Sigma"], A)
+    return fmu, cond_cov + qc
 
 
 def var_exp(pack, fmu, fvar, Y) -> torch.Tensor:

@@ -17,6 +17,31 @@ from . import debug  # noqa: F401
 Array = _np.ndarray
 
 
+class _At:
+    """`x.at[idx].set(v)` of jax arrays (functional update), used by gpfy/spherical.py:341."""
+
+    def __init__(self, arr):
+        self._arr = arr
+        self._idx = None
+
+    def __getitem__(self, idx):
+        self._idx = idx
+        return self
+
+    def set(self, value):
+        out = _np.array(self._arr, copy=True)
+        out[self._idx] = value
+        return out.view(_ShimArray)
+
+
+class _ShimArray(_np.ndarray):
+    """ndarray with the `.at` property; only what `vmap` returns needs it."""
+
+    @property
+    def at(self):
+        return _At(self)
+
+
 class _Config:
     def update(self, *_a, **_k):
         return None
@@ -43,7 +68,7 @@ def vmap(fun, in_axes=0, out_axes=0):
         for i in range(n):
             sl = tree_util.tree_map(lambda a: _np.asarray(a)[i], args)
             outs.append(fun(*sl))
-        return tree_util.tree_map(lambda *xs: _np.stack([_np.asarray(x) for x in xs], 0), *outs)
+        return tree_util.tree_map(lambda *xs: _np.stack([_np.asarray(x) for x in xs], 0).view(_ShimArray), *outs)
 
     return mapped
 

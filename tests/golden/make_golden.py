@@ -137,6 +137,18 @@ def build_case(name, kernel, F, Tr, input_dim, N, lik, q, P=1, projection_dim=No
     out["o_elbo"] = np.array(elbo(param, m, q, lik, (X, Y)))
     out["o_elbo_ds"] = np.array(elbo(param, m, q, lik, (X, Y), dataset_size=10 * N))
 
+    # ---- the kernel-matrix side: K, K2, shape_function, full predictive covariance ----
+    X2 = X[:7] * 0.9 + 0.1
+    out["X2"] = X2
+    out["o_K"] = np.array(kernel.K(param, X))
+    out["o_K_cross"] = np.array(kernel.K(param, X, X2))
+    out["o_K2_cross"] = np.array(kernel.K2(param, X, X2))
+    out["shape_x"] = np.linspace(-1.0, 1.0, 41)
+    out["o_shape"] = np.array(kernel.shape_function(param, jnp.asarray(out["shape_x"])))
+    out["o_project_variance"] = np.array(q.project_variance(param, A))
+    pm, pc = m.predict(param, X)
+    out["o_predict_cov"] = np.array(pc)
+
     # ---- central finite differences of the reference elbo along stored random directions ----
     def with_leaf(path, val):
         pp = copy_tree(param.params)

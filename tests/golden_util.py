@@ -39,6 +39,13 @@ def golden_pack(g, eig=None):
         pack["Sigma"] = g["p_Sigma"]
     if "p_sigma2" in g:
         pack["sigma2"] = g["p_sigma2"]
+    # shape-function description (kernel-matrix side only)
+    pack["kernel"] = str(g["meta_kernel"])
+    if pack["kernel"] == "PolynomialDecay":
+        pack["truncation_level"] = int(g["meta_truncation_level"])
+        pack["beta"] = g["p_beta"]
+    else:
+        pack["depth"] = int(g["meta_depth"])
     return pack
 
 

@@ -53,6 +53,26 @@ def test_forward_functions_match_reference(name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_kernel_matrix_side_matches_reference(name):
+    """K, K2, shape_function, project_variance and the full predictive covariance."""
+    g = load(name)
+    pack = O.pack_to_torch(golden_pack(g))
+    if "beta" in pack:
+        pack["beta"] = O.T(pack["beta"])
+    X, X2 = O.T(g["X"]), O.T(g["X2"])
+    assert rel_err(O.shape_function(pack, O.T(g["shape_x"])).numpy(), g["o_shape"]) < TOL
+    assert rel_err(O.K(pack, X).numpy(), g["o_K"]) < TOL
+    assert rel_err(O.K(pack, X, X2).numpy(), g["o_K_cross"]) < TOL
+    assert rel_err(O.K(pack, X, X2, unit_diagonal=False).numpy(), g["o_K2_cross"]) < TOL
+    A = O.projection(pack, X)
+    pv = O.project_variance_tril(pack["Lq"], A) if "Lq" in pack else O.project_variance_full(pack["Sigma"], A)
+    assert rel_err(pv.numpy(), g["o_project_variance"]) < 1e-11
+    fmu, cov = O.predict(pack, X)
+    assert rel_err(fmu.numpy(), g["o_fmu"]) < 1e-11
+    assert rel_err(cov.numpy(), g["o_predict_cov"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_eigenvalues_match_reference(name):
     g = load(name)
     F = int(g["meta_F"])
