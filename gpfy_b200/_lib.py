@@ -40,6 +40,27 @@ class GpfyStepLayout(ctypes.Structure):
                                               "c_w", "c_b", "c_v", "c_beta", "c_eig", "c_deig", "c_s2", "c_mu", "c_sig", "c_V", "c_total")]
 
 
+MAX_SHAPE_LEVELS = 64
+SHAPE_ARCCOSINE, SHAPE_NTK, SHAPE_POLYDECAY = 0, 1, 2
+
+
+class GpfyShapeFn(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("kind", ctypes.c_int32), ("depth", ctypes.c_int32), ("order", ctypes.c_int32),
+                ("num_levels", ctypes.c_int32), ("grid_resolution", ctypes.c_int32), ("coef", ctypes.c_double * MAX_SHAPE_LEVELS)]
+
+
+def make_shape_fn(kind, depth=1, order=1, coef=(), grid_resolution=100_000):
+    if len(coef) > MAX_SHAPE_LEVELS:
+        raise GpfyError(f"truncation level {len(coef)} exceeds {MAX_SHAPE_LEVELS}")
+    fn = GpfyShapeFn()
+    fn.struct_size = ctypes.sizeof(GpfyShapeFn)
+    fn.kind, fn.depth, fn.order = int(kind), int(depth), int(order)
+    fn.num_levels, fn.grid_resolution = len(coef), int(grid_resolution)
+    for i, c in enumerate(coef):
+        fn.coef[i] = float(c)
+    return fn
+
+
 class GpfyError(RuntimeError):
     pass
 
@@ -75,6 +96,11 @@ _SIGNATURES = {
     "gpfy_to_sphere": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),
     "gpfy_variational_expectations": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),
     "gpfy_project_q": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P, _P, ctypes.c_size_t]),
+    "gpfy_kmat_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(GpfyDesc), ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "gpfy_shape_function": (ctypes.c_int, [_P, ctypes.POINTER(GpfyShapeFn), ctypes.c_double, _P, ctypes.c_int64, _P]),
+    "gpfy_kernel_matrix": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyShapeFn), ctypes.c_int64, _P, ctypes.c_int64, _P,
+                                          _P, _P, _P, ctypes.c_int, _P, _P, ctypes.c_size_t]),
+    "gpfy_project_variance": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, ctypes.c_int, _P, _P, _P, ctypes.c_size_t]),
 }
 
 _lib = None

@@ -5,7 +5,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libgpfy_b200.so")
-SOURCES = ["gemm.cu", "svgp.cu", "step.cu", "xla_ffi_shim.cc"]
+SOURCES = ["gemm.cu", "svgp.cu", "step.cu", "kmat.cu", "xla_ffi_shim.cc"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "gpfy_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

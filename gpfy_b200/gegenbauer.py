@@ -43,7 +43,8 @@ def gegenbauer_fwd(level, alpha, x):
 
 class GegenbauerLookupTable:
     """gegenbauer.py:88-147.  The reference uses the table only for C_n(1) (exact at the last grid
-    node) and for PolynomialDecay's shape function (out of scope); `__call__` interpolates on the host."""
+    node) and for PolynomialDecay's shape function; `__call__` interpolates on the host (init-time algebra), the device
+    kernels re-evaluate the two bracketing grid nodes instead of storing the table (csrc/kmat.cu)."""
 
     def __init__(self, max_level: int, alpha: float, grid_resolution: int = 100_000):
         self.max_level, self.alpha, self.grid_resolution = int(max_level), float(alpha), int(grid_resolution)

@@ -3,7 +3,7 @@
 `conditional(sh, q)` returns a GP that carries the same four closures as the reference AND remembers
 (sh, q), so `predict_diag` runs as ONE fused device call (`gpfy_predict_diag`) instead of materialising
 the [M, N] projection; the closures remain available (and are tested to agree with the fused path, like
-tests/test_model.py:160-183 does for the reference).  `cov` / `predict` (N x N) are out of scope."""
+tests/test_model.py:160-183 does for the reference).  `cov` / `predict` build the [P, N, N] covariance on the device (csrc/kmat.cu)."""
 import dataclasses
 from typing import Callable, Optional, Tuple
 
@@ -56,10 +56,25 @@ class GP:
         return lambda x: self.kernel.K_diag(param, x)
 
     def cov(self, param: Param):
-        raise NotImplementedError("GP.cov (N x N) is outside the accelerated path (SURVEY.md §2)")
+        """model.py:183-199: the [P, N, N] conditional covariance, or the prior K(X) [N, N]."""
+        if self.conditional_fn:
+            return lambda x: self.predict(param, x)[1]
+        return lambda x: self.kernel.K(param, x)
 
     def predict(self, param: Param, X):
-        raise NotImplementedError("GP.predict (N x N covariance) is outside the accelerated path (SURVEY.md §2)")
+        """(mean [N, P], covariance [P, N, N]) — model.py:231-259.  K(X) - A^T A + A^T S A is formed as
+        K + A^T (S - I) A in one pass over the output (gpfy_project_variance with base = K)."""
+        if self.conditional_fn:
+            if self._sh is not None:
+                sh, q, kernel = self._sh, self._q, self.kernel
+                A = self.conditional_fn[0](param, X)
+                K = kernel.K(param, X)
+                mean, _ = q._hot(param).project_q(A, q.mu(param), q.cov_part(param))
+                return mean, q._hot(param).project_variance(A, q.cov_part(param), subtract_identity=True, base=K)
+            proj_fun, cond_mean_fun, cond_cov_fun, _ = self.conditional_fn
+            proj = proj_fun(param, X)
+            return cond_mean_fun(param, proj), cond_cov_fun(param, X, proj)
+        return _zeros(X), self.kernel.K(param, X)
 
     # ---- the fused path ----
     def hot_args(self, param: Param, lik=None):

@@ -44,6 +44,16 @@ def gegenbauer(level, alpha, x, with_grad=False, device=None):
     return (out, dout) if with_grad else out
 
 
+def shape_function(fn, alpha, x, device=None):
+    """Elementwise shape function of a Spherical kernel (`fn` from `_lib.make_shape_fn`) — spherical.py:438-455, 479-500, 589-611."""
+    lib = _lib.load()
+    device = require_cuda(device)
+    xt = _as_dev(x, device)
+    out = torch.empty_like(xt)
+    _lib.check(lib.gpfy_shape_function(_stream(device), ctypes.byref(fn), float(alpha), _ptr(xt), xt.numel(), _ptr(out)))
+    return out
+
+
 class HotPath:
     """One descriptor + cached scratch.  Mirrors the static configuration of
     (SphericalHarmonics, kernel, q, likelihood) in the reference."""
@@ -243,6 +253,43 @@ class HotPath:
         _lib.check(self.lib.gpfy_project_q(_stream(self.device), ctypes.byref(self.desc), n, _ptr(A), _ptr(mu), _ptr(sigma),
                                            _ptr(mean), _ptr(var), _ptr(ws), ws.numel()))
         return mean, var
+
+    def _kmat_workspace(self, n1, n2):
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.gpfy_kmat_workspace_bytes(ctypes.byref(self.desc), int(n1), int(n2), ctypes.byref(nbytes)))
+        ws = self._ws.get("kmat")
+        if ws is None or ws.numel() < nbytes.value:
+            ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)
+            self._ws["kmat"] = ws
+        return ws
+
+    def kernel_matrix(self, fn, X, X2, w, b, variance, unit_diagonal=True):
+        """K [N, N2] of a Spherical kernel with shape function `fn` — spherical.py:318-352 (`K`), :354-382 (`K2`,
+        `unit_diagonal=False`).  X2 None: pairs of X."""
+        X = self._dev(X)
+        X2 = None if X2 is None else self._dev(X2)
+        n1 = X.shape[0]
+        n2 = n1 if X2 is None else X2.shape[0]
+        w, b, variance = self._dev(w), self._dev(b), self._dev(variance)
+        K = torch.empty((n1, n2), dtype=torch.float64, device=self.device)
+        if n1 == 0 or n2 == 0:   # an empty X2 has a null data pointer, which the C-ABI reads as "pairs of X"
+            return K
+        ws = self._kmat_workspace(n1, 0 if X2 is None else n2)
+        _lib.check(self.lib.gpfy_kernel_matrix(_stream(self.device), ctypes.byref(self.desc), ctypes.byref(fn), n1, _ptr(X), n2, _ptr(X2),
+                                               _ptr(w), _ptr(b), _ptr(variance), int(bool(unit_diagonal)), _ptr(K), _ptr(ws), ws.numel()))
+        return K
+
+    def project_variance(self, A, sigma, subtract_identity=False, base=None):
+        """base + A^T (S_p - [subtract_identity] I) A -> [P, N, N] — variational.py:330-351 / :443-464; with base = K(X) and
+        subtract_identity it is the covariance of `GP.predict` (model.py:129-131, spherical_harmonics.py:391-393)."""
+        A, sigma = self._dev(A), self._dev(sigma)
+        base = None if base is None else self._dev(base)
+        n = A.shape[1]
+        out = torch.empty((self.P, n, n), dtype=torch.float64, device=self.device)
+        ws = self._kmat_workspace(n, 0)
+        _lib.check(self.lib.gpfy_project_variance(_stream(self.device), ctypes.byref(self.desc), n, _ptr(A), _ptr(sigma),
+                                                  int(bool(subtract_identity)), _ptr(base), _ptr(out), _ptr(ws), ws.numel()))
+        return out
 
     def inducing_basis(self, V, normalise=True):
         """(vhat [M, dim], lcat [sum m_l^2]) from the raw fundamental points — spherical_harmonics.py:194-239, 265-288."""

@@ -1,8 +1,9 @@
-"""Spherical kernels — the thin slice of gpfy/spherical.py the hot path needs:
-`init`, `_scale_X`, `to_sphere`, `K_diag`, `eigenvalues` (NTK / ArcCosine / PolynomialDecay).
+"""Spherical kernels (mirror of gpfy/spherical.py): `init`, `_scale_X`, `to_sphere`, `K_diag`, `eigenvalues`,
+`shape_function`, `K`, `K2` for NTK / ArcCosine / PolynomialDecay.
 
-`K`, `K2`, `kappa`-based prior covariances and PolynomialDecay's lookup-table shape function only
-serve the full N x N `GP.cov/predict` and are out of scope; calling them raises.
+Everything that touches the N data rows runs on the device (`to_sphere`, `K_diag`, `K`, `K2`, and `shape_function` of a
+CUDA tensor).  `shape_function` of a host array is the N-independent parameter algebra of `init` (the Funk-Hecke
+quadrature of the eigenvalues) and stays in numpy like the bijectors.
 """
 import dataclasses
 import math
@@ -10,7 +11,9 @@ from typing import Optional
 
 import numpy as np
 
-from . import _runtime
+import torch
+
+from . import _lib, _runtime, ops
 from .gegenbauer import GegenbauerLookupTable, gegenbauer_host
 from .harmonics.utils import funk_hecke_lambda
 from .param import Param, identity
@@ -81,12 +84,33 @@ class Spherical:
         return float(param.params[self.name]["variance"]) * r ** (2 * self.order)
 
     def shape_function(self, param: Param, x):
+        """spherical.py:251-263: derived classes implement it; CUDA tensors are evaluated on the device."""
+        if torch.is_tensor(x) and x.is_cuda:
+            alpha = param.constants["sphere"]["alpha"] if "sphere" in param.constants else 0.0
+            return ops.shape_function(self._shape_fn(param), alpha, x, device=x.device)
+        return self._shape_function_host(param, x)
+
+    def _shape_function_host(self, param: Param, x):
         raise NotImplementedError
 
-    def K(self, *a, **k):
-        raise NotImplementedError("Spherical.K (N x N prior covariance) is outside the accelerated path (SURVEY.md §2)")
+    def _shape_fn(self, param: Param):
+        raise NotImplementedError
 
-    K2 = K
+    def _kernel_matrix(self, param: Param, X, X2, unit_diagonal: bool):
+        kp = param.params[self.name]
+        d = int(np.shape(X)[-1])
+        hp = _runtime.hot_path(d, [1], weight_mode=self._weight_mode(param), kernel_order=self.order,
+                               projection_dim=self._projection_dim(param))
+        return hp.kernel_matrix(self._shape_fn(param), X, X2, kp["weight_variances"], kp["bias_variance"], kp["variance"],
+                                unit_diagonal=unit_diagonal)
+
+    def K(self, param: Param, X, X2=None):
+        """spherical.py:318-352: [N, N2] covariance; the diagonal cosine is exactly 1 when X2 is None."""
+        return self._kernel_matrix(param, X, X2, True)
+
+    def K2(self, param: Param, X, X2=None):
+        """spherical.py:354-382: the same matrix point pair by point pair (no diagonal fix-up)."""
+        return self._kernel_matrix(param, X, X2, False)
 
 
 def _kappa(u, order: int):
@@ -107,7 +131,10 @@ class ArcCosine(Spherical):
         if self.order not in {0, 1, 2}:
             raise ValueError("Requested order is not implemented.")
 
-    def shape_function(self, param, x):
+    def _shape_fn(self, param):
+        return _lib.make_shape_fn(_lib.SHAPE_ARCCOSINE, depth=self.depth, order=self.order)
+
+    def _shape_function_host(self, param, x):
         """spherical.py:438-455."""
         y = np.clip(x, -1.0, 1.0)
         for _ in range(self.depth):
@@ -123,7 +150,10 @@ class NTK(Spherical):
     def __post_init__(self):
         object.__setattr__(self, "order", 1)
 
-    def shape_function(self, param, x):
+    def _shape_fn(self, param):
+        return _lib.make_shape_fn(_lib.SHAPE_NTK, depth=self.depth)
+
+    def _shape_function_host(self, param, x):
         """spherical.py:479-500."""
         x = np.clip(x, -1.0, 1.0)
         a, y = x, x
@@ -167,5 +197,19 @@ class PolynomialDecay(Spherical):
         lv = np.clip(np.asarray(levels, dtype=np.int64), 0, self.truncation_level - 1)
         return eig[lv], deig[lv]
 
-    def shape_function(self, param, x):
-        raise NotImplementedError("PolynomialDecay.shape_function only serves the N x N covariance (out of scope)")
+    def _shape_coef(self, param):
+        """lambda_n (n + alpha) / alpha, n < truncation_level (spherical.py:605-608)."""
+        alpha = param.constants["sphere"]["alpha"]
+        levels = np.arange(self.truncation_level)
+        return self.eigenvalues(param, levels) * (levels.astype(np.float64) + alpha) / alpha
+
+    def _shape_fn(self, param):
+        geg = param.constants["sphere"]["gegenbauer_lookup_table"]
+        return _lib.make_shape_fn(_lib.SHAPE_POLYDECAY, coef=self._shape_coef(param), grid_resolution=geg.grid_resolution)
+
+    def _shape_function_host(self, param, x):
+        """spherical.py:589-611: sum_n lambda_n (n + alpha) / alpha C_n^alpha(x) through the lookup table."""
+        x = np.clip(np.asarray(x, dtype=np.float64), -1.0, 1.0)
+        alpha = param.constants["sphere"]["alpha"]
+        geg = param.constants["sphere"]["gegenbauer_lookup_table"]
+        return sum(c * geg(n, alpha, x) for n, c in enumerate(self._shape_coef(param)))

@@ -8,6 +8,7 @@ import dataclasses
 from typing import List, Optional
 
 import numpy as np
+import torch
 from scipy.special import comb
 
 from . import _runtime
@@ -166,6 +167,10 @@ class SphericalHarmonics:
             return kernel.K_diag(param, x) - (proj * proj).sum(-2)
 
         def conditional_cov_fun(param, x, proj):
-            raise NotImplementedError("the N x N conditional covariance is outside the accelerated path (SURVEY.md §2)")
+            # K(x) - proj^T proj (:391-393) as one accumulate pass: base = K, S = 0, minus the identity
+            M = proj.shape[0]
+            hp = _runtime.hot_path(1, [M], num_outputs=1, q_kind="fullcov")
+            zero = torch.zeros((1, M, M), dtype=torch.float64, device=hp.device)
+            return hp.project_variance(proj, zero, subtract_identity=True, base=kernel.K(param, x))[0]
 
         return (project_fun, conditional_cov_fun, conditional_var_fun)

@@ -2,7 +2,7 @@
 
 Projections of an explicit projection matrix A [M, N] run on the device (`gpfy_project_q`); the
 whitened-prior KL of the TriL parameterisation too (`gpfy_prior_kl_valgrad`).  O(M^2) accessors
-(`logdet`, `trace`) are host numpy.  `project_variance` (N x N) is out of scope."""
+(`logdet`, `trace`) are host numpy.  `project_variance` ([P, N, N]) is `gpfy_project_variance`."""
 import dataclasses
 from typing import Optional
 
@@ -62,7 +62,8 @@ class VariationalDistribution:
         return self._hot(param).project_q(A, self.mu(param), self.cov_part(param))[1]
 
     def project_variance(self, param: Param, A):
-        raise NotImplementedError("the N x N projected covariance is outside the accelerated path (SURVEY.md §2)")
+        """A^T S A -> [P, N, N] (variational.py:330-351 / :443-464)."""
+        return self._hot(param).project_variance(A, self.cov_part(param))
 
     def logdet(self, param: Param):
         raise NotImplementedError()

@@ -211,6 +211,41 @@ GPFY_API int gpfy_step_grad(void* stream, const GpfyDesc* desc, const GpfyStepLa
 GPFY_API int gpfy_step_adam(void* stream, int64_t n, double* theta, const double* grad, double* m1, double* m2,
                    const unsigned char* mask, double lr, double b1, double b2, double eps, int64_t step_count);
 
+/* ---- kernel-matrix side (dense N x N2 outputs) ---- */
+#define GPFY_MAX_SHAPE_LEVELS 64
+enum { GPFY_SHAPE_ARCCOSINE = 0, GPFY_SHAPE_NTK = 1, GPFY_SHAPE_POLYDECAY = 2 };
+/* The shape function of a Spherical kernel (host struct, POD):
+ *   ARCCOSINE: kappa_order nested `depth` times (spherical.py:438-455); NTK: spherical.py:479-500;
+ *   POLYDECAY: sum_n coef[n] C_n^alpha(x), C_n interpolated linearly on linspace(-1, 1, grid_resolution) like
+ *   GegenbauerLookupTable (gegenbauer.py:111-119, 152-167); coef[n] = kernel.eigenvalues[n] (n + alpha) / alpha for
+ *   n < num_levels = truncation_level (spherical.py:602-611) - N-independent, computed by the caller. */
+typedef struct GpfyShapeFn {
+  uint32_t struct_size; /* sizeof(GpfyShapeFn) */
+  int32_t kind;         /* GPFY_SHAPE_* */
+  int32_t depth;        /* ArcCosine / NTK */
+  int32_t order;        /* ArcCosine: 0, 1, 2 */
+  int32_t num_levels;   /* PolynomialDecay truncation_level */
+  int32_t grid_resolution; /* PolynomialDecay lookup grid (reference default 100000) */
+  double coef[GPFY_MAX_SHAPE_LEVELS];
+} GpfyShapeFn;
+
+/* Scratch for gpfy_kernel_matrix (n1, n2 rows; n2 = 0 when X2 is NULL) and gpfy_project_variance (n1 = N, n2 = 0). */
+GPFY_API int gpfy_kmat_workspace_bytes(const GpfyDesc* desc, int64_t n1, int64_t n2, size_t* bytes /* host */);
+/* out[i] = shape_function(x[i]), input squashed to [-1, 1] first (replaces Spherical.shape_function of the three kernels). */
+GPFY_API int gpfy_shape_function(void* stream, const GpfyShapeFn* fn /* host */, double alpha, const double* x, int64_t n, double* out);
+/* K[n1, n2] = variance * shape(<xhat_i, xhat2_j>) * (r_i r2_j)^order  (replaces Spherical.K, spherical.py:318-352, and
+ * Spherical.K2, :354-382).  X2 == NULL: pairs of X1; `unit_diagonal` then forces the diagonal cosine to exactly 1 as K
+ * does (:340-341) - K2 passes 0. */
+GPFY_API int gpfy_kernel_matrix(void* stream, const GpfyDesc* desc, const GpfyShapeFn* fn /* host */, int64_t n1, const double* X1,
+                       int64_t n2, const double* X2, const double* w, const double* b, const double* variance,
+                       int unit_diagonal, double* K, void* workspace, size_t workspace_bytes);
+/* out[p] = base + A^T (S_p - subtract_identity * I) A, [P, N, N], with S_p = L_p L_p^T (GPFY_Q_TRIL) or Sigma_p
+ * (replaces VariationalDistribution*.project_variance, variational.py:330-351 / :443-464; with base = K(X) and
+ * subtract_identity = 1 it is the conditional covariance of GP.predict / GP.cov, model.py:129-131, 231-259 and
+ * spherical_harmonics.py:391-393).  A is the [M, N] projection; base [N, N] may be NULL. */
+GPFY_API int gpfy_project_variance(void* stream, const GpfyDesc* desc, int64_t n, const double* A, const double* sigma,
+                          int subtract_identity, const double* base, double* out, void* workspace, size_t workspace_bytes);
+
 /* Sum of the packed buffers of all ranks, in place, on `stream` (the single exchange step).
  * `nccl_comm` is an ncclComm_t owned by the caller; NCCL is resolved at run time from the process
  * (the host framework's copy), so this library has no link-time NCCL dependency. */

@@ -162,3 +162,69 @@ def test_device_trainer_matches_host_training_loop(name):
     dev_param = tr.param()
     for a, b in zip(tree_leaves(dev_param.params), tree_leaves(host_param.params)):
         assert rel_err(a, b) < 1e-8
+
+
+@pytest.mark.parametrize("name", API_CASES)
+def test_kernel_matrix_side_matches_reference(name):
+    """K, K2, shape_function, project_variance, GP.predict / GP.cov against the reference's outputs."""
+    from gpfy_b200.model import GP
+    g = load(name)
+    o = objects_from_golden(g)
+    kernel, q, m, param = o["kernel"], o["q"], o["m"], o["param"]
+    X, X2 = g["X"], g["X2"]
+    sx = torch.as_tensor(g["shape_x"], device="cuda")
+    assert rel_err(_np(kernel.shape_function(param, sx)), g["o_shape"]) < TOL
+    assert rel_err(np.asarray(kernel.shape_function(param, g["shape_x"])), g["o_shape"]) < TOL     # host (init-time) variant
+    K = kernel.K(param, X)
+    assert rel_err(_np(K), g["o_K"]) < TOL
+    assert rel_err(_np(kernel.K(param, X, X2)), g["o_K_cross"]) < TOL
+    assert rel_err(_np(kernel.K2(param, X, X2)), g["o_K2_cross"]) < TOL
+    # reference tests/test_spherical.py: diag(K) == K_diag, K symmetric, K2(X) == K(X) up to the diagonal fix-up
+    assert rel_err(_np(torch.diagonal(K)), g["o_K_diag"]) < 1e-13
+    assert float((K - K.T).abs().max()) == 0.0
+    # ... where the cosine 1 - O(eps) sits on the sqrt(1 - u^2) branch point: 1e-8-level differences, as in the reference
+    K2 = kernel.K2(param, X)
+    off = ~torch.eye(K.shape[0], dtype=torch.bool, device=K.device)
+    assert rel_err(_np(K2 * off), _np(K * off)) < TOL and rel_err(_np(torch.diagonal(K2)), g["o_K_diag"]) < 1e-6
+    A = m.conditional_fn[0](param, X)
+    assert rel_err(_np(q.project_variance(param, A)), g["o_project_variance"]) < TOL
+    mean, cov = m.predict(param, X)
+    assert rel_err(_np(mean), g["o_fmu"]) < TOL
+    assert tuple(cov.shape) == g["o_predict_cov"].shape
+    assert rel_err(_np(cov), g["o_predict_cov"]) < TOL
+    assert rel_err(_np(m.cov(param)(X)), g["o_predict_cov"]) < TOL
+    # the closures compose to the same thing (model.py:129-131), and its diagonal is predict_diag's variance
+    _, _, cond_cov_fun, __ = m.conditional_fn
+    assert rel_err(_np(cond_cov_fun(param, X, A)), g["o_predict_cov"]) < TOL
+    assert rel_err(_np(torch.diagonal(cov, dim1=-2, dim2=-1).T), g["o_fvar"]) < 1e-9
+    prior_mean, prior_cov = GP(kernel).predict(param, X)      # prior process: zero mean, K(X)
+    assert float(prior_mean.abs().max()) == 0.0 and rel_err(_np(prior_cov), g["o_K"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["d8_F6_T12", "s2_deg10_polydecay", "d6_proj3_arccos"])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (63, 65), (200, 77), (513, 300)])
+def test_kernel_matrix_ragged_sizes_against_oracle(name, n1, n2):
+    """Tile-edge coverage (64 x 64 tiles): sizes around and across tile boundaries, against the oracle on seeded inputs."""
+    g = load(name)
+    o = objects_from_golden(g)
+    kernel, q, m, param = o["kernel"], o["q"], o["m"], o["param"]
+    pack = O.pack_to_torch(golden_pack(g))
+    if "beta" in pack:
+        pack["beta"] = O.T(pack["beta"])
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    d = g["X"].shape[1]
+    X, X2 = rng.standard_normal((n1, d)), rng.standard_normal((n2, d))
+    assert rel_err(_np(kernel.K(param, X, X2)), O.K(pack, O.T(X), O.T(X2)).numpy()) < TOL
+    assert rel_err(_np(kernel.K(param, X)), O.K(pack, O.T(X)).numpy()) < TOL
+    mean, cov = m.predict(param, X)
+    omean, ocov = O.predict(pack, O.T(X))
+    assert rel_err(_np(mean), omean.numpy()) < TOL and rel_err(_np(cov), ocov.numpy()) < TOL
+    assert rel_err(_np(cov), _np(cov.transpose(-1, -2))) < 1e-13
+
+
+def test_kernel_matrix_empty_inputs():
+    g = load("d8_F6_T12")
+    o = objects_from_golden(g)
+    K = o["kernel"].K(o["param"], g["X"][:0])
+    assert tuple(K.shape) == (0, 0)
+    assert tuple(o["kernel"].K(o["param"], g["X"], g["X"][:0]).shape) == (g["X"].shape[0], 0)
