@@ -22,6 +22,8 @@ struct ShapeParams {
   int kind, depth, order, num_levels, grid_resolution;
   double alpha;
   double coef[GPFY_MAX_SHAPE_LEVELS];   // PolynomialDecay: lambda_n (n + alpha) / alpha (spherical.py:607-608)
+  double c1[GPFY_MAX_SHAPE_LEVELS];     // C_n = c1[n] x C_{n-1} - c2[n] C_{n-2}: 2 (n + alpha - 1) / n and
+  double c2[GPFY_MAX_SHAPE_LEVELS];     // (n + 2 alpha - 2) / n of gegenbauer.py:49, divided on the host
 };
 
 constexpr double kPi = 3.14159265358979323846;
@@ -62,9 +64,8 @@ __device__ __forceinline__ double polydecay_shape(const ShapeParams& sp, double 
   double a1 = 2.0 * al * xa, b1 = 2.0 * al * xb;   // C_1
   acc += sp.coef[1] * ((1.0 - t) * a1 + t * b1);
   for (int n = 2; n < sp.num_levels; ++n) {
-    const double dn = (double)n;
-    const double a2 = (2.0 * xa * (dn + al - 1.0) * a1 - (dn + 2.0 * al - 2.0) * a0) / dn;   // gegenbauer.py:49
-    const double b2 = (2.0 * xb * (dn + al - 1.0) * b1 - (dn + 2.0 * al - 2.0) * b0) / dn;
+    const double a2 = sp.c1[n] * xa * a1 - sp.c2[n] * a0;   // gegenbauer.py:49 with the division folded into the table
+    const double b2 = sp.c1[n] * xb * b1 - sp.c2[n] * b0;
     acc += sp.coef[n] * ((1.0 - t) * a2 + t * b2);
     a0 = a1; a1 = a2;
     b0 = b1; b1 = b2;
@@ -72,9 +73,10 @@ __device__ __forceinline__ double polydecay_shape(const ShapeParams& sp, double 
   return acc;
 }
 
+template <int KIND>
 __device__ __forceinline__ double shape_eval(const ShapeParams& sp, double x) {
   x = fmin(fmax(x, -1.0), 1.0);   // _squash (spherical.py:265-277)
-  if (sp.kind == GPFY_SHAPE_NTK) {   // spherical.py:493-500
+  if (KIND == GPFY_SHAPE_NTK) {   // spherical.py:493-500
     double a = x, y = x;
     for (int i = 0; i < sp.depth; ++i) {
       double k0, k1;
@@ -84,7 +86,7 @@ __device__ __forceinline__ double shape_eval(const ShapeParams& sp, double x) {
     }
     return y / (double)(sp.depth + 1);
   }
-  if (sp.kind == GPFY_SHAPE_ARCCOSINE) {   // spherical.py:452-455
+  if (KIND == GPFY_SHAPE_ARCCOSINE) {   // spherical.py:452-455
     double y = x;
     for (int i = 0; i < sp.depth; ++i) y = kappa(y, sp.order);
     return y;
@@ -92,71 +94,89 @@ __device__ __forceinline__ double shape_eval(const ShapeParams& sp, double x) {
   return polydecay_shape(sp, x);
 }
 
+#define KM_KIND_SWITCH(kind, ...)                                                        \
+  switch (kind) {                                                                        \
+    case GPFY_SHAPE_ARCCOSINE: { constexpr int KIND = GPFY_SHAPE_ARCCOSINE; __VA_ARGS__; } break; \
+    case GPFY_SHAPE_NTK: { constexpr int KIND = GPFY_SHAPE_NTK; __VA_ARGS__; } break;    \
+    default: { constexpr int KIND = GPFY_SHAPE_POLYDECAY; __VA_ARGS__; } break;          \
+  }
+
+template <int KIND>
 __global__ void shape_function_kernel(const __grid_constant__ ShapeParams sp, const double* __restrict__ x, int64_t n,
                                       double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = shape_eval(sp, x[i]);
+  if (i < n) out[i] = shape_eval<KIND>(sp, x[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K[i, j] = variance * shape(<xhat_i, xhat2_j>) * (r_i r2_j)^order       (spherical.py:336-352, 373-382)
-// One CTA per 64 x 64 tile; 256 threads, each 4 x 4 outputs with columns strided by 16 so that a warp stores two full
-// 128-byte row segments per instruction.  The shape function (acos / sqrt chains) dominates; the dim-long dot product is
-// plain FMA from shared memory.
+// One CTA per 64 x 64 tile, 256 threads.  Phase 1: each thread forms 4 x 4 cosines (plain FMA from shared memory, the
+// contraction is only dim long) and parks them in a shared 64 x 64 tile.  Phase 2: ONE rolled instance of the shape
+// function walks the tile row-major, so a warp evaluates 32 neighbouring columns and stores a full 256-byte row segment;
+// keeping a single copy of the acos / sqrt chains keeps the kernel a few hundred instructions instead of sixteen inlined
+// copies (the first version: 6 k instructions, instruction-fetch bound).
 // ------------------------------------------------------------------------------------------------
 constexpr int KT = 64;
 
-__global__ void __launch_bounds__(256) kernel_matrix_kernel(const __grid_constant__ ShapeParams sp, const double* __restrict__ xs1,
+template <int KIND>
+__global__ void __launch_bounds__(256, 4) kernel_matrix_kernel(const __grid_constant__ ShapeParams sp, const double* __restrict__ xs1,
                                                             const double* __restrict__ r1, int n1, const double* __restrict__ xs2,
                                                             const double* __restrict__ r2, int n2, int dim,
                                                             const double* __restrict__ variance, int kernel_order, int unit_diagonal,
                                                             double* __restrict__ K) {
   extern __shared__ double sm[];
   const int ld = dim | 1;   // odd row pitch: the 16 rows a half-warp reads fall on 16 distinct bank pairs
-  double* a = sm;            // [64][ld]
-  double* b = sm + KT * ld;  // [64][ld]
+  double* a = sm;                  // [64][ld]
+  double* b = a + KT * ld;         // [64][ld]
+  double* ct = b + KT * ld;        // [64][64] cosines
+  double* ra = ct + KT * KT;       // [64] radii of the tile rows
+  double* rb = ra + KT;            // [64] radii of the tile columns
   const int i0 = blockIdx.y * KT, j0 = blockIdx.x * KT;
   for (int e = threadIdx.x; e < KT * dim; e += 256) {
     const int row = e / dim, c = e - row * dim;
     a[row * ld + c] = i0 + row < n1 ? xs1[(int64_t)(i0 + row) * dim + c] : 0.0;
     b[row * ld + c] = j0 + row < n2 ? xs2[(int64_t)(j0 + row) * dim + c] : 0.0;
   }
+  if (threadIdx.x < KT) ra[threadIdx.x] = i0 + threadIdx.x < n1 ? r1[i0 + threadIdx.x] : 0.0;
+  else if (threadIdx.x < 2 * KT) rb[threadIdx.x - KT] = j0 + threadIdx.x - KT < n2 ? r2[j0 + threadIdx.x - KT] : 0.0;
   __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-  for (int c = 0; c < dim; ++c) {
-    double av[4], bv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) av[u] = a[(ty + 16 * u) * ld + c];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) bv[v] = b[(tx + 16 * v) * ld + c];
+  {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
-  }
-  const double var = variance[0];
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int c = 0; c < dim; ++c) {
+      double av[4], bv[4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int i = i0 + ty + 16 * u;
-    if (i >= n1) continue;
-    const double ri = r1[i];
+      for (int u = 0; u < 4; ++u) av[u] = a[(ty + 16 * u) * ld + c];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int j = j0 + tx + 16 * v;
-      if (j >= n2) continue;
-      double c = acc[u][v];
-      if (unit_diagonal && i == j) c = 1.0;   // spherical.py:340-341
-      const double k = shape_eval(sp, c);
-      const double rr = ri * r2[j];
-      double rp = 1.0;
-      for (int o = 0; o < kernel_order; ++o) rp *= rr;
-      K[(int64_t)i * n2 + j] = var * k * rp;
+      for (int v = 0; v < 4; ++v) bv[v] = b[(tx + 16 * v) * ld + c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) ct[(ty + 16 * u) * KT + tx + 16 * v] = acc[u][v];
+  }
+  __syncthreads();
+  const double var = variance[0];
+#pragma unroll 1
+  for (int e = threadIdx.x; e < KT * KT; e += 256) {
+    const int row = e >> 6, col = e & 63;
+    const int i = i0 + row, j = j0 + col;
+    if (i >= n1 || j >= n2) continue;
+    double c = ct[e];
+    if (unit_diagonal && i == j) c = 1.0;   // spherical.py:340-341
+    const double k = shape_eval<KIND>(sp, c);
+    const double rr = ra[row] * rb[col];
+    double rp = 1.0;
+    for (int o = 0; o < kernel_order; ++o) rp *= rr;
+    K[(int64_t)i * n2 + j] = var * k * rp;
   }
 }
 
@@ -239,7 +259,11 @@ static int make_shape_params(const GpfyShapeFn* fn, double alpha, ShapeParams* s
   if (fn->kind == GPFY_SHAPE_POLYDECAY) {
     if (fn->num_levels < 1 || fn->num_levels > GPFY_MAX_SHAPE_LEVELS) { set_error("truncation level %d outside [1, %d]", fn->num_levels, GPFY_MAX_SHAPE_LEVELS); return GPFY_EUNSUPPORTED; }
     if (fn->grid_resolution < 2) { set_error("grid_resolution must be >= 2"); return GPFY_EINVAL; }
-    for (int i = 0; i < fn->num_levels; ++i) sp->coef[i] = fn->coef[i];
+    for (int i = 0; i < fn->num_levels; ++i) {
+      sp->coef[i] = fn->coef[i];
+      sp->c1[i] = i ? 2.0 * (i + alpha - 1.0) / i : 0.0;
+      sp->c2[i] = i ? (i + 2.0 * alpha - 2.0) / i : 0.0;
+    }
   } else {
     if (fn->depth < 0) { set_error("negative depth"); return GPFY_EINVAL; }
     if (fn->kind == GPFY_SHAPE_ARCCOSINE && (fn->order < 0 || fn->order > 2)) { set_error("ArcCosine order %d not in {0, 1, 2}", fn->order); return GPFY_EINVAL; }
@@ -267,7 +291,7 @@ int gpfy_shape_function(void* stream, const GpfyShapeFn* fn, double alpha, const
   ShapeParams sp;
   GPFY_TRY(make_shape_params(fn, alpha, &sp));
   if (n == 0) return GPFY_OK;
-  KM_LAUNCH(shape_function_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, sp, x, n, out);
+  KM_KIND_SWITCH(sp.kind, KM_LAUNCH(shape_function_kernel<KIND>, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, sp, x, n, out));
   return GPFY_OK;
 }
 
@@ -294,9 +318,12 @@ int gpfy_kernel_matrix(void* stream, const GpfyDesc* desc, const GpfyShapeFn* fn
   GPFY_TRY(gpfy_to_sphere(stream, desc, n1, X1, w, b, xs1, r1));
   if (!self) GPFY_TRY(gpfy_to_sphere(stream, desc, n2, X2, w, b, xs2, r2));
   dim3 grid((unsigned)((n2 + KT - 1) / KT), (unsigned)((n1 + KT - 1) / KT));
-  const size_t smem = (size_t)2 * KT * (s.dim | 1) * 8;
-  KM_LAUNCH(kernel_matrix_kernel, grid, 256, smem, st, sp, xs1, r1, (int)n1, xs2, r2, (int)n2, s.dim, variance, desc->kernel_order,
-            self && unit_diagonal, K);
+  const size_t smem = ((size_t)2 * KT * (s.dim | 1) + KT * KT + 2 * KT) * 8;
+  KM_KIND_SWITCH(sp.kind, {
+    if (smem > 48 * 1024) GPFY_CUDA_OK(cudaFuncSetAttribute(kernel_matrix_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KM_LAUNCH(kernel_matrix_kernel<KIND>, grid, 256, smem, st, sp, xs1, r1, (int)n1, xs2, r2, (int)n2, s.dim, variance,
+              desc->kernel_order, self && unit_diagonal, K);
+  });
   return GPFY_OK;
 }
 
