@@ -108,6 +108,74 @@ __global__ void step_adam_kernel(int64_t n, double* __restrict__ theta, const do
   if (mask[i]) theta[i] += -lr * (a / bc1) / (sqrt(v / bc2) + eps);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shuffled minibatches without a permutation array (replaces the HuggingFace
+// `dataset.shuffle().iter(batch_size, drop_last_batch=True)` generator of optimization.py:31-58).
+// Row j of an epoch is pi(j), pi a keyed bijection of [0, n): a balanced Feistel network on the smallest even number
+// of bits covering n, cycle-walked back into range (at most 4 expected walks).  O(1) state per epoch (the round keys),
+// no sort, no n-sized index buffer; the batch gather reads each selected row once and writes a dense [batch, row] slab.
+// ------------------------------------------------------------------------------------------------
+struct FeistelKeys { unsigned int k[GPFY_SHUFFLE_ROUNDS]; };
+
+__host__ __device__ __forceinline__ unsigned int feistel_round(unsigned int r, unsigned int key) {
+  unsigned int h = r * 0x9E3779B1u + key;
+  h ^= h >> 16; h *= 0x85EBCA6Bu;
+  h ^= h >> 13; h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+__host__ __device__ __forceinline__ int64_t feistel_permute(int64_t x, int64_t n, int half_bits, const FeistelKeys& fk) {
+  const unsigned long long mask = (1ull << half_bits) - 1ull;
+  unsigned long long v = (unsigned long long)x;
+  do {
+    unsigned long long l = v >> half_bits, r = v & mask;
+#pragma unroll
+    for (int i = 0; i < GPFY_SHUFFLE_ROUNDS; ++i) {
+      const unsigned long long t = l ^ ((unsigned long long)feistel_round((unsigned int)r, fk.k[i]) & mask);
+      l = r;
+      r = t;
+    }
+    v = (l << half_bits) | r;
+  } while (v >= (unsigned long long)n);
+  return (int64_t)v;
+}
+
+static int feistel_half_bits(int64_t n) {
+  int bits = 2;
+  while (bits < 62 && (1ll << bits) < n) ++bits;
+  return (bits + 1) / 2;
+}
+
+static FeistelKeys feistel_keys(uint64_t seed, uint64_t epoch) {
+  FeistelKeys fk;
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + epoch * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+  for (int i = 0; i < GPFY_SHUFFLE_ROUNDS; ++i) {   // splitmix64 stream
+    z += 0x9E3779B97F4A7C15ull;
+    uint64_t y = z;
+    y = (y ^ (y >> 30)) * 0xBF58476D1CE4E5B9ull;
+    y = (y ^ (y >> 27)) * 0x94D049BB133111EBull;
+    y ^= y >> 31;
+    fk.k[i] = (unsigned int)(y >> 32);
+  }
+  return fk;
+}
+
+// one thread per output element: consecutive threads read consecutive doubles of one source row
+__global__ void minibatch_gather_kernel(FeistelKeys fk, int64_t n_rows, int half_bits, int64_t start, int64_t batch,
+                                        const double* __restrict__ X, int dx, const double* __restrict__ Y, int dy,
+                                        double* __restrict__ Xb, double* __restrict__ Yb, int64_t* __restrict__ idx_out) {
+  const int row_len = dx + dy;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch * row_len) return;
+  const int64_t j = e / row_len;
+  const int c = (int)(e - j * row_len);
+  const int64_t src = feistel_permute(start + j, n_rows, half_bits, fk);
+  if (c < dx) Xb[j * dx + c] = X[src * dx + c];
+  else Yb[j * dy + (c - dx)] = Y[src * dy + (c - dx)];
+  if (c == 0 && idx_out) idx_out[j] = src;
+}
+
 }  // namespace gpfy
 
 using namespace gpfy;
@@ -152,6 +220,25 @@ int gpfy_step_adam(void* stream, int64_t n, double* theta, const double* grad, d
   if (n <= 0) return GPFY_OK;
   const double bc1 = 1.0 - pow(b1, (double)step_count), bc2 = 1.0 - pow(b2, (double)step_count);
   STEP_K(step_adam_kernel, (unsigned)((n + 255) / 256), 256, (cudaStream_t)stream, n, theta, grad, m1, m2, mask, lr, b1, b2, eps, bc1, bc2);
+  return GPFY_OK;
+}
+
+int gpfy_shuffle_index(uint64_t seed, uint64_t epoch, int64_t n_rows, int64_t position, int64_t* out) {
+  if (!out || n_rows <= 0 || position < 0 || position >= n_rows) { set_error("shuffle index: position outside [0, n_rows)"); return GPFY_EINVAL; }
+  *out = feistel_permute(position, n_rows, feistel_half_bits(n_rows), feistel_keys(seed, epoch));
+  return GPFY_OK;
+}
+
+int gpfy_minibatch_gather(void* stream, uint64_t seed, uint64_t epoch, int64_t n_rows, int64_t start, int64_t batch, const double* X,
+                          int dx, const double* Y, int dy, double* Xb, double* Yb, int64_t* idx_out) {
+  if (n_rows <= 0 || batch < 0 || start < 0 || start + batch > n_rows || dx <= 0 || dy < 0) {
+    set_error("minibatch gather: rows [%lld, %lld) outside the epoch of %lld rows", (long long)start, (long long)(start + batch), (long long)n_rows);
+    return GPFY_EINVAL;
+  }
+  if (batch == 0) return GPFY_OK;
+  const int64_t total = batch * (dx + dy);
+  STEP_K(minibatch_gather_kernel, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, feistel_keys(seed, epoch), n_rows,
+         feistel_half_bits(n_rows), start, batch, X, dx, Y, dy, Xb, Yb, idx_out);
   return GPFY_OK;
 }
 

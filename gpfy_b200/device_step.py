@@ -152,6 +152,23 @@ class DeviceTrainer:
         self.loss_trace.append(loss)
         return loss
 
+    def fit_minibatch(self, X, Y, batch_size, num_steps, seed=0):
+        """`num_steps` Adam steps on shuffled minibatches of (X, Y) with the `dataset_size = N` rescale
+        (optimization.py:84-104, 154): gather and step are both stream-ordered, nothing returns to the host.  Under
+        data parallelism every rank samples `batch_size` rows of its own shard."""
+        from .minibatch import DeviceMinibatches
+        batches = DeviceMinibatches(X, Y, batch_size, seed=seed, device=self.hp.device)
+        world = self.allreduce.world if self.allreduce is not None else 1
+        saved = self.dataset_size, self.n_total
+        self.dataset_size, self.n_total = batches.n * world, batch_size * world
+        try:
+            for _ in range(int(num_steps)):
+                Xb, Yb = batches.next()
+                self.step(Xb, Yb)
+        finally:
+            self.dataset_size, self.n_total = saved
+        return self
+
     def losses(self):
         return torch.cat(self.loss_trace).cpu().numpy() if self.loss_trace else np.zeros(0)
 

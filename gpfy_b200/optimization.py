@@ -132,29 +132,24 @@ def loss_and_grad_unconstrained(free_param: Param, m, q, lik, train_data, datase
 def create_training_step(model, dataset, dataset_xy_keys, q, lik, batch_size=None, allreduce=None, n_total=None, seed=0):
     """optimization.py:60-122.  `dataset` is any mapping of column name -> array (the reference takes a
     HuggingFace Dataset; `datasets` is a host-side container either way).  Full batch: the rows are captured
-    once; minibatch: a fresh shuffled batch every step with the `dataset_size = N` rescale (the reference
-    freezes its first batch at trace time — a quirk that is not replicated)."""
+    once; minibatch: a fresh shuffled batch every step, gathered on the device by `gpfy_minibatch_gather`
+    (gpfy_b200.minibatch), with the `dataset_size = N` rescale (the reference freezes its first batch at trace
+    time — a quirk that is not replicated)."""
     x_key, y_key = dataset_xy_keys
     X_all, Y_all = dataset[x_key], dataset[y_key]
     N = int(np.shape(X_all)[0])
     if batch_size:
-        rng = np.random.default_rng(seed)
-        order = {"perm": rng.permutation(N), "pos": 0}
-
-        def next_batch():
-            if order["pos"] + batch_size > N:  # drop_last_batch=True, reshuffle (optimization.py:48-57)
-                order["perm"], order["pos"] = rng.permutation(N), 0
-            idx = np.sort(order["perm"][order["pos"]:order["pos"] + batch_size])
-            order["pos"] += batch_size
-            if torch.is_tensor(X_all):
-                ti = torch.as_tensor(idx, device=X_all.device)
-                return X_all[ti], Y_all[ti]
-            return X_all[idx], Y_all[idx]
+        from .minibatch import DeviceMinibatches
+        batches = DeviceMinibatches(X_all, Y_all, batch_size, seed=seed)
+        next_batch = batches.next
 
         def train_step(state, _=None):
             X, Y = next_batch()
-            loss, grads = loss_and_grad_unconstrained(state.apply_fn(state.params), model, q, lik, (X, Y), dataset_size=N,
-                                                      allreduce=allreduce, n_total=None if n_total is None else batch_size * allreduce.world)
+            # optimization.py:154: scale = dataset_size / batch; under data parallelism every rank draws `batch_size`
+            # rows of its own shard, so the batch is batch_size * world rows of the n_total-row data set
+            loss, grads = loss_and_grad_unconstrained(state.apply_fn(state.params), model, q, lik, (X, Y),
+                                                      dataset_size=N if n_total is None else int(n_total), allreduce=allreduce,
+                                                      n_total=None if n_total is None else batch_size * allreduce.world)
             return state.apply_gradients(grads=grads), loss
         return train_step
 

@@ -211,6 +211,19 @@ GPFY_API int gpfy_step_grad(void* stream, const GpfyDesc* desc, const GpfyStepLa
 GPFY_API int gpfy_step_adam(void* stream, int64_t n, double* theta, const double* grad, double* m1, double* m2,
                    const unsigned char* mask, double lr, double b1, double b2, double eps, int64_t step_count);
 
+/* ---- shuffled minibatches (replaces batched_data_generator, optimization.py:31-58) ----
+ * An epoch visits the rows in the order pi(0), pi(1), ..., pi(n_rows - 1), pi a bijection of [0, n_rows) keyed by
+ * (seed, epoch) - a cycle-walked Feistel network, so there is no permutation array and no sort.  A batch is `batch`
+ * consecutive epoch positions from `start` (the caller drops the last partial batch and bumps `epoch`, like
+ * `dataset.shuffle().iter(batch_size, drop_last_batch=True)`). */
+#define GPFY_SHUFFLE_ROUNDS 6
+/* Xb[j, :] = X[pi(start + j), :], Yb likewise; X [n_rows, dx], Y [n_rows, dy] (dy may be 0) are device pointers or
+ * pinned host pointers (read through unified addressing when the data set exceeds HBM); idx_out [batch] may be NULL. */
+GPFY_API int gpfy_minibatch_gather(void* stream, uint64_t seed, uint64_t epoch, int64_t n_rows, int64_t start, int64_t batch,
+                          const double* X, int dx, const double* Y, int dy, double* Xb, double* Yb, int64_t* idx_out);
+/* pi(position) on the host (same function the kernel evaluates; for tests and host-side bookkeeping). */
+GPFY_API int gpfy_shuffle_index(uint64_t seed, uint64_t epoch, int64_t n_rows, int64_t position, int64_t* out /* host */);
+
 /* ---- kernel-matrix side (dense N x N2 outputs) ---- */
 #define GPFY_MAX_SHAPE_LEVELS 64
 enum { GPFY_SHAPE_ARCCOSINE = 0, GPFY_SHAPE_NTK = 1, GPFY_SHAPE_POLYDECAY = 2 };
