@@ -141,13 +141,13 @@ __host__ __device__ __forceinline__ int64_t feistel_permute(int64_t x, int64_t n
   return (int64_t)v;
 }
 
-static int feistel_half_bits(int64_t n) {
+__host__ __device__ static inline int feistel_half_bits(int64_t n) {
   int bits = 2;
   while (bits < 62 && (1ll << bits) < n) ++bits;
   return (bits + 1) / 2;
 }
 
-static FeistelKeys feistel_keys(uint64_t seed, uint64_t epoch) {
+__host__ __device__ static inline FeistelKeys feistel_keys(uint64_t seed, uint64_t epoch) {
   FeistelKeys fk;
   uint64_t z = seed * 0x9E3779B97F4A7C15ull + epoch * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
   for (int i = 0; i < GPFY_SHUFFLE_ROUNDS; ++i) {   // splitmix64 stream
@@ -174,6 +174,53 @@ __global__ void minibatch_gather_kernel(FeistelKeys fk, int64_t n_rows, int half
   if (c < dx) Xb[j * dx + c] = X[src * dx + c];
   else Yb[j * dy + (c - dx)] = Y[src * dy + (c - dx)];
   if (c == 0 && idx_out) idx_out[j] = src;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident step state, so that a whole training step has no per-step host argument and can be replayed from
+// a CUDA graph:  state[0] = steps taken, state[1] = epoch, state[2] = position inside the epoch.
+// ------------------------------------------------------------------------------------------------
+__global__ void step_adam_state_kernel(int64_t n, double* __restrict__ theta, const double* __restrict__ grad, double* __restrict__ m1,
+                                       double* __restrict__ m2, const unsigned char* __restrict__ mask, double lr, double b1, double b2,
+                                       double eps, const int64_t* __restrict__ state) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = (double)(state[0] + 1);
+  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  const double g = grad[i];
+  const double a = b1 * m1[i] + (1.0 - b1) * g;
+  const double v = b2 * m2[i] + (1.0 - b2) * g * g;
+  m1[i] = a;
+  m2[i] = v;
+  if (mask[i]) theta[i] += -lr * (a / bc1) / (sqrt(v / bc2) + eps);
+}
+
+__global__ void minibatch_gather_state_kernel(uint64_t seed, int64_t n_rows, int64_t batch, const int64_t* __restrict__ state,
+                                              const double* __restrict__ X, int dx, const double* __restrict__ Y, int dy,
+                                              double* __restrict__ Xb, double* __restrict__ Yb, int64_t* __restrict__ idx_out) {
+  const int row_len = dx + dy;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch * row_len) return;
+  const FeistelKeys fk = feistel_keys(seed, (uint64_t)state[1]);
+  const int64_t j = e / row_len;
+  const int c = (int)(e - j * row_len);
+  const int64_t src = feistel_permute(state[2] + j, n_rows, feistel_half_bits(n_rows), fk);
+  if (c < dx) Xb[j * dx + c] = X[src * dx + c];
+  else Yb[j * dy + (c - dx)] = Y[src * dy + (c - dx)];
+  if (c == 0 && idx_out) idx_out[j] = src;
+}
+
+// end of a step: log the loss, count the step, move to the next batch (drop the last partial batch, then reshuffle)
+__global__ void step_advance_kernel(int64_t* state, int64_t n_rows, int64_t batch, const double* __restrict__ loss,
+                                    double* __restrict__ loss_trace, int64_t trace_capacity) {
+  if (blockIdx.x || threadIdx.x) return;
+  if (loss_trace && trace_capacity > 0) loss_trace[state[0] % trace_capacity] = loss[0];
+  state[0] += 1;
+  if (batch > 0) {
+    int64_t pos = state[2] + batch;
+    if (pos + batch > n_rows) { state[1] += 1; pos = 0; }
+    state[2] = pos;
+  }
 }
 
 }  // namespace gpfy
@@ -239,6 +286,30 @@ int gpfy_minibatch_gather(void* stream, uint64_t seed, uint64_t epoch, int64_t n
   const int64_t total = batch * (dx + dy);
   STEP_K(minibatch_gather_kernel, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, feistel_keys(seed, epoch), n_rows,
          feistel_half_bits(n_rows), start, batch, X, dx, Y, dy, Xb, Yb, idx_out);
+  return GPFY_OK;
+}
+
+int gpfy_step_adam_state(void* stream, int64_t n, double* theta, const double* grad, double* m1, double* m2, const unsigned char* mask,
+                         double lr, double b1, double b2, double eps, const int64_t* state) {
+  if (n <= 0) return GPFY_OK;
+  STEP_K(step_adam_state_kernel, (unsigned)((n + 255) / 256), 256, (cudaStream_t)stream, n, theta, grad, m1, m2, mask, lr, b1, b2, eps, state);
+  return GPFY_OK;
+}
+
+int gpfy_minibatch_gather_state(void* stream, uint64_t seed, int64_t n_rows, int64_t batch, const int64_t* state, const double* X, int dx,
+                                const double* Y, int dy, double* Xb, double* Yb, int64_t* idx_out) {
+  if (n_rows <= 0 || batch < 0 || batch > n_rows || dx <= 0 || dy < 0 || !state) { set_error("minibatch gather: bad argument"); return GPFY_EINVAL; }
+  if (batch == 0) return GPFY_OK;
+  const int64_t total = batch * (dx + dy);
+  STEP_K(minibatch_gather_state_kernel, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, seed, n_rows, batch, state, X, dx, Y,
+         dy, Xb, Yb, idx_out);
+  return GPFY_OK;
+}
+
+int gpfy_step_advance(void* stream, int64_t* state, int64_t n_rows, int64_t batch, const double* loss, double* loss_trace,
+                      int64_t trace_capacity) {
+  if (!state || (batch > 0 && batch > n_rows)) { set_error("step advance: bad argument"); return GPFY_EINVAL; }
+  STEP_K(step_advance_kernel, 1, 32, (cudaStream_t)stream, state, n_rows, batch, loss, loss_trace, trace_capacity);
   return GPFY_OK;
 }
 

@@ -4,8 +4,8 @@ The reference's `train_step` (optimization.py:107-120) applies the bijectors, ev
 and lets optax update the unconstrained parameters - all inside one jitted XLA program.  `DeviceTrainer` is the
 equivalent around the CUDA hot path: the unconstrained parameters live in ONE flat device vector, and a step is a
 fixed sequence of stream-ordered C-ABI calls (constrain -> inducing basis -> ELBO + gradient -> all-reduce -> KL ->
-basis VJP -> gradient assembly -> Adam) without a single host synchronisation, so it can be replayed from a CUDA
-graph.  Supports the TriL variational distribution with Gaussian or Bernoulli likelihood and every kernel of
+basis VJP -> gradient assembly -> Adam) without a single host synchronisation; `fit(..., use_graph=True)` /
+`fit_minibatch(..., use_graph=True)` capture that sequence once in a CUDA graph and replay it.  Supports the TriL variational distribution with Gaussian or Bernoulli likelihood and every kernel of
 gpfy_b200.spherical; m_l <= 64 in learned-basis mode.
 """
 import ctypes
@@ -119,6 +119,17 @@ class DeviceTrainer:
     def step(self, X, Y):
         """One Adam step on this rank's rows (device tensors); every call only enqueues work.  The loss (-ELBO) of the
         step stays on the device in `loss_trace`."""
+        loss = torch.empty(1, dtype=torch.float64, device=self.hp.device)
+        self._enqueue_gradient(X, Y, loss)
+        hp, L, lib = self.hp, self.L, self.hp.lib
+        self.count += 1
+        _lib.check(lib.gpfy_step_adam(_stream(hp.device), L.th_total, _ptr(self.theta), _ptr(self.grad), _ptr(self.m1), _ptr(self.m2),
+                                      _ptr(self.mask), self.lr, self.b1, self.b2, self.eps, self.count))
+        self.loss_trace.append(loss)
+        return loss
+
+    def _enqueue_gradient(self, X, Y, loss):
+        """constrain -> inducing basis -> ELBO + gradient -> all-reduce -> KL -> basis VJP -> gradient of -ELBO w.r.t. theta."""
         hp, L, lib = self.hp, self.L, self.hp.lib
         st, d = _stream(hp.device), ctypes.byref(hp.desc)
         _lib.check(lib.gpfy_step_constrain(st, d, ctypes.byref(L), _ptr(self.theta), _ptr(self.tri_map), _ptr(self.cf), _ptr(self.cons)))
@@ -127,8 +138,9 @@ class DeviceTrainer:
             vhat = self.vhat
         else:
             vhat = self.v_V
+        # the sigma2 slot of `cons` is passed for both likelihoods (ignored for Bernoulli): no per-step host scalar
         hp.elbo_valgrad_packed(X, Y, self.v_w, self.v_b, self.v_v, self.v_eig, vhat, self.lcat, self.v_mu, self.v_sig,
-                               self.v_s2 if self.has_s2 else None, out=self.packed)
+                               self.v_s2, out=self.packed)
         n_local = X.shape[0]
         if self.allreduce is not None and self.allreduce.world > 1:
             self.allreduce(self.packed)
@@ -143,28 +155,83 @@ class DeviceTrainer:
             dV = self.dV
         else:
             dV = self.packed[E.d_vhat:E.d_vhat + hp.M * hp.dim]
-        loss = torch.empty(1, dtype=torch.float64, device=hp.device)
         _lib.check(lib.gpfy_step_grad(st, d, ctypes.byref(L), _ptr(self.cons), _ptr(self.packed), _ptr(self.kl), _ptr(dV),
                                       _ptr(self.tri_map), scale / n_total, _ptr(self.grad), _ptr(loss)))
-        self.count += 1
-        _lib.check(lib.gpfy_step_adam(st, L.th_total, _ptr(self.theta), _ptr(self.grad), _ptr(self.m1), _ptr(self.m2), _ptr(self.mask),
-                                      self.lr, self.b1, self.b2, self.eps, self.count))
-        self.loss_trace.append(loss)
-        return loss
 
-    def fit_minibatch(self, X, Y, batch_size, num_steps, seed=0):
+    # ------------------------------------------------------------------
+    # CUDA-graph replay: the step count, the epoch and the position inside it live in `state` on the device
+    # (gpfy_step_adam_state / gpfy_minibatch_gather_state / gpfy_step_advance), so a step has no per-step host argument.
+    def _enqueue_state_step(self, X, Y, batches, state, loss_cur, trace):
+        hp, L, lib = self.hp, self.L, self.hp.lib
+        if batches is not None:
+            X, Y = batches.next_from_state(state)
+        self._enqueue_gradient(X, Y, loss_cur)
+        st = _stream(hp.device)
+        _lib.check(lib.gpfy_step_adam_state(st, L.th_total, _ptr(self.theta), _ptr(self.grad), _ptr(self.m1), _ptr(self.m2),
+                                            _ptr(self.mask), self.lr, self.b1, self.b2, self.eps, _ptr(state)))
+        _lib.check(lib.gpfy_step_advance(st, _ptr(state), batches.n if batches is not None else 0,
+                                         batches.batch_size if batches is not None else 0, _ptr(loss_cur), _ptr(trace), trace.numel()))
+
+    def _run_graph(self, X, Y, batches, num_steps):
+        """`num_steps` steps: one eager step (sizes the scratch), then one captured step replayed num_steps - 1 times."""
+        if self.allreduce is not None and self.allreduce.world > 1:
+            raise _lib.GpfyError("use_graph is single-rank (the all-reduce is enqueued outside graph capture)")
+        dev = self.hp.device
+        num_steps = int(num_steps)
+        if num_steps <= 0:
+            return self
+        if batches is None:
+            X, Y = self.hp._dev(X), self.hp._dev(Y)
+        state = torch.tensor([self.count, batches.epoch if batches is not None else 0, batches.pos if batches is not None else 0],
+                             dtype=torch.int64, device=dev)
+        trace = torch.zeros(num_steps, dtype=torch.float64, device=dev)
+        loss_cur = torch.zeros(1, dtype=torch.float64, device=dev)
+        # trace slots are indexed by the absolute step count modulo the capacity; rotate back afterwards
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._enqueue_state_step(X, Y, batches, state, loss_cur, trace)
+            if num_steps > 1:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    self._enqueue_state_step(X, Y, batches, state, loss_cur, trace)
+                for _ in range(num_steps - 1):     # capture only records; every further step is a replay
+                    graph.replay()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        start = self.count % num_steps
+        self.loss_trace.append(torch.roll(trace, -start) if start else trace)
+        self.count += num_steps
+        if batches is not None:
+            st = state.cpu().numpy()
+            batches.epoch, batches.pos = int(st[1]), int(st[2])
+        return self
+
+    def fit(self, X, Y, num_steps, use_graph=True):
+        """`num_steps` full-batch Adam steps on device tensors (model.py:261-302 without the host in the loop)."""
+        if use_graph:
+            return self._run_graph(X, Y, None, num_steps)
+        for _ in range(int(num_steps)):
+            self.step(X, Y)
+        return self
+
+    def fit_minibatch(self, X, Y, batch_size, num_steps, seed=0, use_graph=False):
         """`num_steps` Adam steps on shuffled minibatches of (X, Y) with the `dataset_size = N` rescale
         (optimization.py:84-104, 154): gather and step are both stream-ordered, nothing returns to the host.  Under
-        data parallelism every rank samples `batch_size` rows of its own shard."""
+        data parallelism every rank samples `batch_size` rows of its own shard.  `use_graph`: capture one step (gather
+        included) in a CUDA graph and replay it - for small batches the step is launch-bound and this removes the
+        per-launch host cost."""
         from .minibatch import DeviceMinibatches
         batches = DeviceMinibatches(X, Y, batch_size, seed=seed, device=self.hp.device)
         world = self.allreduce.world if self.allreduce is not None else 1
         saved = self.dataset_size, self.n_total
         self.dataset_size, self.n_total = batches.n * world, batch_size * world
         try:
-            for _ in range(int(num_steps)):
-                Xb, Yb = batches.next()
-                self.step(Xb, Yb)
+            if use_graph:
+                self._run_graph(None, None, batches, num_steps)
+            else:
+                for _ in range(int(num_steps)):
+                    Xb, Yb = batches.next()
+                    self.step(Xb, Yb)
         finally:
             self.dataset_size, self.n_total = saved
         return self

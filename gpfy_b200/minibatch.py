@@ -64,3 +64,11 @@ class DeviceMinibatches:
         return self.Xb, self.Yb
 
     next = __next__
+
+    def next_from_state(self, state):
+        """The batch at (epoch, position) = state[1:3] on the device (gpfy_step_advance moves it on): no host-side
+        bookkeeping, so the call can sit inside a CUDA graph."""
+        _lib.check(self.lib.gpfy_minibatch_gather_state(_stream(self.device), self.seed, self.n, self.batch_size, _ptr(state),
+                                                        _ptr(self.X), self.dx, _ptr(self.Y), self.dy, _ptr(self.Xb), _ptr(self.Yb),
+                                                        _ptr(self.idx)))
+        return self.Xb, self.Yb

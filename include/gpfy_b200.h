@@ -224,6 +224,18 @@ GPFY_API int gpfy_minibatch_gather(void* stream, uint64_t seed, uint64_t epoch, 
 /* pi(position) on the host (same function the kernel evaluates; for tests and host-side bookkeeping). */
 GPFY_API int gpfy_shuffle_index(uint64_t seed, uint64_t epoch, int64_t n_rows, int64_t position, int64_t* out /* host */);
 
+/* ---- device-resident step state: no per-step host argument, so a training step replays from a CUDA graph ----
+ * state [3] int64 on the device: steps taken (Adam's bias-correction count, model.py:297-298 scan index), epoch, position
+ * inside the epoch.  `_state` variants read it; gpfy_step_advance ends a step: loss_trace[steps % trace_capacity] = loss[0]
+ * (the loss history `GP.fit` returns, model.py:298-300), steps += 1 and, for batch > 0, position += batch with the
+ * drop-last / reshuffle rule of optimization.py:48-57. */
+GPFY_API int gpfy_step_adam_state(void* stream, int64_t n, double* theta, const double* grad, double* m1, double* m2,
+                         const unsigned char* mask, double lr, double b1, double b2, double eps, const int64_t* state);
+GPFY_API int gpfy_minibatch_gather_state(void* stream, uint64_t seed, int64_t n_rows, int64_t batch, const int64_t* state,
+                                const double* X, int dx, const double* Y, int dy, double* Xb, double* Yb, int64_t* idx_out);
+GPFY_API int gpfy_step_advance(void* stream, int64_t* state, int64_t n_rows, int64_t batch, const double* loss, double* loss_trace,
+                      int64_t trace_capacity);
+
 /* ---- kernel-matrix side (dense N x N2 outputs) ---- */
 #define GPFY_MAX_SHAPE_LEVELS 64
 enum { GPFY_SHAPE_ARCCOSINE = 0, GPFY_SHAPE_NTK = 1, GPFY_SHAPE_POLYDECAY = 2 };

@@ -73,3 +73,30 @@ def test_device_minibatch_training_matches_host_loop(name):
     _, _, l_full = m.fit(param, full, adam(lr), 1, progress_bar=False)
     _, _, l_whole = m.fit(param, whole, adam(lr), 1, progress_bar=False)
     assert abs(l_full[0] - l_whole[0]) <= 1e-10 * abs(l_full[0])
+
+
+@pytest.mark.parametrize("name", ["d8_F6_T12", "s2_deg10_polydecay", "d32_F4_T16_bernoulli"])
+def test_cuda_graph_replay_matches_eager_steps(name):
+    """One captured step (gather, constrain, basis, ELBO + gradient, KL, chain rules, Adam, advance) replayed from a
+    CUDA graph == the eager sequence of C-ABI calls: the step count, epoch and position live on the device."""
+    from gpfy_b200.device_step import DeviceTrainer
+    from gpfy_b200.param import tree_leaves
+    g = load(name)
+    o = objects_from_golden(g)
+    q, lik, m, param = o["q"], o["lik"], o["m"], o["param"]
+    X, Y = g["X"], g["Y"]
+    K, lr, batch = 11, 3e-2, 16
+    eager = DeviceTrainer(param, m, q, lik, learning_rate=lr).fit_minibatch(X, Y, batch, K, seed=3)
+    graph = DeviceTrainer(param, m, q, lik, learning_rate=lr).fit_minibatch(X, Y, batch, K, seed=3, use_graph=True)
+    assert graph.count == K and len(graph.losses()) == K
+    assert rel_err(graph.losses(), eager.losses()) < 1e-12
+    for a, b in zip(tree_leaves(graph.param().params), tree_leaves(eager.param().params)):
+        assert rel_err(a, b) < 1e-11
+    # full batch, and continuing an existing run (the count carries over into Adam's bias correction)
+    Xd, Yd = torch.as_tensor(X, device="cuda"), torch.as_tensor(Y, device="cuda")
+    e2 = DeviceTrainer(param, m, q, lik, learning_rate=lr).fit(Xd, Yd, 7, use_graph=False)
+    g2 = DeviceTrainer(param, m, q, lik, learning_rate=lr).fit(Xd, Yd, 3, use_graph=True).fit(Xd, Yd, 4, use_graph=True)
+    assert g2.count == 7 and rel_err(g2.losses(), e2.losses()) < 1e-12
+    # one and two steps (no replay at all / capture without replay)
+    g1 = DeviceTrainer(param, m, q, lik, learning_rate=lr).fit(Xd, Yd, 1, use_graph=True).fit(Xd, Yd, 2, use_graph=True)
+    assert rel_err(g1.losses(), e2.losses()[:3]) < 1e-12
