@@ -23,10 +23,15 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
   const int m_tiles = (a.m + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (a.n + GEMM_BN - 1) / GEMM_BN;
   const int tiles = m_tiles * n_tiles;
-  const int kt = a.k / GEMM_BK;
+  const int kt_full = a.k / GEMM_BK;
   if ((int)blockIdx.x >= tiles) return;
-  const int n_my = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total = n_my * kt;
+  // lower_k: A is lower triangular in 96-row blocks, so row tile t only needs k < 96 (t + 1)
+  auto kt_of = [&](int tile) {
+    const int lim = ((tile % m_tiles) + 1) * (GEMM_BM / GEMM_BK);
+    return (a.lower_k && lim < kt_full) ? lim : kt_full;
+  };
+  int total = 0;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) total += kt_of(t);
 
   if (tid == 0) {
 #pragma unroll
@@ -43,7 +48,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
   const double* pA[2];
   const double* pB[4];
   bool okA[2], okB;
-  int p_tile = blockIdx.x, p_kb = 0, pit = 0;
+  int p_tile = blockIdx.x, p_kb = 0, pit = 0, p_kt = kt_of(blockIdx.x);
   auto producer_tile = [&]() {
     const int row0 = (p_tile % m_tiles) * GEMM_BM, col0 = (p_tile / m_tiles) * GEMM_BN;
 #pragma unroll
@@ -70,10 +75,13 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
       }
       cp_async_mbar_arrive(&bar_full[st]);
       ++pit;
-      if (++p_kb == kt) {
+      if (++p_kb == p_kt) {
         p_kb = 0;
         p_tile += gridDim.x;
-        if (pit < total) producer_tile();
+        if (pit < total) {
+          producer_tile();
+          p_kt = kt_of(p_tile);
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 2; ++i) if (okA[i]) pA[i] += GEMM_BK;
@@ -88,7 +96,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
   for (int s = 0; s < GEMM_STAGES - 1; ++s) produce();
 
   double acc[3][8][2];
-  int c_tile = blockIdx.x, c_kb = 0;
+  int c_tile = blockIdx.x, c_kb = 0, c_kt = kt_of(blockIdx.x);
   int row0 = (c_tile % m_tiles) * GEMM_BM, col0 = (c_tile / m_tiles) * GEMM_BN;
   bool active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;
   for (int it = 0; it < total; ++it) {
@@ -120,7 +128,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_empty[st]);
 
-    if (++c_kb == kt) {
+    if (++c_kb == c_kt) {
       double ps[8][2];
 #pragma unroll
       for (int c = 0; c < 8; ++c) ps[c][0] = ps[c][1] = 0.0;
@@ -170,6 +178,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
       }
       c_kb = 0;
       c_tile += gridDim.x;
+      c_kt = kt_of(c_tile);
       row0 = (c_tile % m_tiles) * GEMM_BM;
       col0 = (c_tile / m_tiles) * GEMM_BN;
       active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;

@@ -1115,6 +1115,10 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
   DegreeTable deg = degree_table(desc);
   RecCoef rc = make_rec_coef(desc->alpha);
   GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
+  // only the quadratic form z^T W2 z is needed: fold W2 onto its lower triangle (W_ij + W_ji below the diagonal, zero
+  // above) and let the GEMM skip the k range right of each row tile's diagonal block
+  for (int q = 0; q < s.P; ++q)
+    GPFY_K(fold_lower_kernel, dim3((Mp + 31) / 32, (Mp + 31) / 32), dim3(32, 8), 0, st, ws + p.o_W2 + q * Mp2, Mp);
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
@@ -1132,6 +1136,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
       g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = nullptr; g.ldc = p.nc;  // only psi = z . (W2 z) is needed (model.py:136): the product is never stored
+      g.lower_k = 1;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
@@ -1192,6 +1197,8 @@ int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* 
     } else {
       GPFY_K(pad_square_kernel, sqg, 256, 0, st, sigma + (int64_t)q * s.M * s.M, S, s.M, Mp, 0);
     }
+    // diag(A^T S A) only: fold S onto its lower triangle, the GEMM then skips a third of its k-steps (see gpfy_predict_diag)
+    GPFY_K(fold_lower_kernel, dim3((Mp + 31) / 32, (Mp + 31) / 32), dim3(32, 8), 0, st, S, Mp);
   }
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
@@ -1204,6 +1211,7 @@ int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* 
       g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = nullptr; g.ldc = p.nc;  // only psi = z . (W2 z) is needed (model.py:136): the product is never stored
+      g.lower_k = 1;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));

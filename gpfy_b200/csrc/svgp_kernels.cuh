@@ -529,6 +529,18 @@ __global__ void __launch_bounds__(256, 2) zonal_bwd_kernel(ZonalBwdArgs a) {
 }
 
 // predict_diag epilogue: fmu = r mz, fvar = v r^(2 order) + r^2 psi  [n, P]  (model.py:220-225)
+// W <- lower(W + W^T) with the diagonal kept: z^T W z is unchanged for every z, the upper triangle becomes zero
+__global__ void fold_lower_kernel(double* W, int n) {
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  for (int i = blockIdx.y * 32 + threadIdx.y; i < n && i < (blockIdx.y + 1) * 32; i += 8) {
+    if (j < i && j < n) {
+      const double lo = W[(int64_t)i * n + j], up = W[(int64_t)j * n + i];
+      W[(int64_t)i * n + j] = lo + up;
+      W[(int64_t)j * n + i] = 0.0;
+    }
+  }
+}
+
 struct PredictArgs {
   const double* psi_part;  // [P][npsi][ldz]
   int npsi;
