@@ -387,7 +387,9 @@ struct ZonalBwdArgs {
 //   dz = sum_p (r p) mu2_p + (2 q r^2) C_p ;  dt = dz * 2 alpha C_{l-1}^{alpha+1}(t)   (gegenbauer.py:73-81)
 //   dT overwrites C_0;  dxhat += Vhat^T dt;  du = (dxhat - xhat (xhat . dxhat)) / r + dr xhat  (VJP of spherical.py:248-249)
 template <int DIMP, int PMAX>
-__global__ void __launch_bounds__(256, 2) zonal_bwd_kernel(ZonalBwdArgs a) {
+// xh + dxh alone are 2 DIMP doubles per thread: beyond DIMP = 16 the kernel runs one CTA per SM (up to 255 registers);
+// under the 128-register cap of two CTAs it spilled 3-5 KB per thread (d = 32: 17.7 ms of a 30.8 ms step).
+__global__ void __launch_bounds__(256, (DIMP > 16 ? 1 : 2)) zonal_bwd_kernel(ZonalBwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint64_t bar;
   double* vs = smem;                      // [Mp][DIMP]
