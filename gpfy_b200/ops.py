@@ -96,16 +96,21 @@ class HotPath:
         return _as_dev(x, self.device)
 
     # ------------------------------------------------------------------
-    def features(self, X, vhat, lcat, w=None, b=None, degree_scale=None, mul_r=False, apply_to_sphere=True):
-        """[M, N] feature matrix and radii (spherical_harmonics.py:290-320,344-362,385-387)."""
+    def features(self, X, vhat, lcat, w=None, b=None, degree_scale=None, mul_r=False, apply_to_sphere=True, out=None):
+        """[M, N] feature matrix and radii (spherical_harmonics.py:290-320,344-362,385-387); `out` = (Phi, r) buffers to reuse."""
         X = self._dev(X)
         n = X.shape[0]
         vhat, lcat = self._dev(vhat), self._dev(lcat)
         w = self._dev(w) if w is not None else None
         b = self._dev(b) if b is not None else None
         ds = self._dev(degree_scale) if degree_scale is not None else None
-        out = torch.empty((self.M, n), dtype=torch.float64, device=self.device)
-        r = torch.empty((n,), dtype=torch.float64, device=self.device)
+        if out is not None:
+            out, r = out
+            if tuple(out.shape) != (self.M, n) or tuple(r.shape) != (n,) or not (out.is_contiguous() and r.is_contiguous()):
+                raise _lib.GpfyError("features: `out` must be contiguous float64 buffers of shape [M, N] and [N]")
+        else:
+            out = torch.empty((self.M, n), dtype=torch.float64, device=self.device)
+            r = torch.empty((n,), dtype=torch.float64, device=self.device)
         ws = self.workspace(n, _lib.OP_FEATURES)
         _lib.check(self.lib.gpfy_sh_features_fwd(
             _stream(self.device), ctypes.byref(self.desc), n, _ptr(X), int(bool(apply_to_sphere)), _ptr(w), _ptr(b),
