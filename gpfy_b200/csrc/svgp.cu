@@ -511,7 +511,11 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
     ZonalFwd2Args fa;
     fa.z = a;
     fa.mt = make_monic(0.5 * a.rc.two_alpha);
+#ifdef GPFY_ZB_CLOCKS   // knock-out bits for time attribution: instrumented builds only (tools/zb_clocks.py)
     { const char* e = getenv("GPFY_ZF_DBG"); fa.dbg = e ? atoi(e) : 0; }
+#else
+    fa.dbg = 0;
+#endif
     const int pmax = a.P == 1 ? 1 : (a.P == 2 ? 2 : 4);
     const int smem = zf2_smem_bytes(a.Mp, DIMP, a.P, a.mz != nullptr, pmax);
     const unsigned pgrid = std::min(grid, (unsigned)(2 * device_sms()));  // persistent: two CTAs per SM
@@ -953,7 +957,11 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       zb.order = desc->kernel_order; zb.vhat_p = ws + p.o_vhat_p; zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.npts = npts;
       zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.dVpart = ws + p.o_dVpart;
       zb.deg = deg; zb.red_sep = fused_red_sep(s);
+#ifdef GPFY_ZB_CLOCKS
       { const char* e = getenv("GPFY_ZB_DBG"); zb.dbg = e ? atoi(e) : 0; }
+#else
+      zb.dbg = 0;
+#endif
       zb3_setup(&zb, desc->alpha, deg, s.M, Mp);
       GPFY_TIMED(TK_ZONAL_BWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd3<DIMP>(st, zb, fuse_lik, p.sms)));

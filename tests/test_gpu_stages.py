@@ -217,3 +217,29 @@ def test_inducing_basis_on_device_matches_reference_and_autograd(name):
     grads = torch.autograd.grad(s, Vt)
     dV = hp.inducing_basis_vjp(np.concatenate(V, 0), lcat, np.concatenate(dvh, 0), np.concatenate([d.ravel() for d in dL]), normalise=True)
     assert rel_err(dV.cpu().numpy(), np.concatenate([x.numpy() for x in grads], 0)) < 1e-9
+
+
+def test_fused_and_general_kernel_paths_agree_on_the_headline_shape(monkeypatch):
+    """Two independent implementations of the same step: the tensor-core zonal forward + fused backward (P = 1,
+    ambient dim <= 16, Mp <= 288) against the general one-point-per-lane kernels that serve every other shape,
+    selected by the library's A/B switches.  Same inputs -> same packed value and gradients, features and predictions."""
+    prob = _problem(20_011)
+    hp, args = prob["hot"], prob["args"]
+    pred_args = [args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)]
+    ds = torch.sqrt(args[5] * args[4])
+    fused = hp.elbo_valgrad_packed(*args).clone()
+    fmu, fvar = (t.clone() for t in hp.predict_diag(*pred_args))
+    A = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0].clone()
+    for k in ("GPFY_NO_FUSED_BWD", "GPFY_OLD_FWD", "GPFY_OLD_FEATURES"):
+        monkeypatch.setenv(k, "1")
+    general = hp.elbo_valgrad_packed(*args)
+    gmu, gvar = hp.predict_diag(*pred_args)
+    gA = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0]
+    lay = hp.layout
+    for name in ("data_term", "d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2"):
+        lo = getattr(lay, name)
+        nxt = min([getattr(lay, n) for n in ("d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2", "total")
+                   if getattr(lay, n) > lo])
+        assert rel_err(fused[lo:nxt].cpu().numpy(), general[lo:nxt].cpu().numpy()) < 1e-11, name
+    assert rel_err(fmu.cpu().numpy(), gmu.cpu().numpy()) < 1e-12 and rel_err(fvar.cpu().numpy(), gvar.cpu().numpy()) < 1e-12
+    assert rel_err(A.cpu().numpy(), gA.cpu().numpy()) < 1e-12
