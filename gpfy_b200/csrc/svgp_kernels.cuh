@@ -530,7 +530,6 @@ __global__ void __launch_bounds__(256, (DIMP > 16 ? 1 : 2)) zonal_bwd_kernel(Zon
   }
 }
 
-// predict_diag epilogue: fmu = r mz, fvar = v r^(2 order) + r^2 psi  [n, P]  (model.py:220-225)
 // W <- lower(W + W^T) with the diagonal kept: z^T W z is unchanged for every z, the upper triangle becomes zero
 __global__ void fold_lower_kernel(double* W, int n) {
   const int j = blockIdx.x * 32 + threadIdx.x;
@@ -543,6 +542,7 @@ __global__ void fold_lower_kernel(double* W, int n) {
   }
 }
 
+// predict_diag epilogue: fmu = r mz, fvar = v r^(2 order) + r^2 psi  [n, P]  (model.py:220-225)
 struct PredictArgs {
   const double* psi_part;  // [P][npsi][ldz]
   int npsi;

@@ -224,7 +224,9 @@ class DeviceTrainer:
         batches = DeviceMinibatches(X, Y, batch_size, seed=seed, device=self.hp.device)
         world = self.allreduce.world if self.allreduce is not None else 1
         saved = self.dataset_size, self.n_total
-        self.dataset_size, self.n_total = batches.n * world, batch_size * world
+        # the global row count (the constructor's n_total under data parallelism; shards may differ by one row)
+        n_global = int(self.n_total) if self.n_total is not None else batches.n * world
+        self.dataset_size, self.n_total = n_global, batch_size * world
         try:
             if use_graph:
                 self._run_graph(None, None, batches, num_steps)

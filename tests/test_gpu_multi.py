@@ -82,7 +82,24 @@ def _train_worker(rank, world, port, ret):
         err = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
                   for a, b in zip(tree_leaves(sharded.param().params), tree_leaves(single.param().params)))
         lerr = float(np.max(np.abs(sharded.losses() - single.losses()) / np.abs(single.losses())))
-        ret[rank] = max(err, lerr)
+        # minibatches: every rank draws `batch` rows of its own shard; one rank stepping on the concatenation of both
+        # ranks' batches with dataset_size = N must follow the same trajectory (optimization.py:154 rescale)
+        from gpfy_b200.minibatch import DeviceMinibatches
+        batch, steps = 512, 4
+        mb_sharded = DeviceTrainer(param, m, q, lik, learning_rate=2e-2, allreduce=gd.PackedAllReduce(), n_total=N)
+        mb_sharded.fit_minibatch(Xs, Ys, batch, steps, seed=11)
+        mb_single = DeviceTrainer(param, m, q, lik, learning_rate=2e-2, dataset_size=N)
+        gens = []
+        for r in range(world):
+            l2, h2 = gd.shard_bounds(N, r, world)
+            gens.append(DeviceMinibatches(X[l2:h2].contiguous(), Y[l2:h2].contiguous(), batch, seed=11))
+        for _ in range(steps):
+            parts = [gen.next() for gen in gens]
+            mb_single.step(torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]))
+        merr = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+                   for a, b in zip(tree_leaves(mb_sharded.param().params), tree_leaves(mb_single.param().params)))
+        mlerr = float(np.max(np.abs(mb_sharded.losses() - mb_single.losses()) / np.abs(mb_single.losses())))
+        ret[rank] = max(err, lerr, merr, mlerr)
     finally:
         dist.destroy_process_group()
 
