@@ -9,7 +9,7 @@ a_n = r_n E z_n, where z_n = C_l^alpha(Vhat x_n) are the *un-whitened* zonal val
 
 so the N-dependent work is one symmetric GEMM  C = W2 Z, one weighted SYRK  Gz = Z diag(q r^2) Z^T,
 thin reductions, and the zonal forward/backward; every L_l^{-1} moves into O(M^3) per-step matrix
-algebra.  Run:  python tools/folded_prototype.py   (compares with oracle autograd).
+algebra.  Run:  python tests/folded_prototype.py   (compares with oracle autograd).
 """
 import math
 import os

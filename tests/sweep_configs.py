@@ -1,5 +1,7 @@
 """Other BASELINE.json shapes at scale (device-resident, 1 GPU): T sweep, degree 12, d = 32 Bernoulli.
-Prints one JSON object; each case is also checked against the oracle on a 2001-row sample."""
+Prints one JSON object per case; each case is also checked against the oracle on a 2001-row sample, which is why this
+script lives under tests/ (only tests/, smoke() and bench.py's CPU baseline may use oracle/).
+Run on a GPU box:  python tests/sweep_configs.py   ->  gpurun_out/sweep.json"""
 import json, sys
 import numpy as np, torch
 sys.path.insert(0, ".")

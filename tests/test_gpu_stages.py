@@ -54,9 +54,9 @@ def test_project_q_matches_reference_golden(name):
     assert rel_err(var.cpu().numpy(), g["o_project_diag_variance"]) < TOL
 
 
-def _problem(N, T=30, P=1, lik="gaussian"):
+def _problem(N, T=30, P=1, lik="gaussian", d=8, F=11):
     from gpfy_b200.synthetic import headline_problem
-    return headline_problem(N, T=T, P=P, likelihood=lik, device="cuda")
+    return headline_problem(N, d=d, F=F, T=T, P=P, likelihood=lik, device="cuda")
 
 
 @pytest.mark.parametrize("N", [1, 31, 1000, 150_001])
@@ -130,12 +130,16 @@ def test_full_size_invariant_at_init_and_determinism():
     assert rel_err(u["sigma"].cpu().numpy(), og["Lq"]) < TOL
 
 
-@pytest.mark.parametrize("T,P,lik", [(30, 1, "gaussian"), (64, 1, "gaussian"), (30, 2, "bernoulli"), (12, 5, "gaussian")])
-def test_headline_shapes_match_oracle_on_a_sample(T, P, lik):
-    """BASELINE configs 2/3 (d = 8, degrees 0..10, T = 30 / 64) and a Bernoulli P = 2 variant: 3001 rows
-    (ragged: not a multiple of any tile) against the oracle, every gradient."""
+@pytest.mark.parametrize("T,P,lik,d,F", [(30, 1, "gaussian", 8, 11), (64, 1, "gaussian", 8, 11), (30, 2, "bernoulli", 8, 11),
+                                         (12, 5, "gaussian", 8, 11),
+                                         (30, 1, "gaussian", 8, 13),            # BASELINE config 4: degrees 0..12 (M = 340)
+                                         (64, 1, "bernoulli", 32, 5),           # config 5: d = 32, degrees 0..4, Bernoulli (M = 226)
+                                         (2**31 - 1, 1, "gaussian", 2, 11)])    # config 1: S^2, degrees 0..10, no truncation (M = 121)
+def test_headline_shapes_match_oracle_on_a_sample(T, P, lik, d, F):
+    """The shapes of BASELINE configs 1-5 (d = 8 degrees 0..10 with T = 30 / 64, degrees 0..12, d = 32 Bernoulli, S^2) and
+    P = 2 / P = 5 variants: 3001 rows (ragged: not a multiple of any tile) against the oracle, every gradient."""
     N = 3001
-    prob = _problem(N, T=T, P=P, lik=lik)
+    prob = _problem(N, T=T, P=P, lik=lik, d=d, F=F)
     hp, args, host = prob["hot"], prob["args"], prob["host"]
     out = hp.unpack(hp.elbo_valgrad_packed(*args))
     pack = {"dim": host["dim"], "alpha": host["alpha"], "V": host["V"], "L": host["L"], "w": host["w"], "b": host["b"],
