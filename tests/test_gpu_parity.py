@@ -57,6 +57,14 @@ def test_features_match_reference_golden(name):
     # projection A = sqrt(1/Kuu) * Kuf (spherical_harmonics.py:385-387)
     A, _ = hp.features(g["X"], vhat, lcat, w=pack["w"], b=pack["b"], degree_scale=np.sqrt(pack["eig"] * pack["v"]), mul_r=True)
     assert rel_err(A.cpu().numpy(), g["o_proj"]) < TOL
+    # caller-provided output buffers are filled in place; wrong shapes are refused
+    import torch
+    from gpfy_b200 import _lib
+    bufs = (torch.full_like(A, float("nan")), torch.full((A.shape[1],), float("nan"), dtype=torch.float64, device=A.device))
+    A2, r2 = hp.features(g["X"], vhat, lcat, w=pack["w"], b=pack["b"], degree_scale=np.sqrt(pack["eig"] * pack["v"]), mul_r=True, out=bufs)
+    assert A2.data_ptr() == bufs[0].data_ptr() and torch.equal(A2, A) and rel_err(r2.cpu().numpy(), g["o_r"]) < TOL
+    with pytest.raises(_lib.GpfyError):
+        hp.features(g["X"], vhat, lcat, w=pack["w"], b=pack["b"], out=(bufs[0][:, :-1], bufs[1]))
 
 
 @pytest.mark.parametrize("name", ARD_CASES)
