@@ -328,33 +328,38 @@ __global__ void __launch_bounds__(256) partial_sums_kernel(const double* partial
   if (threadIdx.x == 0) out[k] = red[0];
 }
 
-// the scalar chain rules on the summed partials (a.partials = [npart] sums)
+// the scalar chain rules on the summed partials (a.partials = [npart] sums); one warp, lanes stride the rows of a
+// degree and combine with the fixed shuffle tree (deterministic)
 __global__ void finalize_kernel(FinalArgs a) {
   const double* sums = a.partials;
-  if (threadIdx.x == 0) {
+  const int lane = threadIdx.x;
+  if (lane == 0) {
     a.packed[a.lay.data_term] = sums[PART_E];
     a.packed[a.lay.d_sigma2] = sums[PART_DS2];
     a.packed[a.lay.d_b] = sums[PART_DB] / (2.0 * sqrt(a.b[0]));
-    if (a.proj > 0) {
-      for (int j = 0; j < a.nw; ++j) a.packed[a.lay.d_w + j] = sums[PART_DW + j];  // W has the identity bijector, no sqrt
-    } else if (a.scalar_w) {
-      double s = 0.0;
-      for (int j = 0; j < a.d; ++j) s += sums[PART_DW + j];
-      a.packed[a.lay.d_w] = s / (2.0 * a.w[0]);
-    } else {
-      for (int j = 0; j < a.d; ++j) a.packed[a.lay.d_w + j] = sums[PART_DW + j] / (2.0 * a.w[j]);
-    }
-    // eigenvalue / variance chain:  d_i = sqrt(eig_l v)
-    double dv = sums[PART_DV];
-    int i = 0;
-    for (int l = 0; l < a.deg.F; ++l) {
-      double s = 0.0;
-      for (int j = 0; j < a.deg.m[l]; ++j, ++i) s += a.dd[i] * a.dvec[i];
-      a.packed[a.lay.d_eig + l] = s / (2.0 * a.eig[l]);
-      dv += s / (2.0 * a.v[0]);
-    }
-    a.packed[a.lay.d_v] = dv;
   }
+  if (a.proj > 0) {
+    for (int j = lane; j < a.nw; j += 32) a.packed[a.lay.d_w + j] = sums[PART_DW + j];  // W has the identity bijector, no sqrt
+  } else if (a.scalar_w) {
+    double s = 0.0;
+    for (int j = lane; j < a.d; j += 32) s += sums[PART_DW + j];
+    s = warp_sum(s);
+    if (lane == 0) a.packed[a.lay.d_w] = s / (2.0 * a.w[0]);
+  } else {
+    for (int j = lane; j < a.d; j += 32) a.packed[a.lay.d_w + j] = sums[PART_DW + j] / (2.0 * a.w[j]);
+  }
+  // eigenvalue / variance chain:  d_i = sqrt(eig_l v)
+  double dv = sums[PART_DV];
+  int base = 0;
+  for (int l = 0; l < a.deg.F; ++l) {
+    double s = 0.0;
+    for (int j = lane; j < a.deg.m[l]; j += 32) s = fma(a.dd[base + j], a.dvec[base + j], s);
+    s = warp_sum(s);
+    if (lane == 0) a.packed[a.lay.d_eig + l] = s / (2.0 * a.eig[l]);
+    dv += s / (2.0 * a.v[0]);
+    base += a.deg.m[l];
+  }
+  if (lane == 0) a.packed[a.lay.d_v] = dv;
 }
 
 // KL(q || N(0, I)) for q = N(mu, L L^T) (variational.py:225-240, 262-286):
