@@ -128,11 +128,18 @@ class DeviceTrainer:
         self.loss_trace.append(loss)
         return loss
 
-    def _enqueue_gradient(self, X, Y, loss):
-        """constrain -> inducing basis -> ELBO + gradient -> all-reduce -> KL -> basis VJP -> gradient of -ELBO w.r.t. theta."""
+    def _enqueue_gradient(self, X, Y, loss, kl_stream=None):
+        """constrain -> inducing basis -> ELBO + gradient -> all-reduce -> KL -> basis VJP -> gradient of -ELBO w.r.t. theta.
+        `kl_stream`: run the two KL kernels on that stream, forked after `constrain` and joined before the gradient
+        assembly (inside a graph capture this becomes a parallel branch; eagerly it would only add host work)."""
         hp, L, lib = self.hp, self.L, self.hp.lib
         st, d = _stream(hp.device), ctypes.byref(hp.desc)
         _lib.check(lib.gpfy_step_constrain(st, d, ctypes.byref(L), _ptr(self.theta), _ptr(self.tri_map), _ptr(self.cf), _ptr(self.cons)))
+        if kl_stream is not None:
+            main = torch.cuda.current_stream(hp.device)
+            kl_stream.wait_stream(main)
+            with torch.cuda.stream(kl_stream):
+                _lib.check(lib.gpfy_prior_kl_valgrad(_stream(hp.device), d, _ptr(self.v_mu), _ptr(self.v_sig), _ptr(self.kl)))
         if self.learned:
             _lib.check(lib.gpfy_inducing_basis_fwd(st, d, _ptr(self.v_V), 1, _ptr(self.vhat), _ptr(self.lcat)))
             vhat = self.vhat
@@ -146,7 +153,8 @@ class DeviceTrainer:
             self.allreduce(self.packed)
         n_total = int(self.n_total) if self.n_total is not None else n_local
         scale = float(self.dataset_size) if self.dataset_size > 0 else float(n_total)
-        _lib.check(lib.gpfy_prior_kl_valgrad(st, d, _ptr(self.v_mu), _ptr(self.v_sig), _ptr(self.kl)))
+        if kl_stream is None:
+            _lib.check(lib.gpfy_prior_kl_valgrad(st, d, _ptr(self.v_mu), _ptr(self.v_sig), _ptr(self.kl)))
         E = hp.layout
         if self.learned:
             _lib.check(lib.gpfy_inducing_basis_vjp(st, d, _ptr(self.v_V), _ptr(self.lcat), 1,
@@ -155,17 +163,19 @@ class DeviceTrainer:
             dV = self.dV
         else:
             dV = self.packed[E.d_vhat:E.d_vhat + hp.M * hp.dim]
+        if kl_stream is not None:
+            torch.cuda.current_stream(hp.device).wait_stream(kl_stream)
         _lib.check(lib.gpfy_step_grad(st, d, ctypes.byref(L), _ptr(self.cons), _ptr(self.packed), _ptr(self.kl), _ptr(dV),
                                       _ptr(self.tri_map), scale / n_total, _ptr(self.grad), _ptr(loss)))
 
     # ------------------------------------------------------------------
     # CUDA-graph replay: the step count, the epoch and the position inside it live in `state` on the device
     # (gpfy_step_adam_state / gpfy_minibatch_gather_state / gpfy_step_advance), so a step has no per-step host argument.
-    def _enqueue_state_step(self, X, Y, batches, state, loss_cur, trace):
+    def _enqueue_state_step(self, X, Y, batches, state, loss_cur, trace, kl_stream=None):
         hp, L, lib = self.hp, self.L, self.hp.lib
         if batches is not None:
             X, Y = batches.next_from_state(state)
-        self._enqueue_gradient(X, Y, loss_cur)
+        self._enqueue_gradient(X, Y, loss_cur, kl_stream)
         st = _stream(hp.device)
         _lib.check(lib.gpfy_step_adam_state(st, L.th_total, _ptr(self.theta), _ptr(self.grad), _ptr(self.m1), _ptr(self.m2),
                                             _ptr(self.mask), self.lr, self.b1, self.b2, self.eps, _ptr(state)))
@@ -193,8 +203,9 @@ class DeviceTrainer:
             self._enqueue_state_step(X, Y, batches, state, loss_cur, trace)
             if num_steps > 1:
                 graph = torch.cuda.CUDAGraph()
+                kl_stream = torch.cuda.Stream(device=dev)
                 with torch.cuda.graph(graph, stream=side):
-                    self._enqueue_state_step(X, Y, batches, state, loss_cur, trace)
+                    self._enqueue_state_step(X, Y, batches, state, loss_cur, trace, kl_stream)
                 for _ in range(num_steps - 1):     # capture only records; every further step is a replay
                     graph.replay()
         torch.cuda.current_stream(dev).wait_stream(side)
