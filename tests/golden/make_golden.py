@@ -214,9 +214,13 @@ def build_gegenbauer():
 
 
 if __name__ == "__main__":
-    build_gegenbauer()
     tril = VariationalDistributionTriL()
     full = VariationalDistributionFullCovariance()
+    if "--orders" in sys.argv:   # only the kernel-order cases (adds to an existing set of goldens)
+        build_case("d3_arccos_order0", ArcCosine(depth=1, order=0), 4, 6, 3, 24, Gaussian(), tril, seed=9)
+        build_case("d3_arccos_order2_bern", ArcCosine(depth=1, order=2), 4, 6, 3, 24, Bernoulli(), tril, P=2, seed=10)
+        sys.exit(0)
+    build_gegenbauer()
     # config 1 of BASELINE.json: S^2 (input_dim 2 => dim 3), degrees 0..10, no truncation
     build_case("s2_deg10_polydecay", PolynomialDecay(truncation_level=11), 11, 2**31 - 1, 2, 48, Gaussian(), tril, seed=1)
     # same with the default truncation_level=10 so that degree 10 is clipped to lambda_9
@@ -233,3 +237,6 @@ if __name__ == "__main__":
     build_case("d4_fullcov_fixedV", PolynomialDecay(), 4, 2**31 - 1, 4, 40, Gaussian(), full, seed=7, full_cov=True)
     # linear projection weights [d, p]
     build_case("d6_proj3_arccos", ArcCosine(depth=2, order=1), 5, 8, 6, 40, Gaussian(), tril, projection_dim=3, seed=8)
+    # kernel order 0 and 2 (K_diag = v r^(2 order), spherical.py:400; kappa_0 / kappa_2, :299-309)
+    build_case("d3_arccos_order0", ArcCosine(depth=1, order=0), 4, 6, 3, 24, Gaussian(), tril, seed=9)
+    build_case("d3_arccos_order2_bern", ArcCosine(depth=1, order=2), 4, 6, 3, 24, Bernoulli(), tril, P=2, seed=10)
