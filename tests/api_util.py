@@ -11,12 +11,13 @@ from gpfy_b200.variational import VariationalDistributionFullCovariance, Variati
 def objects_from_golden(g):
     F, T, d, P = int(g["meta_F"]), int(g["meta_T"]), int(g["meta_input_dim"]), int(g["meta_P"])
     kname = str(g["meta_kernel"])
+    ard = bool(g["meta_ard"]) if "meta_ard" in g else True
     if kname == "PolynomialDecay":
-        kernel = PolynomialDecay(truncation_level=int(g["meta_truncation_level"]))
+        kernel = PolynomialDecay(truncation_level=int(g["meta_truncation_level"]), ard=ard)
     elif kname == "NTK":
-        kernel = NTK(depth=int(g["meta_depth"]))
+        kernel = NTK(depth=int(g["meta_depth"]), ard=ard)
     else:
-        kernel = ArcCosine(depth=int(g["meta_depth"]), order=int(g["meta_order"]))
+        kernel = ArcCosine(depth=int(g["meta_depth"]), order=int(g["meta_order"]), ard=ard)
     lik = Gaussian() if str(g["meta_lik"]) == "Gaussian" else Bernoulli()
     q = VariationalDistributionTriL() if str(g["meta_q"]).endswith("TriL") else VariationalDistributionFullCovariance()
     sh = SphericalHarmonics(F, phase_truncation=T)

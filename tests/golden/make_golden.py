@@ -53,6 +53,8 @@ def build_case(name, kernel, F, Tr, input_dim, N, lik, q, P=1, projection_dim=No
     kp = p[kernel.name]
     if projection_dim:
         kp["weight_variances"] = 0.5 * rng.standard_normal((input_dim, projection_dim))
+    elif not kernel.ard:
+        kp["weight_variances"] = np.array(0.8)     # one shared weight variance (spherical.py:110-114)
     else:
         kp["weight_variances"] = np.exp(0.3 * rng.standard_normal(input_dim))
     kp["bias_variance"] = np.array(0.7)
@@ -88,6 +90,7 @@ def build_case(name, kernel, F, Tr, input_dim, N, lik, q, P=1, projection_dim=No
     out["meta_order"] = np.array(kernel.order)
     out["meta_projection_dim"] = np.array(projection_dim or 0)
     out["meta_kernel"] = np.array(kernel.name)
+    out["meta_ard"] = np.array(bool(kernel.ard))
     out["meta_lik"] = np.array(lik.name)
     out["meta_q"] = np.array(q.name)
     out["meta_alpha"] = np.array(param.constants["sphere"]["alpha"])
@@ -219,6 +222,7 @@ if __name__ == "__main__":
     if "--orders" in sys.argv:   # only the kernel-order cases (adds to an existing set of goldens)
         build_case("d3_arccos_order0", ArcCosine(depth=1, order=0), 4, 6, 3, 24, Gaussian(), tril, seed=9)
         build_case("d3_arccos_order2_bern", ArcCosine(depth=1, order=2), 4, 6, 3, 24, Bernoulli(), tril, P=2, seed=10)
+        build_case("d4_ntk3_scalar_w", NTK(depth=3, ard=False), 4, 8, 4, 24, Gaussian(), tril, seed=11)
         sys.exit(0)
     build_gegenbauer()
     # config 1 of BASELINE.json: S^2 (input_dim 2 => dim 3), degrees 0..10, no truncation
@@ -240,3 +244,5 @@ if __name__ == "__main__":
     # kernel order 0 and 2 (K_diag = v r^(2 order), spherical.py:400; kappa_0 / kappa_2, :299-309)
     build_case("d3_arccos_order0", ArcCosine(depth=1, order=0), 4, 6, 3, 24, Gaussian(), tril, seed=9)
     build_case("d3_arccos_order2_bern", ArcCosine(depth=1, order=2), 4, 6, 3, 24, Bernoulli(), tril, P=2, seed=10)
+    # ard=False: a single weight variance shared by all input dimensions
+    build_case("d4_ntk3_scalar_w", NTK(depth=3, ard=False), 4, 8, 4, 24, Gaussian(), tril, seed=11)
