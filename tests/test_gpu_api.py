@@ -140,7 +140,8 @@ def test_unconstrained_loss_grad_and_fit_decreases_loss():
     assert np.all(np.isfinite(l2))
 
 
-@pytest.mark.parametrize("name", ["d8_F6_T12", "d5_ntk3_P2", "s2_deg10_clip", "d32_F4_T16_bernoulli"])
+@pytest.mark.parametrize("name", ["d8_F6_T12", "d5_ntk3_P2", "s2_deg10_clip", "d32_F4_T16_bernoulli", "d6_proj3_arccos",
+                                  "d4_ntk3_scalar_w", "d3_arccos_order0", "d3_arccos_order2_bern"])
 def test_device_trainer_matches_host_training_loop(name):
     """the on-device step driver (bijectors, eigenvalue chain, KL, Adam on one flat device vector,
     no host round trip) reproduces the host loop `GP.fit` + `create_training_step` + `adam` step for step."""
