@@ -161,19 +161,37 @@ __host__ __device__ static inline FeistelKeys feistel_keys(uint64_t seed, uint64
   return fk;
 }
 
-// one thread per output element: consecutive threads read consecutive doubles of one source row
-__global__ void minibatch_gather_kernel(FeistelKeys fk, int64_t n_rows, int half_bits, int64_t start, int64_t batch,
-                                        const double* __restrict__ X, int dx, const double* __restrict__ Y, int dy,
-                                        double* __restrict__ Xb, double* __restrict__ Yb, int64_t* __restrict__ idx_out) {
-  const int row_len = dx + dy;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// A row is moved as 16-byte pieces of X (when dx is even and both X buffers are 16-byte aligned: VEC = 2) followed by its
+// dy doubles of Y; consecutive threads take consecutive pieces of one row, so a row is one or two full 32-byte sectors
+// per request and the dense output is written coalesced.  Every thread evaluates pi for its own row (about 60 integer
+// operations, hidden behind the load).
+template <int VEC>
+__device__ __forceinline__ void gather_piece(const FeistelKeys& fk, int64_t n_rows, int half_bits, int64_t start, int64_t batch,
+                                             const double* __restrict__ X, int dx, const double* __restrict__ Y, int dy,
+                                             double* __restrict__ Xb, double* __restrict__ Yb, int64_t* __restrict__ idx_out, int64_t e) {
+  const int px = dx / VEC;              // pieces of X per row
+  const int row_len = px + dy;
   if (e >= batch * row_len) return;
   const int64_t j = e / row_len;
   const int c = (int)(e - j * row_len);
   const int64_t src = feistel_permute(start + j, n_rows, half_bits, fk);
-  if (c < dx) Xb[j * dx + c] = X[src * dx + c];
-  else Yb[j * dy + (c - dx)] = Y[src * dy + (c - dx)];
+  if (c < px) {
+    if (VEC == 2) {
+      *reinterpret_cast<double2*>(Xb + j * dx + 2 * c) = __ldg(reinterpret_cast<const double2*>(X + src * dx + 2 * c));
+    } else {
+      Xb[j * dx + c] = __ldg(X + src * dx + c);
+    }
+  } else {
+    Yb[j * dy + (c - px)] = __ldg(Y + src * dy + (c - px));
+  }
   if (c == 0 && idx_out) idx_out[j] = src;
+}
+
+template <int VEC>
+__global__ void minibatch_gather_kernel(FeistelKeys fk, int64_t n_rows, int half_bits, int64_t start, int64_t batch,
+                                        const double* __restrict__ X, int dx, const double* __restrict__ Y, int dy,
+                                        double* __restrict__ Xb, double* __restrict__ Yb, int64_t* __restrict__ idx_out) {
+  gather_piece<VEC>(fk, n_rows, half_bits, start, batch, X, dx, Y, dy, Xb, Yb, idx_out, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -195,19 +213,13 @@ __global__ void step_adam_state_kernel(int64_t n, double* __restrict__ theta, co
   if (mask[i]) theta[i] += -lr * (a / bc1) / (sqrt(v / bc2) + eps);
 }
 
+template <int VEC>
 __global__ void minibatch_gather_state_kernel(uint64_t seed, int64_t n_rows, int64_t batch, const int64_t* __restrict__ state,
                                               const double* __restrict__ X, int dx, const double* __restrict__ Y, int dy,
                                               double* __restrict__ Xb, double* __restrict__ Yb, int64_t* __restrict__ idx_out) {
-  const int row_len = dx + dy;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= batch * row_len) return;
   const FeistelKeys fk = feistel_keys(seed, (uint64_t)state[1]);
-  const int64_t j = e / row_len;
-  const int c = (int)(e - j * row_len);
-  const int64_t src = feistel_permute(state[2] + j, n_rows, feistel_half_bits(n_rows), fk);
-  if (c < dx) Xb[j * dx + c] = X[src * dx + c];
-  else Yb[j * dy + (c - dx)] = Y[src * dy + (c - dx)];
-  if (c == 0 && idx_out) idx_out[j] = src;
+  gather_piece<VEC>(fk, n_rows, feistel_half_bits(n_rows), state[2], batch, X, dx, Y, dy, Xb, Yb, idx_out,
+                    (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // end of a step: log the loss, count the step, move to the next batch (drop the last partial batch, then reshuffle)
@@ -233,6 +245,11 @@ using namespace gpfy;
     GPFY_COUNT_LAUNCH();                                     \
     GPFY_LAUNCH_OK();                                        \
   } while (0)
+
+// 16-byte pieces when every row of X and of the batch buffer starts 16-byte aligned
+static inline int gather_vec(const double* X, const double* Xb, int dx) {
+  return (dx % 2 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)Xb & 15) == 0) ? 2 : 1;
+}
 
 extern "C" {
 
@@ -283,9 +300,15 @@ int gpfy_minibatch_gather(void* stream, uint64_t seed, uint64_t epoch, int64_t n
     return GPFY_EINVAL;
   }
   if (batch == 0) return GPFY_OK;
-  const int64_t total = batch * (dx + dy);
-  STEP_K(minibatch_gather_kernel, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, feistel_keys(seed, epoch), n_rows,
-         feistel_half_bits(n_rows), start, batch, X, dx, Y, dy, Xb, Yb, idx_out);
+  if (gather_vec(X, Xb, dx) == 2) {
+    const int64_t total = batch * (dx / 2 + dy);
+    STEP_K(minibatch_gather_kernel<2>, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, feistel_keys(seed, epoch), n_rows,
+           feistel_half_bits(n_rows), start, batch, X, dx, Y, dy, Xb, Yb, idx_out);
+  } else {
+    const int64_t total = batch * (dx + dy);
+    STEP_K(minibatch_gather_kernel<1>, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, feistel_keys(seed, epoch), n_rows,
+           feistel_half_bits(n_rows), start, batch, X, dx, Y, dy, Xb, Yb, idx_out);
+  }
   return GPFY_OK;
 }
 
@@ -300,9 +323,15 @@ int gpfy_minibatch_gather_state(void* stream, uint64_t seed, int64_t n_rows, int
                                 const double* Y, int dy, double* Xb, double* Yb, int64_t* idx_out) {
   if (n_rows <= 0 || batch < 0 || batch > n_rows || dx <= 0 || dy < 0 || !state) { set_error("minibatch gather: bad argument"); return GPFY_EINVAL; }
   if (batch == 0) return GPFY_OK;
-  const int64_t total = batch * (dx + dy);
-  STEP_K(minibatch_gather_state_kernel, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, seed, n_rows, batch, state, X, dx, Y,
-         dy, Xb, Yb, idx_out);
+  if (gather_vec(X, Xb, dx) == 2) {
+    const int64_t total = batch * (dx / 2 + dy);
+    STEP_K(minibatch_gather_state_kernel<2>, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, seed, n_rows, batch, state, X,
+           dx, Y, dy, Xb, Yb, idx_out);
+  } else {
+    const int64_t total = batch * (dx + dy);
+    STEP_K(minibatch_gather_state_kernel<1>, (unsigned)((total + 255) / 256), 256, (cudaStream_t)stream, seed, n_rows, batch, state, X,
+           dx, Y, dy, Xb, Yb, idx_out);
+  }
   return GPFY_OK;
 }
 
