@@ -53,7 +53,7 @@ def workload_config(N, T, M, world):
         "workload": "svgp_elbo_valgrad", "N_total": int(N), "input_dim": 8, "ambient_dim": 9, "num_frequencies": 11,
         "max_degree": 10, "phase_truncation": int(T), "num_inducing": int(M), "num_outputs": 1, "likelihood": "gaussian",
         "q": "tril", "kernel": "PolynomialDecay(truncation_level=10)", "parallelism": f"rows/{world}",
-        "l2": "per-step inputs (>= 80 MB/rank) plus the per-chunk panels (786 MB/chunk) exceed the 126 MB L2",
+        "l2": "per-step inputs (>= 80 MB/rank) plus the per-chunk panels (Z, C, dT: 6.3 GB per 0.9 M-row chunk) exceed the 126 MB L2",
     }
 
 

@@ -416,12 +416,19 @@ struct Plan {
   int npsi;
 };
 
-static int64_t choose_chunk(int sms, int64_t n) {
-  // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * 8 points give every
-  // CTA the same number of tiles (no tail wave) and enough threads to fill the per-point kernels;
-  // small inputs use one chunk.
-  static int mult = 0;
-  if (!mult) { const char* e = getenv("GPFY_CHUNK_MULT"); mult = e ? atoi(e) : 8; if (mult < 1) mult = 8; }
+static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
+  // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * mult points give every CTA the same
+  // number of tiles (no tail wave).  Larger chunks mean fewer launches and pipeline fills per step (measured at the
+  // headline shape: mult 8 / 16 / 32 / 44 -> 85.1 / 86.0 / 86.4 / 86.5 M points/s), so mult defaults to 32, lowered
+  // (not below 8) where the per-chunk panels Z, C_p, dT would exceed 8 GB.  Small inputs use one chunk.
+  static int mult_env = -1;
+  if (mult_env < 0) { const char* e = getenv("GPFY_CHUNK_MULT"); mult_env = e ? std::max(1, atoi(e)) : 0; }
+  int mult = mult_env;
+  if (!mult) {
+    const double bytes_per_point = (double)(s.P + 2) * s.Mp * 8.0;
+    const int64_t cap = (int64_t)(8.0e9 / bytes_per_point) / ((int64_t)192 * sms);
+    mult = (int)std::min<int64_t>(32, std::max<int64_t>(8, cap));
+  }
   int64_t nc = (int64_t)192 * sms * mult;
   int64_t need = round_up64(n, 128);
   return need < nc ? need : nc;
@@ -430,7 +437,7 @@ static int64_t choose_chunk(int sms, int64_t n) {
 static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->s = s;
   p->sms = device_sms();
-  p->nc = choose_chunk(p->sms, n);
+  p->nc = choose_chunk(p->sms, n, s);
   p->nb = (s.Mp + SYRK_B - 1) / SYRK_B;
   p->nblk = p->nb * (p->nb + 1) / 2;
   p->KS = std::max(1, (2 * p->sms) / p->nblk);
@@ -800,6 +807,14 @@ int gpfy_elbo_packed_layout(const GpfyDesc* desc, GpfyElboLayout* out) {
   out->d_v = o; o += 1;
   out->d_sigma2 = o; o += 1;
   out->total = o;
+  return GPFY_OK;
+}
+
+int gpfy_chunk_rows(const GpfyDesc* desc, int64_t n_points, int64_t* rows) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (!rows || n_points < 0) { set_error("bad argument"); return GPFY_EINVAL; }
+  *rows = choose_chunk(device_sms(), n_points, s);
   return GPFY_OK;
 }
 

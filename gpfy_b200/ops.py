@@ -133,10 +133,10 @@ class HotPath:
 
     # ---- host-resident data: rows are streamed through the device slab by slab ----
     def slab_rows(self, n):
-        """Rows per streamed slab: a whole number of the kernels' point chunks (about 1.1 M rows)."""
-        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        chunk = 192 * sms * 8
-        return max(1, min(int(n), 5 * chunk))
+        """Rows per streamed slab: one internal chunk of the kernels (gpfy_chunk_rows; 0.9 M rows at the headline shape)."""
+        rows = ctypes.c_int64(0)
+        _lib.check(self.lib.gpfy_chunk_rows(ctypes.byref(self.desc), int(max(n, 1)), ctypes.byref(rows)))
+        return max(1, min(int(n), int(rows.value)))
 
     def elbo_valgrad_host(self, X_host, Y_host, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out_host=None, reduce=None):
         """Same as `elbo_valgrad_packed` for X [N, d], Y [N, P] in (pinned) HOST memory: slabs of rows are

@@ -103,6 +103,10 @@ GPFY_API int gpfy_elbo_packed_layout(const GpfyDesc* desc, GpfyElboLayout* out /
 /* Bytes of scratch `op` needs for up to n_points rows (host call, no GPU work). */
 GPFY_API int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t* bytes /* host */);
 
+/* Rows the kernels process per internal chunk for an input of n_points rows (a whole number of GEMM tile rounds per SM);
+ * callers that stream slabs through gpfy_svgp_elbo_rows size their slabs as multiples of it. */
+GPFY_API int gpfy_chunk_rows(const GpfyDesc* desc, int64_t n_points, int64_t* rows /* host */);
+
 /* Elementwise Gegenbauer polynomial and its derivative 2*alpha*C_{level-1}^{alpha+1}
  * (replaces gegenbauer.py:27-85: `gegenbauer`, `gegenbauer_fwd`).  `dout` may be NULL. */
 GPFY_API int gpfy_gegenbauer(void* stream, int level, double alpha, const double* x, int64_t n, double* out, double* dout);
