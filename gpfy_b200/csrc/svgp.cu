@@ -416,22 +416,32 @@ struct Plan {
   int npsi;
 };
 
+static bool fused_bwd_ok(const Shape& s);
+
 static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * mult points give every CTA the same
   // number of tiles (no tail wave).  Larger chunks mean fewer launches and pipeline fills per step (measured at the
-  // headline shape: mult 8 / 16 / 32 / 44 -> 85.1 / 86.0 / 86.4 / 86.5 M points/s), so mult defaults to 32, lowered
-  // (not below 8) where the per-chunk panels Z, C_p, dT would exceed 8 GB.  Small inputs use one chunk.
+  // headline shape: mult 8 / 16 / 32 / 44 -> 85.1 / 86.0 / 86.4 / 86.5 M points/s), so the fused path defaults to
+  // mult = 32, lowered (not below 8) where the per-chunk panels Z, C_p, dT would exceed 8 GB.  The general path keeps
+  // mult = 8: its split-K dVhat kernel has a fixed number of warps per launch and loses more on long chunks than the
+  // GEMM gains (13 degrees, N = 2 M: 46.9 ms at mult 8, 48.5 ms at 32).  Small inputs use one chunk.
   static int mult_env = -1;
   if (mult_env < 0) { const char* e = getenv("GPFY_CHUNK_MULT"); mult_env = e ? std::max(1, atoi(e)) : 0; }
   int mult = mult_env;
   if (!mult) {
     const double bytes_per_point = (double)(s.P + 2) * s.Mp * 8.0;
     const int64_t cap = (int64_t)(8.0e9 / bytes_per_point) / ((int64_t)192 * sms);
-    mult = (int)std::min<int64_t>(32, std::max<int64_t>(8, cap));
+    mult = fused_bwd_ok(s) ? (int)std::min<int64_t>(32, std::max<int64_t>(8, cap)) : 8;
   }
-  int64_t nc = (int64_t)192 * sms * mult;
-  int64_t need = round_up64(n, 128);
-  return need < nc ? need : nc;
+  const int64_t unit = (int64_t)192 * sms, nc_max = unit * mult;
+  const int64_t need = round_up64(n, 128);
+  if (need <= nc_max) return need;
+  // equal chunks: k = ceil(n / nc_max) chunks of ceil(n / k) rows rounded up to whole tile rounds, so the last chunk is
+  // not a sliver (n = 2 M: 3 x 0.68 M instead of 0.91 + 0.91 + 0.18 M)
+  const int64_t k = (n + nc_max - 1) / nc_max;
+  const int64_t per = (n + k - 1) / k;
+  const int64_t nc = round_up64(per, unit);
+  return nc < nc_max ? nc : nc_max;
 }
 
 static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
