@@ -1,22 +1,24 @@
 #!/usr/bin/env python
 """bench.py — ELBO+grad points/sec of the SVGP hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg4|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2]): full SVGP ELBO + gradient step, input_dim d = 8 (ambient dim 9,
-alpha = 3.5), degrees 0..10 (num_frequencies = 11), phase truncation T = 30 (M = 280 inducing
-harmonics, degrees >= 2 trainable), TriL q, Gaussian likelihood, P = 1, float64, N = 10 M synthetic
-rows in total, sharded by rows over the ranks (strong scaling), one all-reduce of the packed buffer.
+Workloads (BASELINE.json `configs`; the default is the one the metric is quoted on):
+  cfg3  configs[2]: full SVGP ELBO + gradient step, d = 8 (ambient dim 9, alpha = 3.5), degrees 0..10, phase truncation
+        T = 30 (M = 280 inducing harmonics), TriL q, Gaussian likelihood, P = 1, float64, N = 10 M rows.
+  cfg4  configs[3]: airline-scale regression, d = 8, degrees 0..12 (F = 13, M = 340), T = 30, N = 100 M rows.
+  cfg5  configs[4]: d = 32 (ambient dim 33), degrees 0..4, T = 64 (M = 226), Bernoulli likelihood, N = 20 M rows.
+Rows are sharded over the ranks (strong scaling: the global data set is the same for every world size, see
+gpfy_b200.synthetic.global_rows), one all-reduce of the packed buffer per step.
 
-A step = one ELBO value + all gradients over every row of the data set (+ the KL term and the
-all-reduce).  `value` has the rows resident in HBM; `e2e` streams them from pinned host memory through
-`HotPath.elbo_valgrad_host` and reads the packed result back, every step.
+A step = one ELBO value + all gradients over every row of the data set (+ the KL term and the all-reduce).  `value`
+has the rows resident in HBM; `e2e` streams them from pinned host memory through `HotPath.elbo_valgrad_host` and reads
+the packed result back, every step.
 
-`--impl reference` times the CPU restatement of the reference (oracle/gpfy_oracle.py, torch float64 on
-the host cores with autograd — JAX is not installable in this image) on a bounded
-sample of the same workload.
+`--impl reference` times the CPU restatement of the reference (oracle/gpfy_oracle.py, torch float64 on the host cores
+with autograd — JAX is not installable in this image) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -30,8 +32,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "ELBO+grad points/sec at N=10M d=8 deg10"
 UNIT = "points/s"
+CONFIGS = {
+    "cfg3": dict(d=8, F=11, T=30, lik="gaussian", N=10_000_000, seed=2, metric="ELBO+grad points/sec at N=10M d=8 deg10",
+                 kernel="PolynomialDecay(truncation_level=10)"),
+    "cfg4": dict(d=8, F=13, T=30, lik="gaussian", N=100_000_000, seed=3, metric="ELBO+grad points/sec at N=100M d=8 deg12",
+                 kernel="PolynomialDecay(truncation_level=10)"),
+    "cfg5": dict(d=32, F=5, T=64, lik="bernoulli", N=20_000_000, seed=4, metric="ELBO+grad points/sec at N=20M d=32 deg4 Bernoulli",
+                 kernel="PolynomialDecay(truncation_level=10)"),
+}
+PREFIX_ROWS = 200_000   # rows of the sharded-vs-single / two-device self-checks
 
 
 def parse():
@@ -40,20 +50,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=float, default=10_000_000, help="total rows over all ranks")
-    ap.add_argument("--T", type=int, default=30, help="phase truncation")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--n", type=float, default=None, help="total rows over all ranks (default: the config's N)")
+    ap.add_argument("--T", type=int, default=None, help="phase truncation (default: the config's T)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Phi-only / predict_diag / train-step side measurements")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="rows per CPU-baseline step")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = dict(CONFIGS[a.config])
+    if a.n is not None:
+        c["N"] = int(a.n)
+    if a.T is not None:
+        c["T"] = int(a.T)
+    a.cfg = c
+    return a
 
 
-def workload_config(N, T, M, world):
+def workload_config(name, c, M, world):
     return {
-        "workload": "svgp_elbo_valgrad", "N_total": int(N), "input_dim": 8, "ambient_dim": 9, "num_frequencies": 11,
-        "max_degree": 10, "phase_truncation": int(T), "num_inducing": int(M), "num_outputs": 1, "likelihood": "gaussian",
-        "q": "tril", "kernel": "PolynomialDecay(truncation_level=10)", "parallelism": f"rows/{world}",
-        "l2": "per-step inputs (>= 80 MB/rank) plus the per-chunk panels (Z, C, dT: 6.3 GB per 0.9 M-row chunk) exceed the 126 MB L2",
+        "workload": f"svgp_elbo_valgrad/{name}", "N_total": int(c["N"]), "input_dim": c["d"], "ambient_dim": c["d"] + 1,
+        "num_frequencies": c["F"], "max_degree": c["F"] - 1, "phase_truncation": int(c["T"]), "num_inducing": int(M), "num_outputs": 1,
+        "likelihood": c["lik"], "q": "tril", "kernel": c["kernel"], "parallelism": f"rows/{world}",
+        "data": "gpfy_b200.synthetic.global_rows(seed=%d): one global data set, identical for every world size and both arms" % c["seed"],
+        "l2": "per-step inputs (>= 80 MB/rank) plus the per-chunk panels (Z, C: GBs per chunk) exceed the 126 MB L2",
     }
 
 
@@ -109,21 +129,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU restatement of the reference (oracle) on the host cores
 # ------------------------------------------------------------------------------------------------
+def oracle_pack(host):
+    return {"dim": host["dim"], "alpha": host["alpha"], "V": host["V"], "L": host["L"], "w": host["w"], "b": host["b"],
+            "v": host["v"], "eig": host["eig"], "order": host["order"], "mu": host["mu"], "Lq": host["Lq"],
+            "sigma2": host["sigma2"], "lik": host["lik"]}
+
+
 def cpu_reference_rate(host, X_sample, Y_sample, steps, warmup):
     """points/s of oracle ELBO+grad (torch float64 CPU, autograd) on `steps` passes over the sample."""
     import torch
     from oracle import gpfy_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    pack = {"dim": host["dim"], "alpha": host["alpha"], "V": host["V"], "L": host["L"], "w": host["w"], "b": host["b"],
-            "v": host["v"], "eig": host["eig"], "order": host["order"], "mu": host["mu"], "Lq": host["Lq"],
-            "sigma2": host["sigma2"], "lik": host["lik"]}
+    pack = oracle_pack(host)
     for _ in range(warmup):
         O.elbo_and_grads(pack, X_sample, Y_sample)
     t0 = time.perf_counter()
     for _ in range(steps):
-        val, _ = O.elbo_and_grads(pack, X_sample, Y_sample)
+        val, grads = O.elbo_and_grads(pack, X_sample, Y_sample)
     dt = time.perf_counter() - t0
-    return X_sample.shape[0] * steps / dt, dt / steps, val
+    return X_sample.shape[0] * steps / dt, dt / steps, val, grads
 
 
 def run_reference(a):
@@ -131,24 +155,91 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
     import torch
     from gpfy_b200 import synthetic
+    c = a.cfg
     S = int(a.cpu_sample)
-    host, X, Y, m = synthetic.headline_host_problem(S, T=a.T)
-    rate, sec, _ = cpu_reference_rate(host, X, Y, max(1, a.steps), max(1, a.warmup))
+    host, X, Y, m = synthetic.headline_host_problem(S, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"])
+    rate, sec, _, _ = cpu_reference_rate(host, X, Y, max(1, a.steps), max(1, a.warmup))
     cores = os.cpu_count() or 1
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "impl": "reference", "metric": c["metric"], "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(a.n, a.T, sum(m), a.gpus),
+        "data": "synthetic", "config": workload_config(a.config, c, sum(m), a.gpus),
+        "rows_per_step": S,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{S} rows of the workload per step, torch {torch.__version__} float64 CPU + autograd "
+                         "sample": f"each step processes rows [0, {S}) of the config's N_total = {c['N']} global rows (a bounded sample; "
+                                   f"the rate is per row), torch {torch.__version__} float64 CPU + autograd "
                                    f"(oracle/gpfy_oracle.py; JAX is not installable here)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# self-checks that need more than one GPU (pytest only ever gets one): run under torchrun after the timed region
+# ------------------------------------------------------------------------------------------------
+def packed_checksum(hp, packed):
+    """data term and the 2-norm of every gradient block of an (all-reduced) packed buffer."""
+    import torch
+    g = hp.unpack(packed)
+    out = {"data_term": float(g["data_term"].item())}
+    for k, v in g.items():
+        if k != "data_term":
+            out["norm_" + k] = float(torch.linalg.vector_norm(v.reshape(-1)).item())
+    return out
+
+
+def sharded_prefix_check(c, dev, rank, world, allreduce):
+    """Every rank takes its shard of the first PREFIX_ROWS global rows, the packed buffers are all-reduced; rank 0 also
+    computes the whole prefix alone.  Returns max |sharded - single| / max |single| (rank 0), to be <= 1e-12."""
+    import torch
+    from gpfy_b200 import synthetic
+    n = min(PREFIX_ROWS, c["N"])
+    kw = dict(d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev)
+    mine = synthetic.headline_problem(n, rank=rank, world=world, **kw)
+    part = mine["hot"].elbo_valgrad_packed(*mine["args"]).clone()
+    allreduce(part)
+    torch.cuda.synchronize()
+    if rank != 0:
+        return None
+    full = synthetic.headline_problem(n, rank=0, world=1, **kw)
+    ref = full["hot"].elbo_valgrad_packed(*full["args"])
+    return float(((part - ref).abs().max() / ref.abs().max()).item())
+
+
+def two_device_threads_check(c, devices):
+    """ONE process, two host threads, one device each (XLA's execution model): each thread runs the hot path
+    on its half of the prefix on its own device, concurrently; the host sum must equal the single-device result."""
+    import torch
+    from gpfy_b200 import synthetic
+    n = min(PREFIX_ROWS, c["N"])
+    kw = dict(d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"])
+    res, err = [None, None], [None, None]
+
+    def work(i):
+        try:
+            torch.cuda.set_device(devices[i])
+            p = synthetic.headline_problem(n, rank=i, world=2, device=devices[i], **kw)
+            for _ in range(3):   # repeated so that the two threads really overlap inside the library
+                out = p["hot"].elbo_valgrad_packed(*p["args"])
+            torch.cuda.synchronize(devices[i])
+            res[i] = out.cpu()
+        except Exception as e:  # noqa: BLE001 - reported in the JSON line
+            err[i] = repr(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if any(err):
+        return {"error": [e for e in err if e]}
+    torch.cuda.set_device(devices[0])
+    full = synthetic.headline_problem(n, rank=0, world=1, device=devices[0], **kw)
+    ref = full["hot"].elbo_valgrad_packed(*full["args"]).cpu()
+    return {"rel": float(((res[0] + res[1] - ref).abs().max() / ref.abs().max()).item()), "devices": [str(d) for d in devices]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,6 +250,7 @@ def run_ours(a):
     from gpfy_b200 import distributed as gd
     from gpfy_b200 import ops, synthetic
 
+    c = a.cfg
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,8 +262,9 @@ def run_ours(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
-    N = int(a.n)
-    prob = synthetic.headline_problem(N, T=a.T, device=dev, rank=rank, world=world)
+    N = int(c["N"])
+    prob = synthetic.headline_problem(N, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev,
+                                      rank=rank, world=world)
     hp, args = prob["hot"], prob["args"]
     X, Y = args[0], args[1]
     n_local = X.shape[0]
@@ -222,6 +315,7 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     value = N / (ms * 1e-3)
     data_term = float(packed[0].item())
+    checksum = packed_checksum(hp, packed)
 
     # ---- end to end: rows in pinned host memory, packed result read back, every step ----
     e2e = None
@@ -251,7 +345,26 @@ def run_ours(a):
             raise SystemExit(f"bench.py: host-streamed result {v_e2e} differs from the device-resident {data_term}")
         e2e = {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int((Xh.numel() + Yh.numel()) * 8 * world), "d2h_bytes_per_step": int(out_h.numel() * 8 * world),
-               "api": "gpfy_b200.ops.HotPath.elbo_valgrad_host (gpfy_svgp_elbo_begin/rows/finish), pinned host rows"}
+               "api": "gpfy_b200.ops.HotPath.elbo_valgrad_host (gpfy_svgp_elbo_begin/rows/finish), pinned host rows, ramped slabs"}
+        del Xh, Yh
+
+    # ---- multi-GPU self-checks (all ranks take part in the first; rank 0 alone runs the second) ----
+    checks = {}
+    if world > 1:
+        rel = sharded_prefix_check(c, dev, rank, world, allreduce)
+        barrier()
+        if rank == 0:
+            checks["sharded_vs_single_prefix"] = {"rows": min(PREFIX_ROWS, N), "rel": rel, "tolerance": 1e-12}
+            if not (rel <= 1e-12):
+                raise SystemExit(f"bench.py: sharded + all-reduced result differs from the single-GPU one on the same rows: rel {rel}")
+            if torch.cuda.device_count() >= 2:
+                other = torch.device("cuda", (local + 1) % torch.cuda.device_count())
+                td = two_device_threads_check(c, [dev, other])
+                checks["one_process_two_threads_two_devices"] = td
+                if "error" in td or not (td["rel"] <= 1e-12):
+                    raise SystemExit(f"bench.py: one process driving two devices from two threads failed: {td}")
+                torch.cuda.set_device(local)
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -278,6 +391,8 @@ def run_ours(a):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("gemm_dmma_kernel", {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
+    if a.config != "cfg3":
+        traffic = None   # the committed ncu capture is of the headline shape
     step_tflops = prob["alg_flops_per_point"] * value / world * 1e-12
     roofline = {
         "bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": fp64_peak,
@@ -298,80 +413,124 @@ def run_ours(a):
         S = int(a.cpu_sample)
         host = prob["host"]
         Xs, Ys = X[:S].cpu().numpy(), Y[:S].cpu().numpy()
-        rate, sec, val = cpu_reference_rate(host, Xs, Ys, steps=3, warmup=1)
-        # cross-check while we are here: the GPU path on the same sample agrees with the oracle
-        chk = hp.elbo_valgrad_packed(X[:S], Y[:S], *args[2:])
-        kl_o = float(kl[0])
-        gpu_val = float(chk[0]) - kl_o
+        rate, sec, val, og = cpu_reference_rate(host, Xs, Ys, steps=3, warmup=1)
+        # cross-check while we are here: the GPU path on the same sample agrees with the oracle, value AND gradients
+        chk = hp.unpack(hp.elbo_valgrad_packed(X[:S], Y[:S], *args[2:]))
+        kl_g = hp.prior_kl_valgrad(mu_d, sig_d)
+        rel = lambda x, y: float(np.max(np.abs(x - y)) / max(np.max(np.abs(y)), 1e-300))
+        gpu_val = float(chk["data_term"]) - float(kl_g[0])
+        F = len(host["V"])
+        gerr = {
+            "mu": rel(chk["mu"].cpu().numpy() - kl_g[1].cpu().numpy(), og["mu"]),
+            "Lq": rel(chk["sigma"].cpu().numpy() - kl_g[2].cpu().numpy(), og["Lq"]),
+            "vhat": rel(chk["vhat"].cpu().numpy(), np.concatenate([og[f"V{i}"] for i in range(F)], 0)),
+            "w": rel(chk["w"].cpu().numpy(), og["w"]), "b": rel(chk["b"].cpu().numpy(), og["b"]),
+            "variance": rel(chk["v"].cpu().numpy(), og["v"]), "eig": rel(chk["eig"].cpu().numpy(), og["eig"]),
+        }
+        if c["lik"] == "gaussian":
+            gerr["sigma2"] = rel(chk["sigma2"].cpu().numpy(), og["sigma2"])
         cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{S} rows x 3 steps ({sec:.2f} s/step), torch {torch.__version__} float64 CPU + autograd "
+               "sample": f"rows [0, {S}) x 3 steps ({sec:.2f} s/step), torch {torch.__version__} float64 CPU + autograd "
                          f"(oracle/gpfy_oracle.py; JAX not installable)",
-               "elbo_rel_diff_gpu_vs_oracle_on_sample": abs(gpu_val - val) / abs(val)}
+               "elbo_rel_diff_gpu_vs_oracle_on_sample": abs(gpu_val - val) / abs(val),
+               "grad_rel_diff_gpu_vs_oracle_on_sample": gerr}
 
-    # ---- BASELINE.json configs[1]: Phi(X) only (projection A = sqrt(lambda v) r Phi), device resident ----
-    phi = None
-    if world == 1:
-        nphi = n_local  # the full N = 10 M: Phi is 8 M N = 22.4 GB of the 180 GB
-        ds = torch.sqrt(args[5] * args[4])
-        # the output buffers are allocated once, outside the timed region (a fresh 22.4 GB torch allocation per call
-        # made this figure swing between 16 and 29 ms with the caching allocator's state)
-        out_phi = (torch.empty((M, nphi), dtype=torch.float64, device=X.device), torch.empty((nphi,), dtype=torch.float64, device=X.device))
-        f = lambda: hp.features(X[:nphi], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True, out=out_phi)
-        for _ in range(2):
-            f()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            f()
-        e1.record(); torch.cuda.synchronize()
-        del out_phi
-        torch.cuda.empty_cache()
-        pms = e0.elapsed_time(e1) / 3
-        hbm_peak = 6549.8
-        try:
-            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        except (OSError, ValueError, KeyError):
-            pass
-        gbs = 8.0 * (8 + M) * nphi / (pms * 1e-3) * 1e-9
-        phi = {"workload": "Phi(X) [M, N] feature matrix, d=8, degrees 0..10, T=%d" % a.T, "N": nphi, "value": nphi / (pms * 1e-3),
-               "unit": UNIT, "ms": pms, "alg_bytes_per_point": 8 * (8 + M), "achieved_gbs": gbs, "hbm_peak_gbs": hbm_peak,
-               "frac_of_hbm_peak": gbs / hbm_peak}
-
-    # ---- a full training step through the gpfy API objects, driven on the device (DeviceTrainer: bijectors, inducing
-    # basis, ELBO + gradient, KL, chain rules, Adam - no host round trip) ----
-    train = None
-    if world == 1:
-        from gpfy_b200.device_step import DeviceTrainer
-        from gpfy_b200.likelihoods import Gaussian
-        from gpfy_b200.model import GP
-        from gpfy_b200.spherical import PolynomialDecay
-        from gpfy_b200.spherical_harmonics import SphericalHarmonics
-        from gpfy_b200.variational import VariationalDistributionTriL
-        sh_, q_, lik_ = SphericalHarmonics(11, phase_truncation=a.T), VariationalDistributionTriL(), Gaussian()
-        m_ = GP(PolynomialDecay()).conditional(sh_, q_)
-        par_ = m_.init(0, input_dim=8, likelihood=lik_, sh_features=sh_, variational_dist=q_)
-        tr = DeviceTrainer(par_, m_, q_, lik_, learning_rate=1e-2)
-        for _ in range(2):
-            tr.step(X, Y)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(a.steps):
-            tr.step(X, Y)
-        e1.record(); torch.cuda.synchronize()
-        tms = e0.elapsed_time(e1) / a.steps
-        ls = tr.losses()
-        train = {"api": "gpfy_b200.device_step.DeviceTrainer (SphericalHarmonics(11, T) + PolynomialDecay + TriL + Gaussian, Adam)",
-                 "value": N / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms, "loss_first": float(ls[0]), "loss_last": float(ls[-1])}
+    extras = {}
+    if world == 1 and not a.no_extras:
+        extras = side_measurements(a, c, prob, e0, e1)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(N, a.T, M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu, "phi_only": phi, "train_step": train, "elbo_data_term": data_term, "kl": float(kl[0]),
+        "config": workload_config(a.config, c, M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "elbo_data_term": data_term, "kl": float(kl[0]), "checksum": checksum,
+        "checks": checks,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_measurements(a, c, prob, e0, e1):
+    """BASELINE.json configs[1] (Phi only), predict_diag and a whole training step at the same shape, 1 GPU."""
+    import torch
+    hp, args, M = prob["hot"], prob["args"], prob["M"]
+    X, Y = args[0], args[1]
+    d, N = c["d"], X.shape[0]
+    hbm_peak = 6549.8
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except (OSError, ValueError, KeyError):
+        pass
+    fp64_peak = 37.141
+    out = {}
+
+    # ---- Phi(X) only (projection A = sqrt(lambda v) r Phi), device resident ----
+    nphi = min(N, int(40e9 / (8 * M)))   # Phi is 8 M N bytes: 22.4 GB at the headline shape, capped at 40 GB
+    ds = torch.sqrt(args[5] * args[4])
+    # the output buffers are allocated once, outside the timed region
+    out_phi = (torch.empty((M, nphi), dtype=torch.float64, device=X.device), torch.empty((nphi,), dtype=torch.float64, device=X.device))
+    f = lambda: hp.features(X[:nphi], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True, out=out_phi)
+    for _ in range(2):
+        f()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        f()
+    e1.record(); torch.cuda.synchronize()
+    del out_phi
+    torch.cuda.empty_cache()
+    pms = e0.elapsed_time(e1) / 3
+    from gpfy_b200.synthetic import algorithmic_flops_per_point
+    phi_flops = algorithmic_flops_per_point(d + 1, prob["m"], with_grad=False)
+    gbs = 8.0 * (d + M) * nphi / (pms * 1e-3) * 1e-9
+    tf = phi_flops * nphi / (pms * 1e-3) * 1e-12
+    out["phi_only"] = {"workload": "Phi(X) [M, N] feature matrix (BASELINE configs[1] at this shape)", "N": nphi,
+                       "value": nphi / (pms * 1e-3), "unit": UNIT, "ms": pms, "alg_bytes_per_point": 8 * (d + M),
+                       "achieved_gbs": gbs, "hbm_peak_gbs": hbm_peak, "frac_of_hbm_peak": gbs / hbm_peak,
+                       "alg_flops_per_point": phi_flops, "achieved_tflops": tf, "frac_of_fp64_peak": tf / fp64_peak}
+
+    # ---- predict_diag over all rows (model.py:201-229) ----
+    pargs = [args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)]
+    for _ in range(2):
+        hp.predict_diag(*pargs)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        hp.predict_diag(*pargs)
+    e1.record(); torch.cuda.synchronize()
+    qms = e0.elapsed_time(e1) / 3
+    pred_flops = phi_flops - sum(v * v for v in prob["m"]) + M * M + 2 * M   # no whitening solve: folded into W2; psi on the lower triangle
+    ptf = pred_flops * N / (qms * 1e-3) * 1e-12
+    out["predict_diag"] = {"workload": "GP.predict_diag (fmu, fvar) [N, 1]", "N": N, "value": N / (qms * 1e-3), "unit": UNIT, "ms": qms,
+                           "alg_flops_per_point": pred_flops, "achieved_tflops": ptf, "frac_of_fp64_peak": ptf / fp64_peak,
+                           "alg_bytes_per_point": 8 * (d + 2)}
+
+    # ---- a full training step through the gpfy API objects, driven on the device (DeviceTrainer) ----
+    from gpfy_b200.device_step import DeviceTrainer
+    from gpfy_b200.likelihoods import Bernoulli, Gaussian
+    from gpfy_b200.model import GP
+    from gpfy_b200.spherical import PolynomialDecay
+    from gpfy_b200.spherical_harmonics import SphericalHarmonics
+    from gpfy_b200.variational import VariationalDistributionTriL
+    sh_, q_ = SphericalHarmonics(c["F"], phase_truncation=c["T"]), VariationalDistributionTriL()
+    lik_ = Gaussian() if c["lik"] == "gaussian" else Bernoulli()
+    m_ = GP(PolynomialDecay()).conditional(sh_, q_)
+    par_ = m_.init(0, input_dim=d, likelihood=lik_, sh_features=sh_, variational_dist=q_)
+    tr = DeviceTrainer(par_, m_, q_, lik_, learning_rate=1e-2)
+    for _ in range(2):
+        tr.step(X, Y)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.steps):
+        tr.step(X, Y)
+    e1.record(); torch.cuda.synchronize()
+    tms = e0.elapsed_time(e1) / a.steps
+    ls = tr.losses()
+    out["train_step"] = {"api": "gpfy_b200.device_step.DeviceTrainer (SphericalHarmonics(F, T) + PolynomialDecay + TriL, Adam)",
+                         "value": N / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms, "loss_first": float(ls[0]), "loss_last": float(ls[-1])}
+    return out
 
 
 if __name__ == "__main__":

@@ -41,8 +41,19 @@ static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // Launch counter (bench.py reports "gpu_launches" from it).
-extern unsigned long long g_launch_count;
-#define GPFY_COUNT_LAUNCH() (++::gpfy::g_launch_count)
+void count_launch();
+#define GPFY_COUNT_LAUNCH() (::gpfy::count_launch())
+
+// Per-device state (a host framework such as XLA drives several GPUs from one process, possibly from several
+// threads).  Everything that CUDA keeps per device - the SM count, cudaFuncSetAttribute(MaxDynamicSharedMemorySize) of the
+// non-templated kernels - is cached here per device ordinal under a mutex, keyed by cudaGetDevice() of the calling thread.
+enum { DEV_CFG_GEMM = 1u << 0, DEV_CFG_SYRK = 1u << 1, DEV_CFG_GEMM32 = 1u << 2, DEV_CFG_SYRK32 = 1u << 3 };
+int device_sms();                                             // SM count of the calling thread's current device
+int device_configure_once(unsigned bit, const void* kernel, int smem_bytes);  // cudaFuncSetAttribute once per device
+
+// Development switches (gpfy_debug_set_option; never read from the environment, default 0 = production path).
+enum { DBG_CHUNK_MULT = 0, DBG_OLD_FWD = 1, DBG_NO_FUSED_BWD = 2, DBG_OLD_FEATURES = 3, DBG_COUNT = 8 };
+int debug_option(int which);
 
 // ------------------------------------------------------------------------------------------------
 // Gegenbauer three-term recurrence coefficients, passed by value as a kernel parameter so the

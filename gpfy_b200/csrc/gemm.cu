@@ -198,11 +198,7 @@ int launch_gemm(cudaStream_t stream, const GemmArgs& a, int num_sms) {
     set_error("launch_gemm: the psi epilogue needs m == k, alpha = 1, beta = 0 and an even ld_psi");
     return GPFY_EINVAL;
   }
-  static bool configured = false;
-  if (!configured) {
-    GPFY_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    configured = true;
-  }
+  GPFY_TRY(device_configure_once(DEV_CFG_GEMM, (const void*)gemm_dmma_kernel, GEMM_SMEM));
   int64_t tiles = (int64_t)((a.m + GEMM_BM - 1) / GEMM_BM) * ((a.n + GEMM_BN - 1) / GEMM_BN);
   if (tiles == 0) return GPFY_OK;
   int grid = (int)(tiles < num_sms ? tiles : num_sms);

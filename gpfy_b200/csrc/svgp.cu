@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "gemm.cuh"
@@ -18,7 +20,40 @@ namespace gpfy {
 // errors / bookkeeping
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-unsigned long long g_launch_count = 0;
+static std::atomic<unsigned long long> g_launch_count{0};
+void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+static std::atomic<int> g_debug_opt[DBG_COUNT];
+int debug_option(int which) { return (which >= 0 && which < DBG_COUNT) ? g_debug_opt[which].load(std::memory_order_relaxed) : 0; }
+
+constexpr int MAX_DEVICES = 64;
+struct DeviceState { int sms = 0; unsigned configured = 0; };
+static std::mutex g_dev_mu;
+static DeviceState g_dev[MAX_DEVICES];
+
+int device_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev[dev].sms) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    g_dev[dev].sms = sms;
+  }
+  return g_dev[dev].sms;
+}
+
+int device_configure_once(unsigned bit, const void* kernel, int smem_bytes) {
+  int dev = 0;
+  GPFY_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) { set_error("device ordinal %d out of range", dev); return GPFY_EUNSUPPORTED; }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!(g_dev[dev].configured & bit)) {
+    GPFY_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    g_dev[dev].configured |= bit;
+  }
+  return GPFY_OK;
+}
 
 // Optional per-kernel device timing (bench.py's roofline line): when enabled, the per-chunk kernels
 // of the ELBO step are bracketed by cudaEvents on the launching stream; gpfy_debug_kernel_time
@@ -100,16 +135,6 @@ int make_shape(const GpfyDesc* desc, Shape* s) {
   if (s->nw > 1024) { set_error("projection with %d weights > 1024 is not built", s->nw); return GPFY_EUNSUPPORTED; }
   if (s->mmax > 1024) { set_error("m_l = %d > 1024 is not built", s->mmax); return GPFY_EUNSUPPORTED; }
   return GPFY_OK;
-}
-
-static int device_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
-  return sms;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,9 +450,7 @@ static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   // mult = 32, lowered (not below 8) where the per-chunk panels Z, C_p, dT would exceed 8 GB.  The general path keeps
   // mult = 8: its split-K dVhat kernel has a fixed number of warps per launch and loses more on long chunks than the
   // GEMM gains (13 degrees, N = 2 M: 46.9 ms at mult 8, 48.5 ms at 32).  Small inputs use one chunk.
-  static int mult_env = -1;
-  if (mult_env < 0) { const char* e = getenv("GPFY_CHUNK_MULT"); mult_env = e ? std::max(1, atoi(e)) : 0; }
-  int mult = mult_env;
+  int mult = std::max(0, debug_option(DBG_CHUNK_MULT));  // 0 = the defaults below
   if (!mult) {
     const double bytes_per_point = (double)(s.P + 2) * s.Mp * 8.0;
     const int64_t cap = (int64_t)(8.0e9 / bytes_per_point) / ((int64_t)192 * sms);
@@ -529,7 +552,7 @@ static int set_smem(K kernel, int bytes) {
 template <int DIMP>
 static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
   const unsigned grid = (unsigned)((((a.npts + 1) & ~(int64_t)1) + 31) / 32);
-  if (a.P <= 4 && getenv("GPFY_OLD_FWD") == nullptr) {  // tensor-core forward kernel
+  if (a.P <= 4 && !debug_option(DBG_OLD_FWD)) {  // tensor-core forward kernel
     ZonalFwd2Args fa;
     fa.z = a;
     fa.mt = make_monic(0.5 * a.rc.two_alpha);
@@ -619,7 +642,7 @@ static int launch_predict(cudaStream_t st, const PredictArgs& a) {
 static int fused_red_sep(const Shape& s) { return (s.Mp / 8) < 2 * ZB_WARPS ? 1 : 0; }
 static bool fused_bwd_ok(const Shape& s) {
   return s.P == 1 && s.proj == 0 && s.dimp <= 16 && (s.Mp / 8) <= ZB_WARPS * ZB_SLOTS &&
-         zb3_smem_bytes(s.Mp, s.dimp, fused_red_sep(s)) <= 227 * 1024 && getenv("GPFY_NO_FUSED_BWD") == nullptr;
+         zb3_smem_bytes(s.Mp, s.dimp, fused_red_sep(s)) <= 227 * 1024 && !debug_option(DBG_NO_FUSED_BWD);
 }
 
 template <int DIMP>
@@ -764,7 +787,15 @@ extern "C" {
 
 int gpfy_abi_version(void) { return GPFY_ABI_VERSION; }
 const char* gpfy_last_error_string(void) { return g_err; }
-GPFY_API unsigned long long gpfy_debug_launch_count(void) { return g_launch_count; }
+GPFY_API unsigned long long gpfy_debug_launch_count(void) { return g_launch_count.load(); }
+
+// Development switches (tests / tools only; process-wide, default 0).  which: 0 = rows per chunk as a multiple of
+// 192 * SMs (0 = default), 1 = legacy forward kernel, 2 = general (unfused) backward, 3 = two-kernel feature path.
+GPFY_API int gpfy_debug_set_option(int which, int value) {
+  if (which < 0 || which >= DBG_COUNT) { set_error("unknown debug option %d", which); return GPFY_EINVAL; }
+  g_debug_opt[which].store(value, std::memory_order_relaxed);
+  return GPFY_OK;
+}
 
 #ifdef GPFY_ZB_CLOCKS
 GPFY_API int gpfy_debug_zb_clocks(unsigned long long* out) {
@@ -863,7 +894,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   GPFY_TRY(run_prologue(st, desc, p, ws, apply_to_sphere ? w : vhat, apply_to_sphere ? b : vhat, nullptr, nullptr, vhat, lcat,
                         nullptr, nullptr, false));
   RecCoef rc = make_rec_coef(desc->alpha);
-  if (ft_smem_bytes(Mp, s.dimp) <= 113 * 1024 && getenv("GPFY_OLD_FEATURES") == nullptr) {
+  if (ft_smem_bytes(Mp, s.dimp) <= 113 * 1024 && !debug_option(DBG_OLD_FEATURES)) {
     // one fused kernel (two CTAs per SM): the zonal values stay in shared memory
     FeaturesArgs fa;
     ZonalArgs& za = fa.z;
@@ -1018,8 +1049,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       sa.nb = p.nb; sa.nblk = p.nblk; sa.KS = p.KS;
       sa.range = round_up64((p.nc + p.KS - 1) / p.KS, SYRK_BK);
       sa.accumulate = 1;
-      static bool cfg = false;
-      if (!cfg) { GPFY_TRY(set_smem(syrk_dmma_kernel, SYRK_SMEM)); cfg = true; }
+      GPFY_TRY(device_configure_once(DEV_CFG_SYRK, (const void*)syrk_dmma_kernel, SYRK_SMEM));
       GPFY_K(syrk_dmma_kernel, p.nblk * p.KS, SYRK_THREADS, SYRK_SMEM, st, sa);
     }
 
@@ -1267,14 +1297,15 @@ typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, vo
 #include <dlfcn.h>
 extern "C" int gpfy_allreduce_packed(void* nccl_comm, void* stream, double* packed, int64_t count) {
   static nccl_allreduce_fn fn = nullptr;
-  if (!fn) {
+  static std::once_flag once;
+  std::call_once(once, [] {
     fn = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
     if (!fn) {
       void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
       if (h) fn = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
     }
-    if (!fn) { set_error("ncclAllReduce not found in the process or libnccl.so.2"); return GPFY_EUNSUPPORTED; }
-  }
+  });
+  if (!fn) { set_error("ncclAllReduce not found in the process or libnccl.so.2"); return GPFY_EUNSUPPORTED; }
   // ncclDouble = 8, ncclSum = 0
   int rc = fn(packed, packed, (size_t)count, 8, 0, nccl_comm, stream);
   if (rc != 0) { set_error("ncclAllReduce returned %d", rc); return GPFY_ECUDA; }

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .ops import _ptr, _stream
-from .param import FillTriangular, Param, tree_map
+from .param import Exp, FillTriangular, Identity, Param, tree_map
 from .spherical import PolynomialDecay
 
 
@@ -37,6 +37,7 @@ class DeviceTrainer:
         if self.learned and max(hp.m) > 64:
             raise _lib.GpfyError("DeviceTrainer needs m_l <= 64 in learned-basis mode")
         self.vnames = sorted(con.params["variational"]["inducing_features"])
+        self._check_bijectors(con, kname, lik, q, bool(hp.projection_dim))
         M, P, F, dim = hp.M, hp.P, hp.F, hp.dim
         ntri = M * (M + 1) // 2
         L = _lib.GpfyStepLayout()
@@ -114,6 +115,29 @@ class DeviceTrainer:
         sl = lambda a, n: c[a:a + n]
         self.v_w, self.v_b, self.v_v, self.v_eig = sl(L.c_w, hp.nw), sl(L.c_b, 1), sl(L.c_v, 1), sl(L.c_eig, F)
         self.v_s2, self.v_mu, self.v_sig, self.v_V = sl(L.c_s2, 1), sl(L.c_mu, M * P), sl(L.c_sig, P * M * M), sl(L.c_V, M * dim)
+
+    def _check_bijectors(self, con, kname, lik, q, projection):
+        """The device kernels implement ONE transform per slot (gpfy_step_constrain / gpfy_step_grad: Exp for the
+        kernel scalars, weights and the noise variance, Identity for projection weights, mu and V, FillTriangular for
+        Sigma - the defaults of the reference, param.py:24-25, variational.py:260).  A Param whose bijector was changed
+        with `set_bijector` would train with the wrong transform, so it is refused here (use the host loop
+        `GP.fit` + `create_training_step`, which honours `param._bijectors`)."""
+        bj = con._bijectors
+        want = [((kname, "weight_variances"), Identity if projection else Exp), ((kname, "bias_variance"), Exp),
+                ((kname, "variance"), Exp)]
+        if "beta" in con.params[kname]:
+            want.append(((kname, "beta"), Exp))
+        if lik._sigma2(con) is not None:
+            want.append((("likelihood", lik.name, "variance"), Exp))
+        want += [(("variational", q.name, "mu"), Identity), (("variational", q.name, "Sigma"), FillTriangular)]
+        want += [(("variational", "inducing_features", n), Identity) for n in self.vnames]
+        for path, cls in want:
+            node = bj
+            for k in path:
+                node = node[k]
+            if type(node) is not cls:
+                raise _lib.GpfyError(f"DeviceTrainer: parameter {'/'.join(path)} has bijector {type(node).__name__}, the device step "
+                                     f"implements {cls.__name__} there; train this Param with GP.fit + create_training_step instead")
 
     # ------------------------------------------------------------------
     def step(self, X, Y):

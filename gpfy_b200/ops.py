@@ -138,6 +138,24 @@ class HotPath:
         _lib.check(self.lib.gpfy_chunk_rows(ctypes.byref(self.desc), int(max(n, 1)), ctypes.byref(rows)))
         return max(1, min(int(n), int(rows.value)))
 
+    @staticmethod
+    def slab_bounds(n, cap):
+        """Row boundaries of the streamed slabs.  Nothing can overlap the copy of the FIRST slab, so the slabs ramp up:
+        cap / 16, cap / 4, then equal slabs of at most `cap` rows (one internal chunk each).  With slab = chunk = half a
+        rank's shard (8 GPUs, N = 10 M) half of the H2D time used to be exposed; now it is 1/32 of it."""
+        n, cap = int(n), int(cap)
+        bounds = [0]
+        for frac in (16, 4):
+            step = max(1024, cap // frac // 1024 * 1024)
+            if bounds[-1] + step + cap // 4 < n:
+                bounds.append(bounds[-1] + step)
+        rem = n - bounds[-1]
+        k = max(1, -(-rem // cap))
+        per = min(cap, -(-(-(-rem // k)) // 1024) * 1024)
+        while bounds[-1] < n:
+            bounds.append(min(n, bounds[-1] + per))
+        return bounds
+
     def elbo_valgrad_host(self, X_host, Y_host, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out_host=None, reduce=None):
         """Same as `elbo_valgrad_packed` for X [N, d], Y [N, P] in (pinned) HOST memory: slabs of rows are
         copied on a side stream while the previous slab is being processed (gpfy_svgp_elbo_begin / rows /
@@ -154,6 +172,7 @@ class HotPath:
         if out_host is None:
             out_host = torch.empty((self.layout.total,), dtype=torch.float64).pin_memory()
         cap = self.slab_rows(n)
+        bounds = self.slab_bounds(n, cap)
         ws = self.workspace(cap, _lib.OP_ELBO)
         st = self._stream_state(cap)
         dptr = ctypes.byref(self.desc)
@@ -162,8 +181,7 @@ class HotPath:
         _lib.check(self.lib.gpfy_svgp_elbo_begin(_stream(self.device), dptr, cap, _ptr(wv), _ptr(bv), _ptr(vv), _ptr(ev), _ptr(vh),
                                                  _ptr(lc), _ptr(muv), _ptr(sg), _ptr(ws), ws.numel()))
         k = 0
-        for lo in range(0, n, cap):
-            hi = min(n, lo + cap)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
             xb, yb = st["X"][k % 2], st["Y"][k % 2]
             with torch.cuda.stream(st["copy"]):
                 st["copy"].wait_event(st["free"][k % 2])      # slab buffer no longer read by the compute stream
@@ -320,6 +338,15 @@ class HotPath:
         out = torch.empty((1 + M * P + P * M * M,), dtype=torch.float64, device=self.device)
         _lib.check(self.lib.gpfy_prior_kl_valgrad(_stream(self.device), ctypes.byref(self.desc), _ptr(mu), _ptr(sigma), _ptr(out)))
         return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
+
+
+DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3}
+
+
+def debug_option(name, value):
+    """Development switch of the library (tests / tools): `chunk_mult` = rows per internal chunk as a multiple of
+    192 * SMs (0 = default); `old_fwd`, `no_fused_bwd`, `old_features` = 1 route a call through the general kernels."""
+    _lib.check(_lib.load().gpfy_debug_set_option(DEBUG_OPTIONS[name], int(value)))
 
 
 def launch_count():

@@ -129,6 +129,26 @@ def loss_and_grad_unconstrained(free_param: Param, m, q, lik, train_data, datase
     return -value, gfree
 
 
+def _materialise_rows(X, Y, device=None):
+    """(X, Y) as float64 CUDA tensors (used in place if they already are), or pinned host tensors when the rows do not
+    fit in the free device memory next to the hot path's workspace (kept at <= 40 % of what is free now)."""
+    from .ops import require_cuda
+    dev = require_cuda(device)
+    if torch.is_tensor(X) and (X.is_cuda or X.is_pinned()):
+        Yt = Y if torch.is_tensor(Y) else torch.as_tensor(np.asarray(Y, dtype=np.float64))
+        if X.is_cuda and not Yt.is_cuda:
+            Yt = Yt.to(device=X.device, dtype=torch.float64)
+        return X, Yt
+    Xt = X if torch.is_tensor(X) else torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float64)))
+    Yt = Y if torch.is_tensor(Y) else torch.from_numpy(np.ascontiguousarray(np.asarray(Y, dtype=np.float64)))
+    Xt, Yt = Xt.to(torch.float64).contiguous(), Yt.to(torch.float64).reshape(Xt.shape[0], -1).contiguous()
+    need = (Xt.numel() + Yt.numel()) * 8
+    free, _ = torch.cuda.mem_get_info(dev)
+    if need <= 0.4 * free:
+        return Xt.to(dev), Yt.to(dev)
+    return Xt.pin_memory(), Yt.pin_memory()
+
+
 def create_training_step(model, dataset, dataset_xy_keys, q, lik, batch_size=None, allreduce=None, n_total=None, seed=0):
     """optimization.py:60-122.  `dataset` is any mapping of column name -> array (the reference takes a
     HuggingFace Dataset; `datasets` is a host-side container either way).  Full batch: the rows are captured
@@ -138,20 +158,27 @@ def create_training_step(model, dataset, dataset_xy_keys, q, lik, batch_size=Non
     x_key, y_key = dataset_xy_keys
     X_all, Y_all = dataset[x_key], dataset[y_key]
     N = int(np.shape(X_all)[0])
+    world = allreduce.world if allreduce is not None else 1
+    if world > 1 and n_total is None:
+        raise ValueError("create_training_step: rows sharded over ranks (allreduce.world > 1) need n_total, the global row count")
     if batch_size:
         from .minibatch import DeviceMinibatches
         batches = DeviceMinibatches(X_all, Y_all, batch_size, seed=seed)
         next_batch = batches.next
+        n_global = N if n_total is None else int(n_total)
 
         def train_step(state, _=None):
             X, Y = next_batch()
             # optimization.py:154: scale = dataset_size / batch; under data parallelism every rank draws `batch_size`
             # rows of its own shard, so the batch is batch_size * world rows of the n_total-row data set
             loss, grads = loss_and_grad_unconstrained(state.apply_fn(state.params), model, q, lik, (X, Y),
-                                                      dataset_size=N if n_total is None else int(n_total), allreduce=allreduce,
-                                                      n_total=None if n_total is None else batch_size * allreduce.world)
+                                                      dataset_size=n_global, allreduce=allreduce, n_total=batch_size * world)
             return state.apply_gradients(grads=grads), loss
         return train_step
+
+    # full batch: the rows are materialised ONCE - on the device when they fit next to the workspace, otherwise in
+    # pinned host memory, from where every step streams them (HotPath.elbo_valgrad_host) - and reused by every step
+    X_all, Y_all = _materialise_rows(X_all, Y_all)
 
     def train_step(state, _=None):
         loss, grads = loss_and_grad_unconstrained(state.apply_fn(state.params), model, q, lik, (X_all, Y_all),

@@ -1,4 +1,4 @@
-"""Seeded synthetic problems of BASELINE.json's shapes, generated on the device.
+"""Seeded synthetic problems of BASELINE.json's shapes: one global data set per configuration, the same for every world size.
 
 Used by bench.py, smoke() and the full-size GPU tests.  There is no network for datasets; the data
 are N(0, I) inputs with a smooth target, the parameters a random but well-conditioned point.
@@ -82,32 +82,67 @@ def headline_params(d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2):
     return host, m
 
 
+DATA_BLOCK = 65536  # rows per independently seeded block of the global data set
+
+
+def global_rows(lo, hi, d=8, P=1, likelihood="gaussian", seed=2):
+    """Rows [lo, hi) of THE global synthetic data set of a configuration, as CPU float64 tensors (X [n, d], Y [n, P]).
+
+    The data set is defined block by block: rows [k B, (k + 1) B), B = DATA_BLOCK, are drawn from a CPU generator
+    seeded with (seed, k) alone, so that row i is the same numbers whatever the world size, the rank that owns it, the
+    device or the arm of bench.py that asks (GPU arm, CPU reference arm, tests).  X ~ N(0, I),
+    y_j = (j + 1) sum_c sin(x_c) / sqrt(d) + 0.1 eps  (thresholded at 0 for the Bernoulli likelihood)."""
+    lo, hi = int(lo), int(hi)
+    n = max(hi - lo, 0)
+    X = torch.empty((n, d), dtype=torch.float64)
+    Y = torch.empty((n, P), dtype=torch.float64)
+    if n == 0:
+        return X, Y
+    g = torch.Generator(device="cpu")
+    for k in range(lo // DATA_BLOCK, (hi - 1) // DATA_BLOCK + 1):
+        g.manual_seed((int(seed) + 1000) * 1_000_003 + k)
+        G = torch.randn((DATA_BLOCK, d + P), dtype=torch.float64, generator=g)
+        b0 = k * DATA_BLOCK
+        s0, s1 = max(lo, b0) - b0, min(hi, b0 + DATA_BLOCK) - b0
+        Xb = G[s0:s1, :d]
+        f = torch.sin(Xb).sum(1, keepdim=True) / math.sqrt(d)
+        Yb = f * torch.arange(1, P + 1, dtype=torch.float64) + 0.1 * G[s0:s1, d:]
+        if likelihood == "bernoulli":
+            Yb = (Yb > 0).to(torch.float64)
+        X[b0 + s0 - lo:b0 + s1 - lo] = Xb
+        Y[b0 + s0 - lo:b0 + s1 - lo] = Yb
+    return X, Y
+
+
+def global_rows_device(lo, hi, device, d=8, P=1, likelihood="gaussian", seed=2, piece=32 * DATA_BLOCK):
+    """`global_rows` materialised on `device`, generated and uploaded in pieces of <= 2 M rows (bounded host memory)."""
+    lo, hi = int(lo), int(hi)
+    X = torch.empty((max(hi - lo, 0), d), dtype=torch.float64, device=device)
+    Y = torch.empty((max(hi - lo, 0), P), dtype=torch.float64, device=device)
+    for a in range(lo, hi, piece):
+        b = min(hi, a + piece)
+        Xc, Yc = global_rows(a, b, d, P, likelihood, seed)
+        X[a - lo:b - lo].copy_(Xc)
+        Y[a - lo:b - lo].copy_(Yc)
+    return X, Y
+
+
 def headline_host_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2):
-    """CPU-only variant (numpy rows) for the reference arm of bench.py: (host params, X, Y, m)."""
+    """CPU-only variant (numpy rows [0, N) of the global data set) for the reference arm of bench.py: (host params, X, Y, m)."""
     host, m = headline_params(d, F, T, P, likelihood, seed)
-    rng = np.random.default_rng(seed + 1000)
-    X = rng.standard_normal((N, d))
-    f = np.sin(X).sum(1, keepdims=True) / math.sqrt(d)
-    Y = np.concatenate([f * (j + 1) for j in range(P)], 1) + 0.1 * rng.standard_normal((N, P))
-    if likelihood == "bernoulli":
-        Y = (Y > 0).astype(np.float64)
-    return host, X, Y, m
+    X, Y = global_rows(0, N, d, P, likelihood, seed)
+    return host, X.numpy(), Y.numpy(), m
 
 
 def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, device="cuda", rank=0, world=1):
-    """BASELINE.json configs[2]: full SVGP ELBO+gradient step, d=8, degrees 0..10, phase truncation T.
-    Rank `rank` of `world` owns a contiguous block of N/world rows of the global data set, generated on the device."""
+    """BASELINE.json configs[2] (and, through d / F / T / likelihood, configs[3], [4]): full SVGP ELBO+gradient step.
+    Rank `rank` of `world` owns the contiguous block `shard_bounds(N, rank, world)` of the N global rows
+    (`global_rows`: the same data set for every world size)."""
     from .distributed import shard_bounds
     host, m = headline_params(d, F, T, P, likelihood, seed)
     M, dim = sum(m), d + 1
     lo, hi = shard_bounds(N, rank, world)
-    g = torch.Generator(device=device)
-    g.manual_seed(1234 + 7919 * rank)
-    X = torch.randn((hi - lo, d), dtype=torch.float64, device=device, generator=g)
-    f = torch.sin(X).sum(1, keepdim=True) / math.sqrt(d)
-    Y = torch.cat([f * (j + 1) for j in range(P)], 1) + 0.1 * torch.randn((hi - lo, P), dtype=torch.float64, device=device, generator=g)
-    if likelihood == "bernoulli":
-        Y = (Y > 0).to(torch.float64)
+    X, Y = global_rows_device(lo, hi, device, d, P, likelihood, seed)
     hp = HotPath(d, m, num_outputs=P, kernel_order=1, likelihood=likelihood, q_kind="tril", weight_mode="ard", device=device)
     vhat = np.concatenate(host["V"], 0)
     lcat = np.concatenate([l.ravel() for l in host["L"]])
@@ -115,7 +150,7 @@ def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, dev
     args = (X, Y, dev(host["w"]), dev(host["b"]), dev(host["v"]), dev(host["eig"]), dev(vhat), dev(lcat), dev(host["mu"]),
             dev(host["Lq"]), dev(host["sigma2"]))
     return {
-        "hot": hp, "args": args, "m": m, "M": M, "dim": dim, "host": host,
+        "hot": hp, "args": args, "m": m, "M": M, "dim": dim, "host": host, "rows": (lo, hi),
         "alg_flops_per_point": algorithmic_flops_per_point(dim, m, True),
         "alg_bytes_per_point": 8 * (d + P),
     }

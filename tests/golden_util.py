@@ -57,3 +57,15 @@ def rel_err(a, b):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def elem_err(a, b, floor=1e-6):
+    """Componentwise: max_i |a_i - b_i| / max(|b_i|, floor * |b|_inf) - the per-element relative error of every entry that is
+    not smaller than `floor` times the largest one (below that the error is measured against the floor)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        raise AssertionError(f"shape mismatch {a.shape} vs {b.shape}")
+    if a.size == 0:
+        return 0.0
+    den = np.maximum(np.abs(b), max(floor * np.max(np.abs(b)), 1e-300))
+    return float(np.max(np.abs(a - b) / den))

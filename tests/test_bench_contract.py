@@ -17,8 +17,20 @@ def test_reference_arm_prints_contract_line():
     assert line["metric"].startswith("ELBO+grad points/sec") and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["config"]["workload"] == "svgp_elbo_valgrad" and line["config"]["num_inducing"] == 280
+    assert line["config"]["workload"] == "svgp_elbo_valgrad/cfg3" and line["config"]["num_inducing"] == 280
+    assert line["config"]["N_total"] == 10_000_000 and line["rows_per_step"] == 2000   # the config's N, and what a step really processed
     assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None
+
+
+def test_reference_arm_other_configs():
+    """--config cfg5 (d = 32, Bernoulli) and cfg4 (13 degrees) on the CPU arm: same line, their own shapes."""
+    for cfg, M, lik in (("cfg5", 226, "bernoulli"), ("cfg4", 340, "gaussian")):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", cfg, "--steps", "1",
+                              "--warmup", "1", "--cpu-sample", "1000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["config"]["workload"] == "svgp_elbo_valgrad/" + cfg and line["config"]["num_inducing"] == M
+        assert line["config"]["likelihood"] == lik and line["value"] > 0
 
 
 def test_product_arm_needs_a_gpu():

@@ -165,6 +165,20 @@ def test_device_trainer_matches_host_training_loop(name):
         assert rel_err(a, b) < 1e-8
 
 
+def test_device_trainer_refuses_a_changed_bijector():
+    """the device step hard-codes Exp / Identity / FillTriangular; a Param whose bijector was changed with
+    set_bijector must be refused (the host loop honours it), not trained with the wrong transform."""
+    from gpfy_b200 import _lib
+    from gpfy_b200.device_step import DeviceTrainer
+    from gpfy_b200.param import identity
+    o = objects_from_golden(load("d8_F6_T12"))
+    kernel, q, lik, m, param = o["kernel"], o["q"], o["lik"], o["m"], o["param"]
+    DeviceTrainer(param, m, q, lik)                      # the defaults are accepted
+    changed = param.set_bijector(kernel.name, variance=identity())
+    with pytest.raises(_lib.GpfyError, match="bijector"):
+        DeviceTrainer(changed, m, q, lik)
+
+
 @pytest.mark.parametrize("name", API_CASES)
 def test_kernel_matrix_side_matches_reference(name):
     """K, K2, shape_function, project_variance, GP.predict / GP.cov against the reference's outputs."""

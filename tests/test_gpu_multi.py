@@ -117,3 +117,41 @@ def test_two_gpu_device_trainer_matches_single_gpu_training():
         p.join(300)
         assert p.exitcode == 0
     assert all(ret.get(r, 1.0) < 1e-9 for r in range(world)), dict(ret)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_two_threads_two_devices():
+    """XLA's execution model: ONE process, one host thread per device, concurrent calls into the library.
+    The per-device state (SM count, shared-memory opt-in of the non-templated kernels) is keyed by device ordinal under
+    a mutex, so the second device must not launch with the first one's configuration.  Each thread computes its half of
+    the rows on its own device; the host sum equals the single-device result."""
+    import threading
+    from gpfy_b200.synthetic import headline_problem
+    N = 150_003
+    res, err = [None, None], [None, None]
+
+    def work(i):
+        try:
+            torch.cuda.set_device(i)
+            p = headline_problem(N, rank=i, world=2, device=torch.device("cuda", i))
+            for _ in range(3):
+                out = p["hot"].elbo_valgrad_packed(*p["args"])
+                fmu, fvar = p["hot"].predict_diag(*[p["args"][k] for k in (0, 2, 3, 4, 5, 6, 7, 8, 9)])
+            torch.cuda.synchronize(i)
+            res[i] = (out.cpu(), fmu.cpu(), fvar.cpu())
+        except Exception as e:  # noqa: BLE001
+            err[i] = repr(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in (1, 0)]   # device 1 first: it must configure itself
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert err == [None, None], err
+    torch.cuda.set_device(0)
+    full = headline_problem(N, rank=0, world=1, device=torch.device("cuda", 0))
+    ref = full["hot"].elbo_valgrad_packed(*full["args"]).cpu()
+    rmu, rvar = full["hot"].predict_diag(*[full["args"][k] for k in (0, 2, 3, 4, 5, 6, 7, 8, 9)])
+    assert float((res[0][0] + res[1][0] - ref).abs().max() / ref.abs().max()) < 1e-12
+    assert torch.allclose(torch.cat([res[0][1], res[1][1]]), rmu.cpu(), rtol=1e-12, atol=1e-13)
+    assert torch.allclose(torch.cat([res[0][2], res[1][2]]), rvar.cpu(), rtol=1e-12, atol=1e-13)

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import gpfy_oracle as O
-from tests.golden_util import CASES, golden_pack, load, rel_err
+from tests.golden_util import CASES, elem_err, golden_pack, load, rel_err
 from tests.test_gpu_parity import ARD_CASES, _cat, _hot, _resolved
 
 pytestmark = pytest.mark.gpu
@@ -90,6 +90,48 @@ def test_stages_and_host_stream_equal_one_shot(N):
     h = hp.unpack(host)
     for k in r:
         assert rel_err(h[k].numpy(), r[k].cpu().numpy()) < 1e-11, k
+
+
+@pytest.mark.parametrize("lik,P,T,F,d", [("gaussian", 1, 30, 11, 8), ("bernoulli", 1, 30, 11, 8), ("gaussian", 2, 12, 6, 8),
+                                          ("gaussian", 1, 30, 13, 8), ("bernoulli", 1, 24, 5, 32)])
+def test_several_internal_chunks_match_oracle(lik, P, T, F, d):
+    """Rows spanning 3.2 internal chunks (chunk = 192 * SMs rows with the development switch chunk_mult = 1), a q far from
+    the prior (random mu, L_q with O(1) off-diagonal mass): value and EVERY gradient against the oracle on all rows,
+    1e-10 normwise and 1e-9 componentwise.  Covers the accumulation across chunks of every split-K / partial-sum buffer
+    on the fused (P = 1, Gaussian), fused-backward (Bernoulli) and general (P = 2) paths."""
+    from gpfy_b200 import ops
+    from gpfy_b200.synthetic import headline_problem
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    N = int(3.2 * 192 * sms) + 5
+    prob = headline_problem(N, d=d, F=F, T=T, P=P, likelihood=lik, device="cuda", seed=11)
+    hp, args, host = prob["hot"], list(prob["args"]), prob["host"]
+    rng = np.random.default_rng(5)
+    M = hp.M
+    host["mu"] = rng.standard_normal((M, P))
+    host["Lq"] = np.stack([np.tril(0.6 * np.eye(M) + 0.8 * rng.standard_normal((M, M)) / np.sqrt(M)) for _ in range(P)])
+    args[8] = torch.as_tensor(host["mu"], device="cuda")
+    args[9] = torch.as_tensor(host["Lq"], device="cuda")
+    try:
+        ops.debug_option("chunk_mult", 1)
+        rows = ctypes.c_int64(0)
+        hp.lib.gpfy_chunk_rows(ctypes.byref(hp.desc), N, ctypes.byref(rows))
+        assert rows.value == 192 * sms and N > 3 * rows.value     # really four launches of every per-chunk kernel
+        out = {k: v.cpu().numpy() for k, v in hp.unpack(hp.elbo_valgrad_packed(*args)).items()}
+    finally:
+        ops.debug_option("chunk_mult", 0)
+    pack = {"dim": host["dim"], "alpha": host["alpha"], "V": host["V"], "L": host["L"], "w": host["w"], "b": host["b"],
+            "v": host["v"], "eig": host["eig"], "order": 1, "mu": host["mu"], "Lq": host["Lq"], "sigma2": host["sigma2"], "lik": lik}
+    oval, og = O.elbo_and_grads(pack, args[0].cpu().numpy(), args[1].cpu().numpy(), data_only=True)
+    assert abs(out["data_term"] - oval) <= TOL * abs(oval)
+    nF = len(host["V"])
+    ref = {"mu": og["mu"], "sigma": og["Lq"], "eig": og["eig"], "w": og["w"], "b": og["b"], "v": og["v"],
+           "vhat": np.concatenate([og[f"V{i}"] for i in range(nF)], 0),
+           "lcat": np.concatenate([np.tril(og[f"L{i}"]).ravel() for i in range(nF)])}
+    if lik == "gaussian":
+        ref["sigma2"] = og["sigma2"]
+    for k, r in ref.items():
+        assert rel_err(out[k].reshape(np.shape(r)), r) < TOL, k
+        assert elem_err(out[k].reshape(np.shape(r)), r) < 1e-9, k
 
 
 def test_empty_input_gives_zero_sums():
@@ -223,7 +265,7 @@ def test_inducing_basis_on_device_matches_reference_and_autograd(name):
     assert rel_err(dV.cpu().numpy(), np.concatenate([x.numpy() for x in grads], 0)) < 1e-9
 
 
-def test_fused_and_general_kernel_paths_agree_on_the_headline_shape(monkeypatch):
+def test_fused_and_general_kernel_paths_agree_on_the_headline_shape():
     """Two independent implementations of the same step: the tensor-core zonal forward + fused backward (P = 1,
     ambient dim <= 16, Mp <= 288) against the general one-point-per-lane kernels that serve every other shape,
     selected by the library's A/B switches.  Same inputs -> same packed value and gradients, features and predictions."""
@@ -234,11 +276,16 @@ def test_fused_and_general_kernel_paths_agree_on_the_headline_shape(monkeypatch)
     fused = hp.elbo_valgrad_packed(*args).clone()
     fmu, fvar = (t.clone() for t in hp.predict_diag(*pred_args))
     A = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0].clone()
-    for k in ("GPFY_NO_FUSED_BWD", "GPFY_OLD_FWD", "GPFY_OLD_FEATURES"):
-        monkeypatch.setenv(k, "1")
-    general = hp.elbo_valgrad_packed(*args)
-    gmu, gvar = hp.predict_diag(*pred_args)
-    gA = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0]
+    from gpfy_b200 import ops
+    try:
+        for k in ("no_fused_bwd", "old_fwd", "old_features"):
+            ops.debug_option(k, 1)
+        general = hp.elbo_valgrad_packed(*args)
+        gmu, gvar = hp.predict_diag(*pred_args)
+        gA = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0]
+    finally:
+        for k in ("no_fused_bwd", "old_fwd", "old_features"):
+            ops.debug_option(k, 0)
     lay = hp.layout
     for name in ("data_term", "d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2"):
         lo = getattr(lay, name)

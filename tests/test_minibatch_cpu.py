@@ -44,3 +44,16 @@ def test_bad_arguments_are_reported():
         shuffle_index(0, 0, 10, 10)
     with pytest.raises(_lib.GpfyError):
         shuffle_index(0, 0, 0, 0)
+
+
+def test_streamed_slab_bounds_ramp_and_cover():
+    """HotPath.slab_bounds: slabs cover [0, n) exactly, none exceeds the workspace capacity, and the first one is small
+    (<= cap / 16) whenever there is more than a chunk and a quarter of data (its copy cannot overlap any compute)."""
+    from gpfy_b200.ops import HotPath
+    for n, cap in ((10_000_000, 909_312), (1_250_000, 625_152), (1, 1), (31, 128), (1000, 1024), (150_001, 150_016),
+                   (2_000_000, 681_984), (909_312, 909_312), (909_313, 909_312)):
+        b = HotPath.slab_bounds(n, cap)
+        sizes = [y - x for x, y in zip(b[:-1], b[1:])]
+        assert b[0] == 0 and b[-1] == n and all(0 < s <= cap for s in sizes), (n, cap, b)
+        if n > 2 * cap:
+            assert sizes[0] <= cap // 16 and sizes[1] <= cap // 4
