@@ -95,10 +95,15 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) produce();
 
+  // A warp's three 8-row sub-tiles are rows r * 32 + wm * 8 (+ g) of the CTA tile - interleaved, so that a partial last row
+  // tile (m = 352 or 256: 64 of 96 rows) costs every warp two of its three sub-tiles instead of idling a warp row.
   double acc[3][8][2];
   int c_tile = blockIdx.x, c_kb = 0, c_kt = kt_of(blockIdx.x);
   int row0 = (c_tile % m_tiles) * GEMM_BM, col0 = (c_tile / m_tiles) * GEMM_BN;
-  bool active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;
+  bool active = (row0 + wm * 8) < a.m && (col0 + wn * 64) < a.n;
+  bool ract[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) ract[r] = (row0 + r * 32 + wm * 8) < a.m;
   for (int it = 0; it < total; ++it) {
     const int st = it % GEMM_STAGES;
     if (c_kb == 0) {
@@ -108,20 +113,22 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
         for (int c = 0; c < 8; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
     }
     mbar_wait(&bar_full[st], (it / GEMM_STAGES) & 1);
-    const double* as = As + st * GEMM_BM * GEMM_AS + (wm * 24 + g) * GEMM_AS + t4;
+    const double* as = As + st * GEMM_BM * GEMM_AS + (wm * 8 + g) * GEMM_AS + t4;
     const double* bs = Bs + st * GEMM_BK * GEMM_BS + t4 * GEMM_BS + wn * 64 + g;
 #pragma unroll
     for (int k4 = 0; k4 < GEMM_BK / 4; ++k4) {
       if (active) {
         double af[3], bf[8];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) af[r] = as[r * 8 * GEMM_AS + k4 * 4];
+        for (int r = 0; r < 3; ++r) af[r] = as[r * 32 * GEMM_AS + k4 * 4];
 #pragma unroll
         for (int c = 0; c < 8; ++c) bf[c] = bs[k4 * 4 * GEMM_BS + c * 8];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
+          if (ract[r]) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
+            for (int c = 0; c < 8; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
+          }
       }
       if (k4 == 0) produce();  // the copy issue hides behind the DMMAs just queued
     }
@@ -135,7 +142,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
       if (active && !(VAR & 2)) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const int row = row0 + wm * 24 + r * 8 + g;
+          const int row = row0 + r * 32 + wm * 8 + g;
           if (row < a.m) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -181,7 +188,9 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
       c_kt = kt_of(c_tile);
       row0 = (c_tile % m_tiles) * GEMM_BM;
       col0 = (c_tile / m_tiles) * GEMM_BN;
-      active = (row0 + wm * 24) < a.m && (col0 + wn * 64) < a.n;
+      active = (row0 + wm * 8) < a.m && (col0 + wn * 64) < a.n;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) ract[r] = (row0 + r * 32 + wm * 8) < a.m;
     }
   }
 }

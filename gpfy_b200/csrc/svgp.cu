@@ -11,6 +11,7 @@
 #include "gemm.cuh"
 #include "svgp_kernels.cuh"
 #include "zonal_bwd3.cuh"
+#include "zonal_bwd4.cuh"
 #include "zonal_fwd2.cuh"
 #include "basis.cuh"
 
@@ -442,6 +443,7 @@ struct Plan {
 };
 
 static bool fused_bwd_ok(const Shape& s);
+static bool bwd4_ok(const Shape& s);
 
 static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   // GEMM tiles are 96 x 192 with one persistent CTA per SM: chunks of 192 * sms * mult points give every CTA the same
@@ -454,7 +456,7 @@ static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   if (!mult) {
     const double bytes_per_point = (double)(s.P + 2) * s.Mp * 8.0;
     const int64_t cap = (int64_t)(8.0e9 / bytes_per_point) / ((int64_t)192 * sms);
-    mult = fused_bwd_ok(s) ? (int)std::min<int64_t>(32, std::max<int64_t>(8, cap)) : 8;
+    mult = (fused_bwd_ok(s) || bwd4_ok(s)) ? (int)std::min<int64_t>(32, std::max<int64_t>(8, cap)) : 8;
   }
   const int64_t unit = (int64_t)192 * sms, nc_max = unit * mult;
   const int64_t need = round_up64(n, 128);
@@ -564,17 +566,19 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
     const int pmax = a.P == 1 ? 1 : (a.P == 2 ? 2 : 4);
     const int smem = zf2_smem_bytes(a.Mp, DIMP, a.P, a.mz != nullptr, pmax);
     const unsigned pgrid = std::min(grid, (unsigned)(2 * device_sms()));  // persistent: two CTAs per SM
-#define GPFY_ZF(PM)                                                \
-  {                                                                \
-    GPFY_TRY(set_smem(zonal_fwd2_kernel<DIMP, PM>, smem));         \
-    zonal_fwd2_kernel<DIMP, PM><<<pgrid, 256, smem, st>>>(fa);     \
+#define GPFY_ZF(PM, ZP)                                                \
+  {                                                                    \
+    GPFY_TRY(set_smem(zonal_fwd2_kernel<DIMP, PM, ZP>, smem));         \
+    zonal_fwd2_kernel<DIMP, PM, ZP><<<pgrid, 256, smem, st>>>(fa);     \
   }
-    if (pmax == 1) GPFY_ZF(1) else if (pmax == 2) GPFY_ZF(2) else GPFY_ZF(4)
+    if (a.ZPb) { if (pmax != 1) { set_error("the derivative panel is built for P = 1"); return GPFY_EINVAL; } GPFY_ZF(1, true) }
+    else if (pmax == 1) GPFY_ZF(1, false) else if (pmax == 2) GPFY_ZF(2, false) else GPFY_ZF(4, false)
 #undef GPFY_ZF
     GPFY_COUNT_LAUNCH();
     GPFY_LAUNCH_OK();
     return GPFY_OK;
   }
+  if (a.ZPb) { set_error("the legacy forward kernel has no derivative panel"); return GPFY_EINVAL; }
   const int smem = (a.Mp * DIMP + (a.mz ? a.P * a.Mp : 0)) * 8;
 #define GPFY_ZN(PM)                                               \
   {                                                               \
@@ -643,6 +647,39 @@ static int fused_red_sep(const Shape& s) { return (s.Mp / 8) < 2 * ZB_WARPS ? 1 
 static bool fused_bwd_ok(const Shape& s) {
   return s.P == 1 && s.proj == 0 && s.dimp <= 16 && (s.Mp / 8) <= ZB_WARPS * ZB_SLOTS &&
          zb3_smem_bytes(s.Mp, s.dimp, fused_red_sep(s)) <= 227 * 1024 && !debug_option(DBG_NO_FUSED_BWD);
+}
+
+// The general fused backward kernel (zonal_bwd4): P = 1, no projection weights, up to 8 row tiles per compute warp.
+static bool bwd4_ok(const Shape& s) {
+  int RG, NST;
+  return s.P == 1 && s.proj == 0 && (s.Mp / 8 + ZB4_CW - 1) / ZB4_CW <= (s.dimp > 16 ? 4 : 8) && zb4_plan(s.Mp, s.dimp, &RG, &NST) &&
+         !debug_option(DBG_NO_BWD4) && !debug_option(DBG_OLD_FWD);
+}
+
+template <int DIMP>
+static int launch_zonal_bwd4(cudaStream_t st, ZonalBwd4Args& a, int sms) {
+  int RG = 0, NST = 0;
+  if (!zb4_plan(a.Mp, DIMP, &RG, &NST)) { set_error("zonal_bwd4: no row split of Mp = %d fits in shared memory", a.Mp); return GPFY_EUNSUPPORTED; }
+  a.RG = RG; a.G = a.Mp / RG; a.NST = NST; a.HB = zb4_header_ring(a.G, NST);
+  const int smem = zb4_smem_bytes(a.Mp, DIMP, RG, NST);
+  const int tiles = (int)((a.npts + 31) / 32);
+  const unsigned grid = (unsigned)std::min(tiles, sms);
+  const int slots = (a.Mp / 8 + ZB4_CW - 1) / ZB4_CW;
+  if (slots <= 4) {
+    GPFY_TRY(set_smem(zonal_bwd4_kernel<DIMP, 4>, smem));
+    zonal_bwd4_kernel<DIMP, 4><<<grid, ZB4_THREADS, smem, st>>>(a);
+  } else {
+    if constexpr (DIMP <= 16) {
+      GPFY_TRY(set_smem(zonal_bwd4_kernel<DIMP, 8>, smem));
+      zonal_bwd4_kernel<DIMP, 8><<<grid, ZB4_THREADS, smem, st>>>(a);
+    } else {
+      set_error("zonal_bwd4: Mp = %d with ambient dim > 16 is not built", a.Mp);
+      return GPFY_EUNSUPPORTED;
+    }
+  }
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
 }
 
 template <int DIMP>
@@ -898,7 +935,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     // one fused kernel (two CTAs per SM): the zonal values stay in shared memory
     FeaturesArgs fa;
     ZonalArgs& za = fa.z;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
+    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
     za.X = X; za.xcols = apply_to_sphere ? s.d : s.dim; za.apply_to_sphere = apply_to_sphere;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = n;
@@ -912,7 +949,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     ZonalArgs za;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
+    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
     za.X = X + c0 * (apply_to_sphere ? s.d : s.dim);
     za.xcols = apply_to_sphere ? s.d : s.dim;
     za.apply_to_sphere = apply_to_sphere;
@@ -970,19 +1007,21 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
   DegreeTable deg = degree_table(desc);
   RecCoef rc = make_rec_coef(desc->alpha);
 
-  const bool fused = fused_bwd_ok(s);                                  // zonal_bwd2: dT stays on chip, dVhat fused
+  const bool fused = fused_bwd_ok(s);                                  // zonal_bwd3: dT stays on chip, dVhat fused
   const bool fuse_lik = fused && desc->likelihood == GPFY_LIK_GAUSSIAN;  // + psi / likelihood fused (no GEMM psi epilogue)
+  const bool bwd4 = !fused && bwd4_ok(s);                              // zonal_bwd4: C + derivative panel, any Mp / dim
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
+    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
     za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
     if (fuse_lik) { za.Yg = Y + c0; za.s2g = sigma2; za.wq = ws + p.o_wq; za.wp = ws + p.o_wp; za.cq = ws + p.o_cq; }
+    za.ZPb = bwd4 ? ws + p.o_dT : nullptr;   // the derivative panel takes the place of the legacy path's dT buffer
     {
       GPFY_TIMED(TK_ZONAL_FWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
@@ -996,7 +1035,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       g.C = ws + p.o_C + (int64_t)q * Mp * p.nc; g.ldc = p.nc;
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = fuse_lik ? nullptr : ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
-      g.c_blocked = fused ? 1 : 0;  // tile-contiguous, pre-swizzled C for the fused backward kernel
+      g.c_blocked = (fused || bwd4) ? 1 : 0;  // tile-contiguous, pre-swizzled C for the fused backward kernels
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
@@ -1026,6 +1065,13 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       zb3_setup(&zb, desc->alpha, deg, s.M, Mp);
       GPFY_TIMED(TK_ZONAL_BWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd3<DIMP>(st, zb, fuse_lik, p.sms)));
+    } else if (bwd4) {
+      ZonalBwd4Args zb;
+      zb.C = ws + p.o_C; zb.ZP = ws + p.o_dT; zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
+      zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p; zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.npts = npts;
+      zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.dVpart = ws + p.o_dVpart;
+      GPFY_TIMED(TK_ZONAL_BWD, st);
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd4<DIMP>(st, zb, p.sms)));
     } else {
       ZonalBwdArgs zb;
       zb.C = ws + p.o_C; zb.dT = ws + p.o_dT; zb.ldz = p.nc; zb.c_stride = (int64_t)Mp * p.nc;
@@ -1053,7 +1099,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       GPFY_K(syrk_dmma_kernel, p.nblk * p.KS, SYRK_THREADS, SYRK_SMEM, st, sa);
     }
 
-    if (!fused) {
+    if (!fused && !bwd4) {
       DvhatArgs da;
       da.dT = ws + p.o_dT; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
       da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
@@ -1192,7 +1238,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
-    za.Yg = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
+    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;

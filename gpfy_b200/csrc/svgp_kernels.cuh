@@ -40,6 +40,7 @@ struct ZonalArgs {
   double* wq;           // [ldz] q r^2
   double* wp;           // [ldz] p r
   double* cq;           // [ldz] 2 q r^2
+  double* ZPb;          // [tiles][Mp][32] blocked + swizzled derivative panel d/dt C_l^alpha(t) for zonal_bwd4, or null
   DegreeTable deg;
   RecCoef rc;
 };
@@ -754,15 +755,18 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
   double* gp = a.Gpart + ((int64_t)ks * a.nblk + blk) * (SYRK_B * SYRK_B);
   if (!diag) {
     double acc[3][6][2];
+    bool ract[3];   // sub-tiles whose rows lie beyond Mp (a partial last block row) are skipped by every warp alike
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r) {
+      ract[r] = (bi * SYRK_B + r * 32 + wm * 8) < a.Mp;
 #pragma unroll
       for (int c = 0; c < 6; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+    }
     for (int kb = 0; kb < kt; ++kb) {
       const int st = kb % SYRK_STAGES;
       mbar_wait(&bar_full[st], (kb / SYRK_STAGES) & 1);
       const double* base = smem + st * SYRK_STAGE_DBL;
-      const double* zi = base + (wm * 24 + g) * SYRK_ZS + t4;
+      const double* zi = base + (wm * 8 + g) * SYRK_ZS + t4;   // sub-tile r = rows r * 32 + wm * 8 (interleaved, see gemm.cu)
       const double* zj = base + SYRK_B * SYRK_ZS + (wn * 48 + g) * SYRK_ZS + t4;
       const double* wqs = base + 2 * SYRK_B * SYRK_ZS;
 #pragma unroll
@@ -770,13 +774,15 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
         double af[3], bf[6];
         const double w = wqs[k4 * 4 + t4];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) af[r] = zi[r * 8 * SYRK_ZS + k4 * 4];
+        for (int r = 0; r < 3; ++r) af[r] = zi[r * 32 * SYRK_ZS + k4 * 4];
 #pragma unroll
         for (int c = 0; c < 6; ++c) bf[c] = zj[c * 8 * SYRK_ZS + k4 * 4] * w;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
+          if (ract[r]) {
 #pragma unroll
-          for (int c = 0; c < 6; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
+            for (int c = 0; c < 6; ++c) dmma884(acc[r][c][0], acc[r][c][1], af[r], bf[c]);
+          }
         if (k4 == 0) produce();
       }
       __syncwarp();
@@ -784,7 +790,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int row = wm * 24 + r * 8 + g;
+      const int row = r * 32 + wm * 8 + g;
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         const int col = wn * 48 + c * 8 + 2 * t4;

@@ -20,6 +20,9 @@ namespace gpfy {
 struct MonicTab {
   double beta[GPFY_MAX_DEGREES + 2];
   double lead[GPFY_MAX_DEGREES + 2];
+  // d/dt C_l^lam = 2 sum_{j = l-1, l-3, ... >= 0} (j + lam) C_j^lam = sum_j dco[j] p_j   (equivalent to 2 lam C_{l-1}^{lam+1},
+  // gegenbauer.py:73-81, but on the polynomials the lam-recurrence passes through anyway; all coefficients positive)
+  double dco[GPFY_MAX_DEGREES + 2];
 };
 
 static inline MonicTab make_monic(double lam) {
@@ -32,6 +35,7 @@ static inline MonicTab make_monic(double lam) {
     m.lead[k] = d1 * m.lead[k - 1];
     m.beta[k] = m.lead[k] != 0.0 ? d2 * m.lead[k - 2] / m.lead[k] : 0.0;
   }
+  for (int k = 0; k < GPFY_MAX_DEGREES + 2; ++k) m.dco[k] = 2.0 * (k + lam) * m.lead[k];
   return m;
 }
 
@@ -76,6 +80,74 @@ __device__ __forceinline__ void monic_uniform(const double* beta, int l, const d
       p2[u] = a[u];
       p1[u] = b[u];
       p[u] = fma(t[u], b[u], -b0 * a[u]);
+    }
+  }
+}
+
+// monic_uniform plus the derivative zp = d/dt C_l^lam(t) = sum over j = l-1, l-3, ... of dco[j] p_j (see MonicTab::dco).
+template <int NV>
+__device__ __forceinline__ void monic_uniform_d(const double* beta, const double* dco, int l, const double (&t)[NV], double (&p)[NV],
+                                                double (&zp)[NV]) {
+  if (l == 1) {
+#pragma unroll
+    for (int u = 0; u < NV; ++u) { p[u] = t[u]; zp[u] = dco[0]; }
+    return;
+  }
+  const bool odd = l & 1;
+  double a[NV], b[NV];
+  {
+    const double c0 = dco[0], c1 = dco[1];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) { a[u] = 1.0; b[u] = t[u]; zp[u] = odd ? c0 : c1 * t[u]; }
+  }
+  const int nd = (l - 2 - (l & 1)) >> 1;
+  double b0 = beta[2], b1 = beta[3];
+#pragma unroll 1
+  for (int j = 0; j < nd; ++j) {
+    const double nb0 = beta[2 * j + 4], nb1 = beta[2 * j + 5];
+    const double dc = dco[2 * j + 2 + (odd ? 0 : 1)];   // odd l collects the even polynomials (a), even l the odd ones (b)
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      a[u] = fma(t[u], b[u], -b0 * a[u]);
+      b[u] = fma(t[u], a[u], -b1 * b[u]);
+      zp[u] = fma(dc, odd ? a[u] : b[u], zp[u]);
+    }
+    b0 = nb0;
+    b1 = nb1;
+  }
+  if (odd) {   // (b0, b1) = (beta[l - 1], beta[l]):  p_{l-1} joins the derivative sum
+    const double dc = dco[l - 1];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const double p1 = fma(t[u], b[u], -b0 * a[u]);
+      p[u] = fma(t[u], p1, -b1 * b[u]);
+      zp[u] = fma(dc, p1, zp[u]);
+    }
+  } else {     // (b0, b1) = (beta[l], beta[l + 1]);  b = p_{l-1} is already in the sum
+#pragma unroll
+    for (int u = 0; u < NV; ++u) p[u] = fma(t[u], b[u], -b0 * a[u]);
+  }
+}
+
+// monic_mixed plus the derivative (per-lane degree l; l <= 0 gives zp = 0)
+template <int NV>
+__device__ __forceinline__ void monic_mixed_d(const double* beta, const double* dco, int l, int lmax, const double (&t)[NV],
+                                              double (&p)[NV], double (&zp)[NV]) {
+  double p1[NV];
+  const double z0 = l >= 1 ? ((l & 1) ? dco[0] : 0.0) : 0.0, z1 = (l >= 2 && !(l & 1)) ? dco[1] : 0.0;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) { p1[u] = 1.0; p[u] = t[u]; zp[u] = fma(z1, t[u], z0); }
+#pragma unroll 1
+  for (int k = 2; k <= lmax; ++k) {
+    const double b = beta[k];
+    const bool on = k <= l;
+    const double dc = (k < l && !((l - 1 - k) & 1)) ? dco[k] : 0.0;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const double pn = fma(t[u], p[u], -b * p1[u]);
+      p1[u] = on ? p[u] : p1[u];
+      p[u] = on ? pn : p[u];
+      zp[u] = fma(dc, pn, zp[u]);
     }
   }
 }

@@ -16,7 +16,7 @@ struct ZonalFwd2Args {
 };
 
 static inline int zf2_smem_bytes(int Mp, int dimp, int P, bool with_mz, int pmax) {
-  int dbl = Mp * dimp + (with_mz ? P * Mp : 0) + 2 * 32 * dimp + 2 * 8 * pmax * 32 + 2 * 32 + 2 * GPFY_MAX_DEGREES + 8;
+  int dbl = Mp * dimp + (with_mz ? P * Mp : 0) + 2 * 32 * dimp + 2 * 8 * pmax * 32 + 2 * 32 + 3 * GPFY_MAX_DEGREES + 10;
   return dbl * 8 + Mp * 4 + 16;
 }
 
@@ -24,7 +24,8 @@ static inline int zf2_smem_bytes(int Mp, int dimp, int P, bool with_mz, int pmax
 // blockIdx, blockIdx + gridDim, ...  Per tile there is ONE CTA barrier: warp 0 (helper) loads and projects the NEXT
 // tile's points while the seven compute warps work on the current one (coordinates and the mu2 . z partial sums are double-buffered in
 // shared memory), and finishes the previous tile's per-point outputs right after the barrier.
-template <int DIMP, int PMAX>
+// ZPOUT: also store the derivative panel (blocked like the GEMM's C) for zonal_bwd4; the headline path leaves it off.
+template <int DIMP, int PMAX, bool ZPOUT>
 __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constant__ ZonalFwd2Args args) {
   constexpr int KS = DIMP / 4;
   const ZonalArgs& a = args.z;
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
   double* rs = red + 2 * 8 * PMAX * 32;                // [2][32] radii of the tile's points
   double* leads = rs + 2 * 32;                         // [MAX_DEGREES + 2]
   double* betas = leads + GPFY_MAX_DEGREES + 2;        // [MAX_DEGREES + 6] recurrence coefficients (read ahead)
-  int* rowdeg = reinterpret_cast<int*>(betas + GPFY_MAX_DEGREES + 6);  // [Mp]
+  double* dcos = betas + GPFY_MAX_DEGREES + 6;         // [MAX_DEGREES + 2] derivative coefficients (MonicTab::dco)
+  int* rowdeg = reinterpret_cast<int*>(dcos + GPFY_MAX_DEGREES + 2);  // [Mp]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
     }
     rowdeg[i] = l;
   }
-  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) leads[i] = args.mt.lead[i];
+  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) { leads[i] = args.mt.lead[i]; dcos[i] = args.mt.dco[i]; }
   for (int i = tid; i < GPFY_MAX_DEGREES + 6; i += 256) betas[i] = i < GPFY_MAX_DEGREES + 2 ? args.mt.beta[i] : 0.0;
 
   // warp 0, lane = point: onto the sphere (spherical.py:214-249); coordinates to shared memory, r and xhat to HBM
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
   stage_params_tma(vs, a.vhat_p, (unsigned)((Mp * DIMP + (a.mz ? a.P * Mp : 0)) * 8), &bar);
   __syncthreads();
 
-  const int ntile = (a.M + 7) / 8;
+  const int ntile = ZPOUT ? Mp / 8 : (a.M + 7) / 8;   // the derivative panel is written for the padding rows too (zeros)
   for (int it = 0; it < n_my; ++it) {
     if (warp == 0) {  // helper warp: the next tile's points while the seven compute warps work, then this tile's outputs
       if (it + 1 < n_my) project_tile(it + 1);
@@ -144,18 +146,40 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
       }
       const int l = rowdeg[row];
       const int lo = rowdeg[rt * 8], hi = rowdeg[rt * 8 + 7];
-      double p[8], p1[8], p2[8], z[8];
-      if (lo == hi && lo >= 1) {
-        monic_uniform<8>(betas, lo, t, p, p1, p2);
-        const double ld = leads[lo];
+      double p[8], z[8];
+      if constexpr (ZPOUT) {
+        double zp[8];
+        if (lo == hi && lo >= 1) {
+          monic_uniform_d<8>(betas, dcos, lo, t, p, zp);
+          const double ld = leads[lo];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
+          for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
+        } else {
+          const int lmax = __reduce_max_sync(0xffffffffu, l);
+          monic_mixed_d<8>(betas, dcos, l, lmax, t, p, zp);
+          const double ld = l >= 1 ? leads[l] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
+        }
+        double* zrow = a.ZPb + ((p0 >> 5) * (int64_t)Mp + row) * 32;
+        const int swz = (row & 3) << 2;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<double2*>(zrow + ((8 * nt + 2 * t4) ^ swz)) = make_double2(zp[2 * nt], zp[2 * nt + 1]);
       } else {
-        const int lmax = __reduce_max_sync(0xffffffffu, l);
-        monic_mixed<8>(betas, l, lmax, t, p, p1, p2);
-        const double ld = l >= 1 ? leads[l] : 0.0;
+        double p1[8], p2[8];
+        if (lo == hi && lo >= 1) {
+          monic_uniform<8>(betas, lo, t, p, p1, p2);
+          const double ld = leads[lo];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
+          for (int u = 0; u < 8; ++u) z[u] = ld * p[u];
+        } else {
+          const int lmax = __reduce_max_sync(0xffffffffu, l);
+          monic_mixed<8>(betas, l, lmax, t, p, p1, p2);
+          const double ld = l >= 1 ? leads[l] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
+        }
       }
       if (row < a.M) {
         if (!(args.dbg & 1))

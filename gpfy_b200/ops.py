@@ -139,21 +139,19 @@ class HotPath:
         return max(1, min(int(n), int(rows.value)))
 
     @staticmethod
-    def slab_bounds(n, cap):
+    def slab_bounds(n, cap, unit=1024):
         """Row boundaries of the streamed slabs.  Nothing can overlap the copy of the FIRST slab, so the slabs ramp up:
-        cap / 16, cap / 4, then equal slabs of at most `cap` rows (one internal chunk each).  With slab = chunk = half a
-        rank's shard (8 GPUs, N = 10 M) half of the H2D time used to be exposed; now it is 1/32 of it."""
-        n, cap = int(n), int(cap)
+        about cap / 16, cap / 4, then slabs of `cap` rows (one internal chunk each).  With slab = chunk = half a rank's
+        shard (8 GPUs, N = 10 M) half of the H2D time used to be exposed; now it is 1/32 of it.  Every slab but the last
+        is a multiple of `unit` = 192 * SMs rows, a whole number of GEMM tile rounds per SM (no tail wave)."""
+        n, cap, unit = int(n), int(cap), max(1, int(unit))
         bounds = [0]
         for frac in (16, 4):
-            step = max(1024, cap // frac // 1024 * 1024)
-            if bounds[-1] + step + cap // 4 < n:
+            step = max(unit, cap // frac // unit * unit)
+            if bounds[-1] + step + cap // 4 < n and step <= cap:
                 bounds.append(bounds[-1] + step)
-        rem = n - bounds[-1]
-        k = max(1, -(-rem // cap))
-        per = min(cap, -(-(-(-rem // k)) // 1024) * 1024)
         while bounds[-1] < n:
-            bounds.append(min(n, bounds[-1] + per))
+            bounds.append(min(n, bounds[-1] + cap))
         return bounds
 
     def elbo_valgrad_host(self, X_host, Y_host, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out_host=None, reduce=None):
@@ -172,7 +170,7 @@ class HotPath:
         if out_host is None:
             out_host = torch.empty((self.layout.total,), dtype=torch.float64).pin_memory()
         cap = self.slab_rows(n)
-        bounds = self.slab_bounds(n, cap)
+        bounds = self.slab_bounds(n, cap, 192 * torch.cuda.get_device_properties(self.device).multi_processor_count)
         ws = self.workspace(cap, _lib.OP_ELBO)
         st = self._stream_state(cap)
         dptr = ctypes.byref(self.desc)
@@ -340,12 +338,14 @@ class HotPath:
         return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
 
 
-DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3}
+DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4}
 
 
 def debug_option(name, value):
     """Development switch of the library (tests / tools): `chunk_mult` = rows per internal chunk as a multiple of
-    192 * SMs (0 = default); `old_fwd`, `no_fused_bwd`, `old_features` = 1 route a call through the general kernels."""
+    192 * SMs (0 = default); `no_fused_bwd` = 1 sends the headline shapes through the general fused backward kernel
+    (zonal_bwd4), `no_bwd4` = 1 on top of it through the legacy one-point-per-lane kernels; `old_fwd`, `old_features` = 1
+    select the legacy forward / two-kernel feature path."""
     _lib.check(_lib.load().gpfy_debug_set_option(DEBUG_OPTIONS[name], int(value)))
 
 

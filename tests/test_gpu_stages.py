@@ -266,9 +266,11 @@ def test_inducing_basis_on_device_matches_reference_and_autograd(name):
 
 
 def test_fused_and_general_kernel_paths_agree_on_the_headline_shape():
-    """Two independent implementations of the same step: the tensor-core zonal forward + fused backward (P = 1,
-    ambient dim <= 16, Mp <= 288) against the general one-point-per-lane kernels that serve every other shape,
-    selected by the library's A/B switches.  Same inputs -> same packed value and gradients, features and predictions."""
+    """Three independent implementations of the same step: the headline kernels (tensor-core zonal forward + zonal_bwd3,
+    P = 1, ambient dim <= 16, Mp <= 288), the general fused backward (zonal_bwd4: C + derivative panel, any Mp / dim) and
+    the legacy one-point-per-lane kernels that serve P > 1 and projection weights, selected by the library's development
+    switches.  Same inputs -> same packed value and gradients, features and predictions."""
+    from gpfy_b200 import ops
     prob = _problem(20_011)
     hp, args = prob["hot"], prob["args"]
     pred_args = [args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)]
@@ -276,21 +278,26 @@ def test_fused_and_general_kernel_paths_agree_on_the_headline_shape():
     fused = hp.elbo_valgrad_packed(*args).clone()
     fmu, fvar = (t.clone() for t in hp.predict_diag(*pred_args))
     A = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0].clone()
-    from gpfy_b200 import ops
+    all_opts = ("no_fused_bwd", "no_bwd4", "old_fwd", "old_features")
+    lay = hp.layout
+    names = ("data_term", "d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2")
+
+    def same(x, y, tol):
+        for name in names:
+            lo = getattr(lay, name)
+            nxt = min([getattr(lay, n) for n in names[1:] + ("total",) if getattr(lay, n) > lo])
+            assert rel_err(x[lo:nxt].cpu().numpy(), y[lo:nxt].cpu().numpy()) < tol, name
+
     try:
-        for k in ("no_fused_bwd", "old_fwd", "old_features"):
+        ops.debug_option("no_fused_bwd", 1)                      # -> zonal_bwd4 (+ lik_point + GEMM psi epilogue)
+        same(hp.elbo_valgrad_packed(*args), fused, 1e-11)
+        for k in all_opts:                                       # -> legacy kernels everywhere
             ops.debug_option(k, 1)
-        general = hp.elbo_valgrad_packed(*args)
+        same(hp.elbo_valgrad_packed(*args), fused, 1e-11)
         gmu, gvar = hp.predict_diag(*pred_args)
         gA = hp.features(args[0], args[6], args[7], w=args[2], b=args[3], degree_scale=ds, mul_r=True)[0]
     finally:
-        for k in ("no_fused_bwd", "old_fwd", "old_features"):
+        for k in all_opts:
             ops.debug_option(k, 0)
-    lay = hp.layout
-    for name in ("data_term", "d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2"):
-        lo = getattr(lay, name)
-        nxt = min([getattr(lay, n) for n in ("d_mu", "d_sigma", "d_eig", "d_vhat", "d_lcat", "d_w", "d_b", "d_v", "d_sigma2", "total")
-                   if getattr(lay, n) > lo])
-        assert rel_err(fused[lo:nxt].cpu().numpy(), general[lo:nxt].cpu().numpy()) < 1e-11, name
     assert rel_err(fmu.cpu().numpy(), gmu.cpu().numpy()) < 1e-12 and rel_err(fvar.cpu().numpy(), gvar.cpu().numpy()) < 1e-12
     assert rel_err(A.cpu().numpy(), gA.cpu().numpy()) < 1e-12

@@ -52,8 +52,10 @@ def test_streamed_slab_bounds_ramp_and_cover():
     from gpfy_b200.ops import HotPath
     for n, cap in ((10_000_000, 909_312), (1_250_000, 625_152), (1, 1), (31, 128), (1000, 1024), (150_001, 150_016),
                    (2_000_000, 681_984), (909_312, 909_312), (909_313, 909_312)):
-        b = HotPath.slab_bounds(n, cap)
+        unit = 192 * 148
+        b = HotPath.slab_bounds(n, cap, unit)
         sizes = [y - x for x, y in zip(b[:-1], b[1:])]
         assert b[0] == 0 and b[-1] == n and all(0 < s <= cap for s in sizes), (n, cap, b)
+        assert all(s % unit == 0 for s in sizes[:-1]) or len(sizes) == 1
         if n > 2 * cap:
-            assert sizes[0] <= cap // 16 and sizes[1] <= cap // 4
+            assert sizes[0] <= max(unit, cap // 16) and sizes[1] <= cap // 4
