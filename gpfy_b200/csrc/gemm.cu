@@ -23,7 +23,8 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
   const int m_tiles = (a.m + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (a.n + GEMM_BN - 1) / GEMM_BN;
   const int tiles = m_tiles * n_tiles;
-  const int kt_full = a.k / GEMM_BK;
+  const int m_eff = a.m_eff > 0 ? a.m_eff : a.m;
+  const int kt_full = (a.k_eff > 0 ? a.k_eff : a.k) / GEMM_BK;
   if ((int)blockIdx.x >= tiles) return;
   // lower_k: A is lower triangular in 96-row blocks, so row tile t only needs k < 96 (t + 1)
   auto kt_of = [&](int tile) {
@@ -103,7 +104,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
   bool active = (row0 + wm * 8) < a.m && (col0 + wn * 64) < a.n;
   bool ract[3];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) ract[r] = (row0 + r * 32 + wm * 8) < a.m;
+  for (int r = 0; r < 3; ++r) ract[r] = (row0 + r * 32 + wm * 8) < m_eff;
   for (int it = 0; it < total; ++it) {
     const int st = it % GEMM_STAGES;
     if (c_kb == 0) {
@@ -190,7 +191,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
       col0 = (c_tile / m_tiles) * GEMM_BN;
       active = (row0 + wm * 8) < a.m && (col0 + wn * 64) < a.n;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) ract[r] = (row0 + r * 32 + wm * 8) < a.m;
+      for (int r = 0; r < 3; ++r) ract[r] = (row0 + r * 32 + wm * 8) < m_eff;
     }
   }
 }
@@ -198,6 +199,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs a) { gemm_body<0>(a); }
 
 int launch_gemm(cudaStream_t stream, const GemmArgs& a, int num_sms) {
+  if ((a.m_eff & 7) || (a.k_eff % GEMM_BK) || a.m_eff > a.m || a.k_eff > a.k) { set_error("launch_gemm: m_eff must be a multiple of 8, k_eff of 16"); return GPFY_EINVAL; }
   if (a.k % GEMM_BK != 0 || (a.n & 1) || (a.lda & 1) || (a.ldb & 1) || (a.ldc & 1)) {
     set_error("launch_gemm: k=%d must be a multiple of 16 and n=%d, lda, ldb, ldc even", a.k, a.n);
     return GPFY_EINVAL;

@@ -38,6 +38,9 @@ struct GemmArgs {
   // block is zero), so row tile t stops its k loop at 96 (t + 1): a third fewer k-steps for three row tiles.  Used by
   // predict_diag, where only psi_n = z_n^T W z_n is wanted and W can be folded onto its lower triangle.
   int lower_k = 0;
+  // Rows of A at and beyond m_eff and rows of B (k) at and beyond k_eff are known to be zero (the padding of M up to the
+  // next multiple of 32): their 8-row sub-tiles / 16-deep k-steps are skipped (C still receives the zeros).  0 = m / k.
+  int m_eff = 0, k_eff = 0;
 };
 
 static inline int gemm_psi_slabs(int m) { return ((m + 95) / 96) * 4; }

@@ -241,22 +241,25 @@ __global__ void gemv_kernel(const double* A, int Mp, int trans, const double* x,
 }
 
 // Gz [Mp, Mp] (full symmetric) = sum_ks Gpart blocks;  bz [Mp] = sum_ks bzpart
-__global__ void reduce_g_kernel(const double* Gpart, const double* bzpart, double* Gz, double* bz, int Mp, int nb, int nblk,
-                                int KS) {
+__global__ void reduce_g_kernel(const double* Gpart, const double* bzpart, double* Gz, double* bz, int Mp, SyrkSplit sp) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < (int64_t)Mp * Mp) {
     const int i = (int)(e / Mp), j = (int)(e % Mp);
     int bi = i / SYRK_B, bj = j / SYRK_B, ri = i % SYRK_B, rj = j % SYRK_B;
     // lower blocks only; inside a diagonal block only the lower half is guaranteed (upper warp tiles are skipped)
     if (bi < bj || (bi == bj && ri < rj)) { int t = bi; bi = bj; bj = t; t = ri; ri = rj; rj = t; }
-    const int blk = bi * (bi + 1) / 2 + bj;
+    const int KS = sp.ks[sp.type(bi, bj)];
+    const double* src = Gpart + (int64_t)sp.gslot(bi, bj) * (SYRK_B * SYRK_B) + ri * SYRK_B + rj;
     double s = 0.0;
-    for (int ks = 0; ks < KS; ++ks) s += Gpart[((int64_t)ks * nblk + blk) * (SYRK_B * SYRK_B) + ri * SYRK_B + rj];
+    for (int ks = 0; ks < KS; ++ks) s += src[(int64_t)ks * (SYRK_B * SYRK_B)];
     Gz[e] = s;
   }
   if (e < Mp) {
+    const int bi = (int)(e / SYRK_B);
+    const int KS = sp.ks[sp.type(bi, bi)];
+    const double* src = bzpart + (int64_t)sp.bslot(bi) * SYRK_B + (e % SYRK_B);
     double s = 0.0;
-    for (int ks = 0; ks < KS; ++ks) s += bzpart[(int64_t)ks * (nb * SYRK_B) + e];
+    for (int ks = 0; ks < KS; ++ks) s += src[(int64_t)ks * SYRK_B];
     bz[e] = s;
   }
 }
@@ -432,7 +435,8 @@ struct Plan {
   Shape s;
   int sms;
   int64_t nc;       // points per chunk (multiple of 128)
-  int nb, nblk, KS; // SYRK blocks / splits
+  int nb;           // SYRK row blocks
+  SyrkSplit split;  // per block type: how many CTAs share a chunk's points
   int KSV;          // dVhat splits
   int64_t nblocks_c; // lik_bwd blocks per full chunk
   int npart;
@@ -474,8 +478,17 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->sms = device_sms();
   p->nc = choose_chunk(p->sms, n, s);
   p->nb = (s.Mp + SYRK_B - 1) / SYRK_B;
-  p->nblk = p->nb * (p->nb + 1) / 2;
-  p->KS = std::max(1, (2 * p->sms) / p->nblk);
+  {
+    SyrkSplit& sp = p->split;
+    sp.nb = p->nb;
+    sp.last_rows = s.Mp - (p->nb - 1) * SYRK_B;
+    const int noff = p->nb * (p->nb - 1) / 2, slots = 2 * p->sms;
+    // One uniform split count.  Measured (r02c): splits proportional to the tensor-core tile count of each block type
+    // (12 diagonal / 18 off-diagonal / 12 partial) made the SYRK 5 - 10 % SLOWER at Mp = 352 and 256 - the kernel is not
+    // bound by its DMMA count alone - so the per-type table stays at one value.
+    (void)noff;
+    for (int t = 0; t < 4; ++t) sp.ks[t] = std::max(1, slots / (p->nb * (p->nb + 1) / 2));
+  }
   p->KSV = std::max(p->sms, (8 * p->sms) / (s.Mp / 32));  // dVhat partial slots: >= one per persistent CTA of the fused backward kernel
   p->nblocks_c = p->nc / 32;
   p->npsi = gemm_psi_slabs(s.Mp);
@@ -503,8 +516,8 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->o_dd = take(Mp);
   p->o_partials = take(p->nblocks_c * p->npart);
   if (op == GPFY_OP_ELBO) {
-    p->o_Gpart = take((int64_t)s.P * p->KS * p->nblk * SYRK_B * SYRK_B);
-    p->o_bzpart = take((int64_t)s.P * p->KS * p->nb * SYRK_B);
+    p->o_Gpart = take((int64_t)s.P * p->split.total() * SYRK_B * SYRK_B);
+    p->o_bzpart = take((int64_t)s.P * p->split.bslot(p->nb) * SYRK_B);
     p->o_dVpart = take((int64_t)p->KSV * Mp * ((s.dimp + 7) / 8) * 8);
   } else {
     p->o_Gpart = p->o_bzpart = p->o_dVpart = o;
@@ -1036,6 +1049,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = fuse_lik ? nullptr : ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       g.c_blocked = (fused || bwd4) ? 1 : 0;  // tile-contiguous, pre-swizzled C for the fused backward kernels
+      g.m_eff = round_up(s.M, 8); g.k_eff = round_up(s.M, GEMM_BK);   // rows / columns M..Mp of W2 and rows M.. of Z are zero
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
 
@@ -1090,13 +1104,12 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       SyrkArgs sa;
       sa.Z = ws + p.o_Z; sa.ldz = p.nc; sa.Mp = Mp; sa.npts = npts;
       sa.wq = ws + p.o_wq + (int64_t)q * p.nc; sa.wp = ws + p.o_wp + (int64_t)q * p.nc;
-      sa.Gpart = ws + p.o_Gpart + (int64_t)q * p.KS * p.nblk * SYRK_B * SYRK_B;
-      sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.KS * p.nb * SYRK_B;
-      sa.nb = p.nb; sa.nblk = p.nblk; sa.KS = p.KS;
-      sa.range = round_up64((p.nc + p.KS - 1) / p.KS, SYRK_BK);
+      sa.Gpart = ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B;
+      sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B;
+      sa.split = p.split; sa.chunk = p.nc;
       sa.accumulate = 1;
       GPFY_TRY(device_configure_once(DEV_CFG_SYRK, (const void*)syrk_dmma_kernel, SYRK_SMEM));
-      GPFY_K(syrk_dmma_kernel, p.nblk * p.KS, SYRK_THREADS, SYRK_SMEM, st, sa);
+      GPFY_K(syrk_dmma_kernel, p.split.total(), SYRK_THREADS, SYRK_SMEM, st, sa);
     }
 
     if (!fused && !bwd4) {
@@ -1129,8 +1142,8 @@ int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity
   for (int q = 0; q < s.P; ++q) {
     double* Gz = ws + p.o_Gz;
     double* bz = ws + p.o_bz + (int64_t)q * Mp;
-    GPFY_K(reduce_g_kernel, sqg, 256, 0, st, ws + p.o_Gpart + (int64_t)q * p.KS * p.nblk * SYRK_B * SYRK_B,
-           ws + p.o_bzpart + (int64_t)q * p.KS * p.nb * SYRK_B, Gz, bz, Mp, p.nb, p.nblk, p.KS);
+    GPFY_K(reduce_g_kernel, sqg, 256, 0, st, ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B,
+           ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B, Gz, bz, Mp, p.split);
     GPFY_TRY(gemm_sq(st, ws + p.o_E, Gz, ws + p.o_tmp1, Mp, 1.0, 0.0, p.sms));             // T1 = E Gz
     GPFY_TRY(gemm_sq(st, ws + p.o_tmp1, ws + p.o_ET, ws + p.o_tmp2, Mp, 1.0, 0.0, p.sms));  // dW0 = T1 E^T
     double* dsig = packed + lay.d_sigma + (int64_t)q * s.M * s.M;
@@ -1251,6 +1264,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = nullptr; g.ldc = p.nc;  // only psi = z . (W2 z) is needed (model.py:136): the product is never stored
       g.lower_k = 1;
+      g.m_eff = round_up(s.M, 8); g.k_eff = round_up(s.M, GEMM_BK);
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));
@@ -1326,6 +1340,7 @@ int gpfy_project_q(void* stream, const GpfyDesc* desc, int64_t n, const double* 
       g.B = ws + p.o_Z; g.ldb = p.nc;
       g.C = nullptr; g.ldc = p.nc;  // only psi = z . (W2 z) is needed (model.py:136): the product is never stored
       g.lower_k = 1;
+      g.m_eff = round_up(s.M, 8); g.k_eff = round_up(s.M, GEMM_BK);
       g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
       g.psi_out = ws + p.o_psi + (int64_t)q * p.npsi * p.nc; g.ld_psi = p.nc;
       GPFY_TRY(launch_gemm(st, g, p.sms));

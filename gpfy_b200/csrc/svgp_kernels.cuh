@@ -639,6 +639,33 @@ constexpr int SYRK_ZS = SYRK_BK + 4;
 constexpr int SYRK_STAGE_DBL = 2 * SYRK_B * SYRK_ZS + 2 * SYRK_BK;
 constexpr int SYRK_SMEM = SYRK_STAGES * SYRK_STAGE_DBL * 8;
 
+// How the point range of a chunk is split among the CTAs of each 96 x 96 block.  A diagonal block costs a CTA 12 tensor-
+// core tiles per warp and k-step, a full off-diagonal one 18, an off-diagonal block of a partial last block row (Mp = 352
+// or 256: 64 of 96 rows) 12: every block TYPE gets its own number of splits, proportional to that cost, so all CTAs carry
+// about the same work whatever the mix of types (with one uniform split count 4 diagonal + 6 off-diagonal blocks left a
+// fifth of the SMs with two full off-diagonal CTAs: +22 % on the SYRK at 13 degrees).
+struct SyrkSplit {
+  int nb;        // row blocks
+  int last_rows; // valid rows of the last block row (96 when Mp is a multiple of 96)
+  int ks[4];     // splits of a block of type 0 diagonal, 1 off-diagonal, 2 off-diagonal in a partial last row, 3 partial diagonal
+  __host__ __device__ int type(int bi, int bj) const {
+    const bool part = bi == nb - 1 && last_rows < 96;
+    return bi == bj ? (part ? 3 : 0) : (part ? 2 : 1);
+  }
+  __host__ __device__ int bslot(int bi) const {   // first bz slot of diagonal block bi (= its first G slot)
+    int o = 0;
+    for (int b = 0; b < bi; ++b) o += ks[type(b, b)];
+    return o;
+  }
+  __host__ __device__ int gslot(int bi, int bj) const {   // first G slot of block (bi, bj): diagonal blocks, then (1,0), (2,0), (2,1), ...
+    if (bi == bj) return bslot(bi);
+    int o = bslot(nb);
+    for (int i = 1; i < bi; ++i) o += i * ks[type(i, 0)];
+    return o + bj * ks[type(bi, 0)];
+  }
+  __host__ __device__ int total() const { return gslot(nb, 0); }
+};
+
 struct SyrkArgs {
   const double* Z;
   int64_t ldz;
@@ -646,10 +673,10 @@ struct SyrkArgs {
   int64_t npts;
   const double* wq;   // [npts]
   const double* wp;   // [npts]
-  double* Gpart;      // [KS][nblk][96*96]
-  double* bzpart;     // [KS][nb*96]
-  int nb, nblk, KS;
-  int64_t range;      // points per split (multiple of 16)
+  double* Gpart;      // [split.total()][96*96]
+  double* bzpart;     // [split.bslot(nb)][96]
+  SyrkSplit split;
+  int64_t chunk;      // rows of a full chunk: block type t covers it in split.ks[t] ranges of ceil(chunk / ks[t]) rows (multiple of 16)
   int accumulate;
 };
 
@@ -688,25 +715,26 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;   // off-diagonal: 4 x 2 warps, warp tile 24 x 48
   const int g = lane >> 2, t4 = lane & 3;
-  // CTA -> (block, split): the nb diagonal blocks first, then the off-diagonal ones
-  int bi, bj, ks;
-  const int ndiag = a.nb * a.KS;
-  if ((int)blockIdx.x < ndiag) {
-    bi = bj = (int)blockIdx.x % a.nb;
-    ks = (int)blockIdx.x / a.nb;
-  } else {
-    const int noff = a.nblk - a.nb;
-    const int j = (int)blockIdx.x - ndiag;
-    int o = j % noff;
-    ks = j / noff;
-    bi = 1;
-    while (o >= bi) { o -= bi; ++bi; }
-    bj = o;
+  // CTA -> (block, split): slots are numbered block by block (SyrkSplit::gslot), the nb diagonal blocks first
+  int bi = 0, bj = 0, ks = (int)blockIdx.x;
+  {
+    const int nb = a.split.nb;
+    bool found = false;
+    for (int b = 0; b < nb && !found; ++b) {
+      const int k = a.split.ks[a.split.type(b, b)];
+      if (ks < k) { bi = bj = b; found = true; } else ks -= k;
+    }
+    for (int i = 1; i < nb && !found; ++i)
+      for (int j = 0; j < i && !found; ++j) {
+        const int k = a.split.ks[a.split.type(i, j)];
+        if (ks < k) { bi = i; bj = j; found = true; } else ks -= k;
+      }
   }
   const bool diag = bi == bj;
-  const int blk = bi * (bi + 1) / 2 + bj;
-  const int64_t p0 = (int64_t)ks * a.range;
-  int64_t p1 = p0 + a.range;
+  const int nks = a.split.ks[a.split.type(bi, bj)];
+  const int64_t range = ((a.chunk + nks - 1) / nks + SYRK_BK - 1) / SYRK_BK * SYRK_BK;
+  const int64_t p0 = (int64_t)ks * range;
+  int64_t p1 = p0 + range;
   if (p1 > a.npts) p1 = a.npts;
   const int kt = p1 > p0 ? (int)((p1 - p0 + SYRK_BK - 1) / SYRK_BK) : 0;
 
@@ -752,7 +780,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
 #pragma unroll
   for (int s = 0; s < SYRK_STAGES - 1; ++s) produce();
 
-  double* gp = a.Gpart + ((int64_t)ks * a.nblk + blk) * (SYRK_B * SYRK_B);
+  double* gp = a.Gpart + (int64_t)(a.split.gslot(bi, bj) + ks) * (SYRK_B * SYRK_B);
   if (!diag) {
     double acc[3][6][2];
     bool ract[3];   // sub-tiles whose rows lie beyond Mp (a partial last block row) are skipped by every warp alike
@@ -829,7 +857,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     if (lane == 0) mbar_arrive(&bar_empty[st]);
   }
   const int ra = warp < 4 ? 11 - warp : 11 - warp, rb = warp < 4 ? -1 : warp - 4;
-  double* bzp = a.bzpart + (int64_t)ks * (a.nb * SYRK_B) + bi * SYRK_B;
+  double* bzp = a.bzpart + (int64_t)(a.split.bslot(bi) + ks) * SYRK_B;
 #pragma unroll
   for (int c = 0; c < 12; ++c) {
     int row, col;

@@ -31,9 +31,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, 
                ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | layout << 61
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout = 2 /* SWIZZLE_128B */) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-         (1ull << 46) | (2ull << 61);   // SWIZZLE_128B
+         (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
@@ -45,8 +45,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 struct Maps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
 
+// A_MN: the MN-major tf32 operand uses the SWIZZLE_128B_BASE32B layout (type 1; 32-byte swizzle chunks, atoms of 4 k-rows x
+// 128 B; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) - "for mn-major tf32 operands, SW128_32B is the only available smem
+// layout" (cutlass sm100_common.inl).  lbo / sbo are passed at run time to try the candidates in one run.
 template <int A_MN>
-__global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ Maps maps, float* D) {
+__global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ Maps maps, float* D, uint32_t a_lbo, uint32_t a_sbo) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* a_hi = (float*)smem;                       // [128 x 32] = 16 KB
@@ -95,8 +98,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ M
           const uint32_t d = tmem + h * NH;
           uint64_t dah, dal;
           if (A_MN) {
-            dah = smem_desc(smem_u32(a_hi) + ks * 1024, 4096, 1024);
-            dal = smem_desc(smem_u32(a_lo) + ks * 1024, 4096, 1024);
+            dah = smem_desc(smem_u32(a_hi) + ks * 1024, a_lbo, a_sbo, 1);
+            dal = smem_desc(smem_u32(a_lo) + ks * 1024, a_lbo, a_sbo, 1);
           } else {
             dah = smem_desc(smem_u32(a_hi) + ks * 32, 16, 1024);
             dal = smem_desc(smem_u32(a_lo) + ks * 32, 16, 1024);
@@ -136,14 +139,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ M
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static CUtensorMap make_map(EncodeFn enc, float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+static CUtensorMap make_map(EncodeFn enc, float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); exit(1); }
   return m;
 }
@@ -176,7 +180,8 @@ int main() {
   CK(cudaMalloc(&dBh, N * K * 4)); CK(cudaMalloc(&dBl, N * K * 4)); CK(cudaMalloc(&dAh, M * K * 4)); CK(cudaMalloc(&dAl, M * K * 4)); CK(cudaMalloc(&dD, M * N * 4));
   CK(cudaMemcpy(dBh, Bh.data(), N * K * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dBl, Bl.data(), N * K * 4, cudaMemcpyHostToDevice));
   const int smem = 32768 + 2 * 36864 + 1024;
-  for (int variant = 0; variant < 2; ++variant) {
+  const uint32_t cand[4][2] = {{0, 0}, {4096, 512}, {512, 4096}, {4096, 1024}};   // (LBO, SBO) candidates of the MN-major operand
+  for (int variant = 0; variant < 4; ++variant) {
     std::vector<double> Ax(M * K);
     if (variant == 0) Ax = A;
     else for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) Ax[k * M + m] = A[m * K + k];   // [k][m]: MN-major
@@ -185,14 +190,14 @@ int main() {
     CK(cudaMemset(dD, 0, M * N * 4));
     Maps maps;
     if (variant == 0) { maps.a_hi = make_map(enc, dAh, K, M, 32, 128); maps.a_lo = make_map(enc, dAl, K, M, 32, 128); }
-    else { maps.a_hi = make_map(enc, dAh, M, K, 32, 32); maps.a_lo = make_map(enc, dAl, M, K, 32, 32); }
+    else { maps.a_hi = make_map(enc, dAh, M, K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); maps.a_lo = make_map(enc, dAl, M, K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); }
     maps.b_hi = make_map(enc, dBh, K, N, 32, 144); maps.b_lo = make_map(enc, dBl, K, N, 32, 144);
     if (variant == 0) {
       CK(cudaFuncSetAttribute(probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      probe_kernel<0><<<1, 128, smem>>>(maps, dD);
+      probe_kernel<0><<<1, 128, smem>>>(maps, dD, 0, 0);
     } else {
       CK(cudaFuncSetAttribute(probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      probe_kernel<1><<<1, 128, smem>>>(maps, dD);
+      probe_kernel<1><<<1, 128, smem>>>(maps, dD, cand[variant][0], cand[variant][1]);
     }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -200,8 +205,9 @@ int main() {
     CK(cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0, maxref = 0; int bad = 0;
     for (int i = 0; i < M * N; ++i) { double e = fabs(D[i] - ref[i]); if (e > maxerr) maxerr = e; if (fabs(ref[i]) > maxref) maxref = fabs(ref[i]); if (e > 1e-4) ++bad; }
-    printf("variant %d (%s): max abs err %.3e, max |ref| %.3e, rel %.3e, entries off by > 1e-4: %d  D[0..3] = %g %g %g %g  ref = %g %g %g %g\n", variant,
-           variant ? "A MN-major" : "A K-major", maxerr, maxref, maxerr / maxref, bad, D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+    printf("variant %d (%s, LBO %u SBO %u): max abs err %.3e, max |ref| %.3e, rel %.3e, entries off by > 1e-4: %d  D[0..3] = %g %g %g %g  ref = %g %g %g %g\n", variant,
+           variant ? "A MN-major" : "A K-major", cand[variant][0], cand[variant][1], maxerr, maxref, maxerr / maxref, bad, D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+    fflush(stdout);
   }
   return 0;
 }
