@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--n", type=float, default=None, help="total rows over all ranks (default: the config's N)")
     ap.add_argument("--T", type=int, default=None, help="phase truncation (default: the config's T)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f64: the reference's precision (headline).  f32: the dense contraction as 3 x TF32 on tcgen05 (GPFY_PREC_TF32X3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the Phi-only / predict_diag / train-step side measurements")
@@ -264,7 +266,7 @@ def run_ours(a):
         dist.init_process_group(backend="nccl", device_id=dev)
     N = int(c["N"])
     prob = synthetic.headline_problem(N, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev,
-                                      rank=rank, world=world)
+                                      rank=rank, world=world, precision=a.dtype)
     hp, args = prob["hot"], prob["args"]
     X, Y = args[0], args[1]
     n_local = X.shape[0]
@@ -391,14 +393,26 @@ def run_ours(a):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("gemm_dmma_kernel", {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    if a.config != "cfg3":
+    if a.config != "cfg3" or a.dtype != "f64":
         traffic = None   # the committed ncu capture is of the headline shape
     step_tflops = prob["alg_flops_per_point"] * value / world * 1e-12
+    kernel_name, kernel_peak = "gemm_dmma_kernel (FP64 DMMA m8n8k4)", fp64_peak
+    peak_source = ("measured FP64 DMMA peak on this pool's B200 (profiles/fp64_peak_r01.json, tools/fp64_peak.cu); "
+                   "MEASURED_PEAKS.json has no FP64 entry and tcgen05 has no f64 kind")
+    if a.dtype == "f32":
+        bf16 = 1638.0
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except (OSError, ValueError, KeyError):
+            pass
+        kernel_name = "gemm_tf32x3_kernel (tcgen05 kind::tf32, 3 MMAs per product, TMEM accumulators, TMA tensor loads)"
+        kernel_peak = bf16 / 2.0 / 3.0
+        peak_source = ("MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate) / 3 (three TF32 MMAs per "
+                       "fp32-accurate product); achieved counts the algorithmic 2 M^2 flops per point once")
     roofline = {
-        "bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": fp64_peak,
-        "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
-        "peak_source": "measured FP64 DMMA peak on this pool's B200 (profiles/fp64_peak_r01.json, tools/fp64_peak.cu); "
-                       "MEASURED_PEAKS.json has no FP64 entry and tcgen05 has no f64 kind",
+        "bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": kernel_peak,
+        "unit": "TFLOP/s", "frac": achieved / kernel_peak, "traffic": traffic,
+        "peak_source": peak_source,
         "avg_launch_ms": g_avg_s * 1e3, "launches": g_n, "points_per_launch": pts_per_launch,
         "alg_flops_per_point_kernel": 2.0 * M * M, "kernel_share_of_step": g_ms / (ms * a.steps),
         "step": {"alg_flops_per_point": prob["alg_flops_per_point"], "achieved_tflops_per_gpu": step_tflops,
@@ -435,17 +449,36 @@ def run_ours(a):
                "elbo_rel_diff_gpu_vs_oracle_on_sample": abs(gpu_val - val) / abs(val),
                "grad_rel_diff_gpu_vs_oracle_on_sample": gerr}
 
+    f32_err = None
+    if a.dtype == "f32" and world == 1:
+        # the f32 instantiation against the f64 path on the same rows (tolerance of BASELINE.json north_star: 1e-5)
+        S = min(PREFIX_ROWS, N)
+        p64 = synthetic.headline_problem(S, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev)
+        ref = p64["hot"].unpack(p64["hot"].elbo_valgrad_packed(*p64["args"]))
+        got = hp.unpack(hp.elbo_valgrad_packed(X[:S], Y[:S], *args[2:]))
+        f32_err = {"rows": S, "tolerance": 1e-5}
+        for k in ref:
+            den = float(ref[k].abs().max())
+            if den > 0:
+                diff = (got[k] - ref[k]).abs()
+                f32_err[k] = {"max_rel": float(diff.max()) / den, "mean_rel": float(diff.mean()) / den}
+        if max(v["max_rel"] for v in f32_err.values() if isinstance(v, dict)) > 1e-5:
+            raise SystemExit(f"bench.py: the f32 path is outside 1e-5 of the f64 path: {f32_err}")
+        del p64
+
     extras = {}
     if world == 1 and not a.no_extras:
         extras = side_measurements(a, c, prob, e0, e1)
 
     line = {
         "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": workload_config(a.config, c, M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "elbo_data_term": data_term, "kl": float(kl[0]), "checksum": checksum,
         "checks": checks,
     }
+    if f32_err is not None:
+        line["f32_vs_f64"] = f32_err
     line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:

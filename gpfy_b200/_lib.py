@@ -4,12 +4,13 @@ import os
 
 from .build import LIB
 
-GPFY_ABI_VERSION = 1
+GPFY_ABI_VERSION = 2
 GPFY_MAX_DEGREES = 32
 LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1
 Q_TRIL, Q_FULLCOV = 0, 1
 W_ARD, W_SCALAR, W_PROJECTION = 0, 1, 2
 OP_FEATURES, OP_ELBO, OP_PREDICT = 0, 1, 2
+PREC_F64, PREC_TF32X3 = 0, 1
 
 
 class GpfyDesc(ctypes.Structure):
@@ -25,6 +26,7 @@ class GpfyDesc(ctypes.Structure):
         ("q_kind", ctypes.c_int32),
         ("weight_mode", ctypes.c_int32),
         ("projection_dim", ctypes.c_int32),
+        ("precision", ctypes.c_int32),
         ("alpha", ctypes.c_double),
     ]
 
@@ -146,7 +148,7 @@ def check(rc):
 
 
 def make_desc(input_dim, m, num_outputs=1, kernel_order=1, likelihood=LIK_GAUSSIAN, q_kind=Q_TRIL, weight_mode=W_ARD,
-              projection_dim=0):
+              projection_dim=0, precision=PREC_F64):
     d = GpfyDesc()
     d.struct_size = ctypes.sizeof(GpfyDesc)
     d.abi_version = GPFY_ABI_VERSION
@@ -162,6 +164,7 @@ def make_desc(input_dim, m, num_outputs=1, kernel_order=1, likelihood=LIK_GAUSSI
     d.q_kind = int(q_kind)
     d.weight_mode = int(weight_mode)
     d.projection_dim = int(projection_dim) if weight_mode == W_PROJECTION else 0
+    d.precision = int(precision)
     sphere_dim = d.projection_dim if d.projection_dim > 0 else int(input_dim)
     d.alpha = (sphere_dim + 1 - 2.0) / 2.0
     return d

@@ -9,11 +9,15 @@
 //
 // Shape: per CTA tile D[128 points x Mp features] = Zt[128 x Mp] W2^T.
 //   A = the tile's 128 points of the feature-major panels Zh / Zl [Mp][ld] (points contiguous = "MN-major" operand):
-//       per 32-feature k-block four TMA boxes of 32 points x 32 features per plane, 128 B swizzle (UTMALDG)
+//       per 32-feature k-block four TMA boxes of 32 points x 32 features per plane.  An MN-major tf32 operand has exactly
+//       one legal shared-memory layout, SWIZZLE_128B_BASE32B (32-byte swizzle chunks, atoms of 4 k-rows x 128 B; TMA mode
+//       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): LBO = 4096 B between the 32-point chunks, SBO = 512 B between 4-row groups
+//       (tools/umma_probe.cu pins these against a CPU product: profiles/umma_probe_r02.log)
 //   B = W2h / W2l [Mp][Mp] row-major (K-major operand), loaded in two halves of Mp / 2 rows per k-block
 //   D in TMEM: lane = point, column = feature (Mp <= 512 columns), two MMAs of N = Mp / 2 per k-step
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue
-// (tcgen05.ld -> psi_n = z_n . C_n in fp64 -> C stored as float in the tile-contiguous swizzled layout of zonal_bwd4).
+// (tcgen05.ld -> psi_n = z_n . C_n in fp64 -> C widened to double and stored in the tile-contiguous swizzled layout the
+// backward kernels zonal_bwd3 / zonal_bwd4 read, so everything downstream of the contraction is shared with the f64 path).
 // Two independent rings feed the MMA warp: A (2 stages) and B halves (NSB stages), so Mp up to 384 fits in 227 KB.
 #pragma once
 #include <cuda.h>
@@ -34,14 +38,14 @@ struct Gemm32Args {
   const float* Zh;      // for the psi epilogue (the same panels the TMA maps describe)
   const float* Zl;
   int64_t ldz;
-  float* C;             // [tiles32][Mp][32] blocked + swizzled floats
+  double* C;            // [tiles32][Mp][32] blocked + swizzled (the layout of GemmArgs::c_blocked), or null (psi only)
   double* psi;          // [ldz] z_n . C_n, or null
   int Mp;
   int64_t npts;         // points of this launch (tiles of 128; the panels are padded to a multiple of 128 columns)
   int nsb;              // B-ring stages
 };
 
-static inline int g32_b_stage_bytes(int Mp) { return 2 * (Mp / 2) * 128; }   // two planes x Mp / 2 rows x 128 B
+__host__ __device__ static inline int g32_b_stage_bytes(int Mp) { return 2 * (Mp / 2) * 128; }   // two planes x Mp / 2 rows x 128 B
 static inline int g32_nsb(int Mp) {
   const int avail = 226 * 1024 - 2048 - G32_NSA * G32_A_STAGE;
   int n = avail / g32_b_stage_bytes(Mp);
@@ -55,10 +59,11 @@ __device__ __forceinline__ void g32_tma_2d(void* smem, const CUtensorMap* map, i
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(g32_smem_u32(smem)), "l"((uint64_t)map), "r"(g32_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-// cute::UMMA::SmemDescriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61
-__device__ __forceinline__ uint64_t g32_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// cute::UMMA::SmemDescriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | layout type << 61
+// (layout 2 = SWIZZLE_128B for the K-major operand, 1 = SWIZZLE_128B_BASE32B for the MN-major tf32 operand)
+__device__ __forceinline__ uint64_t g32_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-         (1ull << 46) | (2ull << 61);
+         (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void g32_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
@@ -158,8 +163,8 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
 #pragma unroll
             for (int ks = 0; ks < G32_BK / 8; ++ks) {
               // A (MN-major): 8 features = one 1 KB group of a chunk, chunks 4 KB apart; B (K-major): 8 k = 32 B inside the swizzled row
-              const uint64_t dah = g32_desc(ah + ks * 1024, 4096, 1024), dal = g32_desc(al + ks * 1024, 4096, 1024);
-              const uint64_t dbh = g32_desc(bh + ks * 32, 16, 1024), dbl = g32_desc(bl + ks * 32, 16, 1024);
+              const uint64_t dah = g32_desc(ah + ks * 1024, 4096, 512, 1), dal = g32_desc(al + ks * 1024, 4096, 512, 1);
+              const uint64_t dbh = g32_desc(bh + ks * 32, 16, 1024, 2), dbl = g32_desc(bl + ks * 32, 16, 1024, 2);
               g32_mma(d, dal, dbh, idesc, (kb | ks) ? 1u : 0u);
               g32_mma(d, dah, dbl, idesc, 1u);
               g32_mma(d, dah, dbh, idesc, 1u);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
       const int64_t n = p0 + lane;
       mbar_wait(&d_full, (unsigned)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
-      float* ctile = a.C + (p0 >> 5) * (int64_t)Mp * 32;
+      double* ctile = a.C ? a.C + (p0 >> 5) * (int64_t)Mp * 32 : nullptr;
       double psi = 0.0;
       for (int c0 = 0; c0 < Mp; c0 += 32) {
         uint32_t v[32];
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
         for (int j = 0; j < 32; ++j) {
           const int row = c0 + j;
           const float cv = __uint_as_float(v[j]);
-          ctile[row * 32 + (lane ^ ((row & 3) << 2))] = cv;
+          if (ctile) ctile[row * 32 + (lane ^ ((row & 3) << 2))] = (double)cv;
           if (a.psi) psi = fma((double)zh[(int64_t)j * a.ldz] + (double)zl[(int64_t)j * a.ldz], (double)cv, psi);
         }
       }

@@ -133,6 +133,7 @@ int make_shape(const GpfyDesc* desc, Shape* s) {
   if (desc->likelihood != GPFY_LIK_GAUSSIAN && desc->likelihood != GPFY_LIK_BERNOULLI) { set_error("unknown likelihood %d", desc->likelihood); return GPFY_EINVAL; }
   if (desc->q_kind != GPFY_Q_TRIL && desc->q_kind != GPFY_Q_FULLCOV) { set_error("unknown q_kind %d", desc->q_kind); return GPFY_EINVAL; }
   if (desc->weight_mode < GPFY_W_ARD || desc->weight_mode > GPFY_W_PROJECTION) { set_error("unknown weight_mode %d", desc->weight_mode); return GPFY_EINVAL; }
+  if (desc->precision != GPFY_PREC_F64 && desc->precision != GPFY_PREC_TF32X3) { set_error("unknown precision %d", desc->precision); return GPFY_EINVAL; }
   if (s->nw > 1024) { set_error("projection with %d weights > 1024 is not built", s->nw); return GPFY_EUNSUPPORTED; }
   if (s->mmax > 1024) { set_error("m_l = %d > 1024 is not built", s->mmax); return GPFY_EUNSUPPORTED; }
   return GPFY_OK;
@@ -442,7 +443,8 @@ struct Plan {
   int npart;
   // offsets (doubles)
   int64_t o_sw, o_sb, o_dvec, o_vhat_p, o_mu2, o_linv, o_E, o_ET, o_tmp1, o_tmp2, o_tmp3, o_LqP, o_W0, o_W2, o_dE, o_Gz, o_bz,
-      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, total;
+      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, o_W2f, o_Zf, total;
+  bool f32;         // GPFY_PREC_TF32X3: float hi / lo planes of W2 (o_W2f) and Z (o_Zf) for the tcgen05 contraction
   int npsi;
 };
 
@@ -473,8 +475,9 @@ static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   return nc < nc_max ? nc : nc_max;
 }
 
-static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
+static void make_plan(const Shape& s, int64_t n, int op, Plan* p, bool f32 = false) {
   p->s = s;
+  p->f32 = f32;
   p->sms = device_sms();
   p->nc = choose_chunk(p->sms, n, s);
   p->nb = (s.Mp + SYRK_B - 1) / SYRK_B;
@@ -533,6 +536,9 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p) {
   p->o_cq = take((int64_t)s.P * p->nc);
   p->o_dr = take(p->nc);
   p->o_dT = take(op == GPFY_OP_ELBO ? Mp * p->nc : 0);
+  // two float planes = one double per element
+  p->o_W2f = take(f32 ? (int64_t)s.P * Mp2 : 0);
+  p->o_Zf = take(f32 && op != GPFY_OP_FEATURES ? Mp * p->nc : 0);
   p->total = o;
 }
 
@@ -780,6 +786,72 @@ static int gemm_sq(cudaStream_t st, const double* A, const double* B, double* C,
     GPFY_LAUNCH_OK();                                 \
   } while (0)
 
+// ---- the f32 instantiation of the contraction (GPFY_PREC_TF32X3): tcgen05 kernel of gemm_tf32.cuh ----
+static bool want_f32(const GpfyDesc* desc) { return desc->precision == GPFY_PREC_TF32X3; }
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {   // the driver API entry point through the runtime: no link-time libcuda dependency
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TensorMapEncodeFn)f;
+  });
+  return fn;
+}
+// 2-D float tensor [outer][inner] (row stride = inner_ld floats), box = box_inner x box_outer elements
+static int make_map_f32(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t inner_ld, uint32_t box_inner,
+                        uint32_t box_outer, CUtensorMapSwizzle swz) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return GPFY_EUNSUPPORTED; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner_ld * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GPFY_ECUDA; }
+  return GPFY_OK;
+}
+
+// The shapes the tcgen05 contraction is built for.
+static int check_f32_shape(const Shape& s) {
+  if (s.P != 1 || s.proj != 0 || s.Mp > 512 || g32_nsb(s.Mp) < 2) {
+    set_error("GPFY_PREC_TF32X3 is built for num_outputs = 1, no projection weights and M <= 512 (got P = %d, M = %d)", s.P, s.M);
+    return GPFY_EUNSUPPORTED;
+  }
+  return GPFY_OK;
+}
+
+// C (blocked, may be null) and / or psi = z . C for npts points of the chunk panels, output q
+static int launch_gemm32(cudaStream_t st, const Plan& p, double* ws, int q, int64_t npts, double* C, double* psi) {
+  const Shape& s = p.s;
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  float* zh = reinterpret_cast<float*>(ws + p.o_Zf);
+  float* zl = zh + (int64_t)Mp * p.nc;
+  float* wh = reinterpret_cast<float*>(ws + p.o_W2f) + 2 * q * Mp2;
+  float* wl = wh + Mp2;
+  Gemm32Maps maps;
+  GPFY_TRY(make_map_f32(&maps.zh, zh, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  GPFY_TRY(make_map_f32(&maps.zl, zl, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  GPFY_TRY(make_map_f32(&maps.wh, wh, (uint64_t)Mp, (uint64_t)Mp, (uint64_t)Mp, 32, (uint32_t)(Mp / 2), CU_TENSOR_MAP_SWIZZLE_128B));
+  GPFY_TRY(make_map_f32(&maps.wl, wl, (uint64_t)Mp, (uint64_t)Mp, (uint64_t)Mp, 32, (uint32_t)(Mp / 2), CU_TENSOR_MAP_SWIZZLE_128B));
+  Gemm32Args ga;
+  ga.Zh = zh; ga.Zl = zl; ga.ldz = p.nc; ga.C = C; ga.psi = psi; ga.Mp = Mp; ga.npts = npts; ga.nsb = g32_nsb(Mp);
+  const int smem = g32_smem_bytes(Mp);
+  GPFY_TRY(set_smem(gemm_tf32x3_kernel, smem));
+  const int tiles = (int)((npts + G32_BM - 1) / G32_BM);
+  gemm_tf32x3_kernel<<<std::min(tiles, p.sms), G32_THREADS, smem, st>>>(maps, ga);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
 // Shared prologue: sqrt weights, padded Vhat, Linv, E = diag(sqrt(eig v)) Linv, E^T, and per output
 // W0 = L L^T - I (or Sigma - I), W2 = E^T W0 E, mu2 = E^T mu.
 static int run_prologue(cudaStream_t st, const GpfyDesc* desc, const Plan& p, double* ws, const double* w, const double* b,
@@ -814,6 +886,10 @@ static int run_prologue(cudaStream_t st, const GpfyDesc* desc, const Plan& p, do
     }
     GPFY_TRY(gemm_sq(st, W0, ws + p.o_E, ws + p.o_tmp1, Mp, 1.0, 0.0, p.sms));              // W0 E
     GPFY_TRY(gemm_sq(st, ws + p.o_ET, ws + p.o_tmp1, ws + p.o_W2 + q * Mp2, Mp, 1.0, 0.0, p.sms));  // E^T W0 E
+    if (p.f32) {   // hi / lo TF32 planes of W2 for the tcgen05 contraction
+      float* wh = reinterpret_cast<float*>(ws + p.o_W2f) + 2 * q * Mp2;
+      GPFY_K(tf32_split_kernel, sqg, 256, 0, st, ws + p.o_W2 + q * Mp2, wh, wh + Mp2, Mp2);
+    }
     // mu2_q = E^T mu[:, q]
     GPFY_K(gemv_kernel, (Mp + 3) / 4, 128, 0, st, ws + p.o_E, Mp, 1, mu + q, s.P, s.M, ws + p.o_mu2 + (int64_t)q * Mp, 1, Mp);
   }
@@ -914,7 +990,7 @@ int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t*
   GPFY_TRY(make_shape(desc, &s));
   if (!bytes || n_points < 0 || op < GPFY_OP_FEATURES || op > GPFY_OP_PREDICT) { set_error("bad argument"); return GPFY_EINVAL; }
   Plan p;
-  make_plan(s, n_points, op, &p);
+  make_plan(s, n_points, op, &p, want_f32(desc) && op != GPFY_OP_FEATURES);
   *bytes = (size_t)p.total * 8;
   return GPFY_OK;
 }
@@ -948,7 +1024,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     // one fused kernel (two CTAs per SM): the zonal values stay in shared memory
     FeaturesArgs fa;
     ZonalArgs& za = fa.z;
-    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
+    za.Yg = nullptr; za.ZPb = nullptr; za.Zh = za.Zl = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
     za.X = X; za.xcols = apply_to_sphere ? s.d : s.dim; za.apply_to_sphere = apply_to_sphere;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = n;
@@ -962,7 +1038,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
     const int64_t npts = std::min(p.nc, n - c0);
     ZonalArgs za;
-    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
+    za.Yg = nullptr; za.ZPb = nullptr; za.Zh = za.Zl = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
     za.X = X + c0 * (apply_to_sphere ? s.d : s.dim);
     za.xcols = apply_to_sphere ? s.d : s.dim;
     za.apply_to_sphere = apply_to_sphere;
@@ -988,7 +1064,11 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
 static int elbo_plan(const GpfyDesc* desc, int64_t n_capacity, void* workspace, size_t workspace_bytes, Shape* s, Plan* p) {
   GPFY_TRY(make_shape(desc, s));
   if (n_capacity < 0) { set_error("n_capacity < 0"); return GPFY_EINVAL; }
-  make_plan(*s, n_capacity, GPFY_OP_ELBO, p);
+  make_plan(*s, n_capacity, GPFY_OP_ELBO, p, want_f32(desc));
+  if (p->f32) {
+    GPFY_TRY(check_f32_shape(*s));
+    if (!fused_bwd_ok(*s) && !bwd4_ok(*s)) { set_error("GPFY_PREC_TF32X3 needs one of the fused backward kernels for this shape"); return GPFY_EUNSUPPORTED; }
+  }
   return check_ws(*p, workspace, workspace_bytes);
 }
 
@@ -1004,6 +1084,11 @@ int gpfy_svgp_elbo_begin(void* stream, const GpfyDesc* desc, int64_t n_capacity,
   // pad rows of Z are never written by the zonal kernel; accumulators start at zero
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp + 32 - s.M) * p.nc * 8, st));
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, (size_t)(p.o_Z - p.o_partials) * 8, st));  // partials, Gpart, bzpart, dVpart
+  if (p.f32 && s.Mp > s.M) {   // padding rows of the two float planes
+    float* zh = reinterpret_cast<float*>(ws + p.o_Zf);
+    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
+    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)(s.Mp + s.M) * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
+  }
   return GPFY_OK;
 }
 
@@ -1027,7 +1112,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
-    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
+    za.Yg = nullptr; za.ZPb = nullptr; za.Zh = za.Zl = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
@@ -1035,11 +1120,16 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     za.deg = deg; za.rc = rc;
     if (fuse_lik) { za.Yg = Y + c0; za.s2g = sigma2; za.wq = ws + p.o_wq; za.wp = ws + p.o_wp; za.cq = ws + p.o_cq; }
     za.ZPb = bwd4 ? ws + p.o_dT : nullptr;   // the derivative panel takes the place of the legacy path's dT buffer
+    if (p.f32) { za.Zh = reinterpret_cast<float*>(ws + p.o_Zf); za.Zl = za.Zh + (int64_t)Mp * p.nc; }
     {
       GPFY_TIMED(TK_ZONAL_FWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
     }
 
+    if (p.f32) {  // C = W2 Z on tcgen05 in 3 x TF32 (P = 1); psi goes out as one slab
+      GPFY_TIMED(TK_GEMM, st);
+      GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi));
+    } else
     for (int q = 0; q < s.P; ++q) {  // C_q = W2_q Z
       GPFY_TIMED(TK_GEMM, st);
       GemmArgs g;
@@ -1055,7 +1145,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
 
     if (!fuse_lik) {
       LikPointArgs lp;
-      lp.psi_part = ws + p.o_psi; lp.npsi = p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
+      lp.psi_part = ws + p.o_psi; lp.npsi = p.f32 ? 1 : p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
       lp.R = ws + p.o_R; lp.Y = Y + c0 * s.P; lp.vptr = variance; lp.s2ptr = sigma2;
       lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
       lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
@@ -1234,7 +1324,8 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
   GPFY_TRY(make_shape(desc, &s));
   if (n == 0) return GPFY_OK;
   Plan p;
-  make_plan(s, n, GPFY_OP_PREDICT, &p);
+  make_plan(s, n, GPFY_OP_PREDICT, &p, want_f32(desc));
+  if (p.f32) GPFY_TRY(check_f32_shape(s));
   GPFY_TRY(check_ws(p, workspace, workspace_bytes));
   double* ws = (double*)workspace;
   const int Mp = s.Mp;
@@ -1242,6 +1333,11 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
   DegreeTable deg = degree_table(desc);
   RecCoef rc = make_rec_coef(desc->alpha);
   GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
+  if (p.f32 && s.Mp > s.M) {
+    float* zh = reinterpret_cast<float*>(ws + p.o_Zf);
+    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
+    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)(s.Mp + s.M) * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
+  }
   // only the quadratic form z^T W2 z is needed: fold W2 onto its lower triangle (W_ij + W_ji below the diagonal, zero
   // above) and let the GEMM skip the k range right of each row tile's diagonal block
   for (int q = 0; q < s.P; ++q)
@@ -1251,13 +1347,17 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     const int64_t npts = std::min(p.nc, n - c0);
     const int64_t npts_e = (npts + 1) & ~(int64_t)1;
     ZonalArgs za;
-    za.Yg = nullptr; za.ZPb = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
+    za.Yg = nullptr; za.ZPb = nullptr; za.Zh = za.Zl = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = s.proj;
     za.X = X + c0 * s.d; za.xcols = s.d; za.apply_to_sphere = 1;
     za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
     za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = nullptr; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
+    if (p.f32) { za.Zh = reinterpret_cast<float*>(ws + p.o_Zf); za.Zl = za.Zh + (int64_t)Mp * p.nc; }
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+    if (p.f32) {
+      GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, nullptr, ws + p.o_psi));   // psi only, 3 x TF32 on tcgen05
+    } else
     for (int q = 0; q < s.P; ++q) {
       GemmArgs g;
       g.A = ws + p.o_W2 + q * Mp2; g.lda = Mp;
@@ -1270,7 +1370,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
     PredictArgs pa;
-    pa.psi_part = ws + p.o_psi; pa.npsi = p.npsi; pa.mz = ws + p.o_mz; pa.ldz = p.nc;
+    pa.psi_part = ws + p.o_psi; pa.npsi = p.f32 ? 1 : p.npsi; pa.mz = ws + p.o_mz; pa.ldz = p.nc;
     pa.R = ws + p.o_R; pa.vptr = variance; pa.P = s.P; pa.order = desc->kernel_order; pa.npts = npts;
     pa.fmu = fmu + c0 * s.P; pa.fvar = fvar + c0 * s.P;
     GPFY_TRY(launch_predict(st, pa));

@@ -4,6 +4,7 @@
 // (variational.py:305 folded) and, for the Gaussian likelihood, the per-point weights (likelihoods.py:210-218).
 // One CTA = 32 points x all rows; warp w takes the 8-row tiles w, w + 8, ...
 #pragma once
+#include "gemm_tf32.cuh"
 #include "svgp_kernels.cuh"
 #include "zonal_common.cuh"
 
@@ -191,6 +192,20 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
           else if (n0 < a.npts) {
             dst[0] = z[2 * nt];
             if (n0 + 1 < npts_e) dst[1] = 0.0;  // keep the even-padded tail column finite
+          }
+        }
+        if (a.Zh) {   // the same values as two TF32 planes (hi + lo) for the tcgen05 contraction
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int64_t n0 = p0 + 8 * nt + 2 * t4;
+            float h0, l0, h1, l1;
+            tf32_split(z[2 * nt], h0, l0);
+            tf32_split(z[2 * nt + 1], h1, l1);
+            if (n0 + 1 >= a.npts) { h1 = 0.f; l1 = 0.f; }
+            if (n0 < a.npts) {
+              *reinterpret_cast<float2*>(a.Zh + (int64_t)row * a.ldz + n0) = make_float2(h0, h1);
+              *reinterpret_cast<float2*>(a.Zl + (int64_t)row * a.ldz + n0) = make_float2(l0, l1);
+            }
           }
         }
         if (a.mz) {

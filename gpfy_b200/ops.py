@@ -59,7 +59,7 @@ class HotPath:
     (SphericalHarmonics, kernel, q, likelihood) in the reference."""
 
     def __init__(self, input_dim, m, num_outputs=1, kernel_order=1, likelihood="gaussian", q_kind="tril",
-                 weight_mode="ard", device=None, projection_dim=0):
+                 weight_mode="ard", device=None, projection_dim=0, precision="f64"):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.m = [int(v) for v in m]
@@ -75,7 +75,9 @@ class HotPath:
             input_dim, self.m, num_outputs, kernel_order,
             _lib.LIK_GAUSSIAN if likelihood == "gaussian" else _lib.LIK_BERNOULLI,
             _lib.Q_TRIL if q_kind == "tril" else _lib.Q_FULLCOV,
-            {"scalar": _lib.W_SCALAR, "projection": _lib.W_PROJECTION}.get(weight_mode, _lib.W_ARD), self.projection_dim)
+            {"scalar": _lib.W_SCALAR, "projection": _lib.W_PROJECTION}.get(weight_mode, _lib.W_ARD), self.projection_dim,
+            {"f64": _lib.PREC_F64, "f32": _lib.PREC_TF32X3, "tf32x3": _lib.PREC_TF32X3}[precision])
+        self.precision = precision
         self.nw = self.input_dim * self.projection_dim if self.projection_dim else (1 if self.scalar_w else self.input_dim)
         self.layout = _lib.GpfyElboLayout()
         _lib.check(self.lib.gpfy_elbo_packed_layout(ctypes.byref(self.desc), ctypes.byref(self.layout)))

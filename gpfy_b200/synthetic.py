@@ -134,7 +134,7 @@ def headline_host_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2
     return host, X.numpy(), Y.numpy(), m
 
 
-def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, device="cuda", rank=0, world=1):
+def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, device="cuda", rank=0, world=1, precision="f64"):
     """BASELINE.json configs[2] (and, through d / F / T / likelihood, configs[3], [4]): full SVGP ELBO+gradient step.
     Rank `rank` of `world` owns the contiguous block `shard_bounds(N, rank, world)` of the N global rows
     (`global_rows`: the same data set for every world size)."""
@@ -143,7 +143,8 @@ def headline_problem(N, d=8, F=11, T=30, P=1, likelihood="gaussian", seed=2, dev
     M, dim = sum(m), d + 1
     lo, hi = shard_bounds(N, rank, world)
     X, Y = global_rows_device(lo, hi, device, d, P, likelihood, seed)
-    hp = HotPath(d, m, num_outputs=P, kernel_order=1, likelihood=likelihood, q_kind="tril", weight_mode="ard", device=device)
+    hp = HotPath(d, m, num_outputs=P, kernel_order=1, likelihood=likelihood, q_kind="tril", weight_mode="ard", device=device,
+                 precision=precision)
     vhat = np.concatenate(host["V"], 0)
     lcat = np.concatenate([l.ravel() for l in host["L"]])
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)

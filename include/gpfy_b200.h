@@ -7,7 +7,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host".
- *   - all arithmetic is IEEE float64 (the reference forces x64: utils.py:26, param.py:151).
+ *   - all arithmetic is IEEE float64 (the reference forces x64: utils.py:26, param.py:151) unless the descriptor asks for
+ *     GPFY_PREC_TF32X3 (the f32 instantiation of the dense contraction); buffers are float64 either way.
  *   - stream-ordered: every call only enqueues work on `stream`; no allocation, no host sync.
  *     Scratch comes from the caller (`gpfy_workspace_bytes`).
  *   - return 0 on success, negative GPFY_E* otherwise; `gpfy_last_error_string()` explains
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GPFY_ABI_VERSION 1
+#define GPFY_ABI_VERSION 2
 #define GPFY_MAX_DEGREES 32
 
 enum {
@@ -51,6 +52,13 @@ enum {
 enum { GPFY_LIK_GAUSSIAN = 0, GPFY_LIK_BERNOULLI = 1 };
 enum { GPFY_Q_TRIL = 0, GPFY_Q_FULLCOV = 1 };
 enum { GPFY_W_ARD = 0, GPFY_W_SCALAR = 1, GPFY_W_PROJECTION = 2 };
+/* Arithmetic of the dense contraction C = W2 Z (variational.py:323-328 folded; 55 % of the step's flops):
+ *   GPFY_PREC_F64    : IEEE float64 on the FP64 tensor cores (DMMA) - the reference's precision (utils.py:26, param.py:151);
+ *   GPFY_PREC_TF32X3 : the f32 instantiation - operands split into two TF32 planes, three tcgen05 kind::tf32 MMAs per
+ *                      product into an fp32 TMEM accumulator (~2^-21 relative per product); everything else (zonal
+ *                      recurrences, likelihood, reductions over N) stays float64.  Results agree with GPFY_PREC_F64 to 1e-5
+ *                      (BASELINE.json north_star).  Built for num_outputs = 1, M <= 512, no projection weights. */
+enum { GPFY_PREC_F64 = 0, GPFY_PREC_TF32X3 = 1 };
 
 /* POD, versioned.  Mirrors the static (non-pytree) fields the reference keeps on its dataclasses:
  * SphericalHarmonics.num_frequencies / phase_truncation (spherical_harmonics.py:75-76, via m[]),
@@ -70,6 +78,7 @@ typedef struct GpfyDesc {
   int32_t weight_mode;  /* GPFY_W_ARD: weight_variances [d]; GPFY_W_SCALAR: one value (spherical.py:110-114);
                            GPFY_W_PROJECTION: a [d, p] linear projection X @ W, identity bijector (spherical.py:110-117,225-226) */
   int32_t projection_dim; /* p for GPFY_W_PROJECTION, else 0 */
+  int32_t precision;    /* GPFY_PREC_*: arithmetic of the dense contraction (gpfy_svgp_elbo_*, gpfy_predict_diag) */
   double alpha;         /* (ambient dim - 2) / 2 (spherical_harmonics.py:149) */
 } GpfyDesc;
 
