@@ -9,7 +9,7 @@ GPFY_MAX_DEGREES = 32
 LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1
 Q_TRIL, Q_FULLCOV = 0, 1
 W_ARD, W_SCALAR, W_PROJECTION = 0, 1, 2
-OP_FEATURES, OP_ELBO, OP_PREDICT = 0, 1, 2
+OP_FEATURES, OP_ELBO, OP_PREDICT, OP_FEATURES_VJP = 0, 1, 2, 3
 PREC_F64, PREC_TF32X3 = 0, 1
 
 
@@ -79,6 +79,8 @@ _SIGNATURES = {
     "gpfy_gegenbauer": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_double, _P, ctypes.c_int64, _P, _P]),
     "gpfy_sh_features_fwd": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, ctypes.c_int, _P, _P, _P, _P,
                                             _P, ctypes.c_int, _P, _P, _P, ctypes.c_size_t]),
+    "gpfy_sh_features_vjp": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, ctypes.c_int, _P, _P, _P, _P,
+                                            _P, ctypes.c_int, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t]),
     "gpfy_svgp_elbo_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 12 +
                                [_P, ctypes.c_size_t]),
     "gpfy_svgp_elbo_begin": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 8 + [_P, ctypes.c_size_t]),
@@ -91,6 +93,7 @@ _SIGNATURES = {
     "gpfy_step_grad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyStepLayout), _P, _P, _P, _P, _P, ctypes.c_double, _P, _P]),
     "gpfy_step_adam": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P, _P, _P] + [ctypes.c_double] * 4 + [ctypes.c_int64]),
     "gpfy_prior_kl_valgrad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, _P]),
+    "gpfy_prior_kl_valgrad_ws": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, _P, _P, ctypes.c_size_t]),
     "gpfy_predict_diag": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 11 + [_P, ctypes.c_size_t]),
     "gpfy_allreduce_packed": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),
     "gpfy_debug_kernel_timing": (ctypes.c_int, [ctypes.c_int]),

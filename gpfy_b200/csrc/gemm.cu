@@ -162,7 +162,7 @@ __device__ __forceinline__ void gemm_body(const GemmArgs& a) {
                 }
                 if ((!(VAR & 8) || v.x == 1.2345e300) && a.C) *dst = v;  // VAR bit 3: keep the MMAs, drop the stores; C == null: psi only
                 if (a.psi_out && !(VAR & 4)) {
-                  const double2 z = *reinterpret_cast<const double2*>(a.B + (int64_t)row * a.ldb + col);
+                  const double2 z = *reinterpret_cast<const double2*>((a.psi_B ? a.psi_B : a.B) + (int64_t)row * a.ldb + col);
                   ps[c][0] = fma(z.x, v.x, ps[c][0]);
                   ps[c][1] = fma(z.y, v.y, ps[c][1]);
                 }

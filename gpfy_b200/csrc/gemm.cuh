@@ -29,6 +29,7 @@ struct GemmArgs {
   // i.e. the pieces of z_n^T W2 z_n (variational.py:326-327 folded); fixed layout => deterministic.
   double* psi_out;
   int64_t ld_psi;
+  const double* psi_B = nullptr;   // panel whose rows are dotted with C in the psi epilogue (same layout / ld as B); null = B
   // c_blocked != 0: C is written as [n / 32][m][32] (each 32-column block of all m rows contiguous, so the
   // fused backward kernel fetches a tile with a few TMA bulk copies) with the column inside a block XOR-
   // swizzled by the row, (col & 31) ^ ((row & 3) << 2), which makes the tensor-core fragment reads of that

@@ -14,6 +14,7 @@
 #include "zonal_bwd4.cuh"
 #include "zonal_fwd2.cuh"
 #include "basis.cuh"
+#include "features_vjp.cuh"
 
 namespace gpfy {
 
@@ -429,6 +430,78 @@ __global__ void __launch_bounds__(1024) kl_tril_value_kernel(const double* mu, c
   if (threadIdx.x == 0) out[0] = red[0] - 0.5 * (double)nmu;
 }
 
+// KL(q || N(0, I)) for q = N(mu, Sigma) with a dense covariance (variational.py:375-399).  One CTA per output p:
+//   A <- Sigma_p, in-place right-looking Cholesky (lower), logdet = 2 sum log diag;  X = L^-1 by forward substitution, one
+//   thread per column;  dKL/dSigma = 1/2 I - 1/2 X^T X (the symmetrised cotangent of jnp.linalg.cholesky's logdet).
+__global__ void __launch_bounds__(1024) kl_full_chol_kernel(const double* Sigma, double* A, double* X, double* logdet, int M) {
+  const int p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int64_t MM = (int64_t)M * M;
+  double* a = A + p * MM;
+  double* x = X + p * MM;
+  const double* s = Sigma + p * MM;
+  for (int64_t e = tid; e < MM; e += nt) a[e] = s[e];
+  __syncthreads();
+  for (int j = 0; j < M; ++j) {
+    const double d = sqrt(a[(int64_t)j * M + j]);       // every thread reads the same (updated) pivot
+    __syncthreads();
+    for (int i = j + tid; i < M; i += nt) a[(int64_t)i * M + j] = (i == j) ? d : a[(int64_t)i * M + j] / d;
+    __syncthreads();
+    const int rem = M - j - 1;                            // trailing update of the lower triangle: (i, k), j < k <= i
+    for (int64_t e = tid; e < (int64_t)rem * rem; e += nt) {
+      const int i = j + 1 + (int)(e / rem), k = j + 1 + (int)(e % rem);
+      if (k <= i) a[(int64_t)i * M + k] -= a[(int64_t)i * M + j] * a[(int64_t)k * M + j];
+    }
+    __syncthreads();
+  }
+  // X = L^-1: column c by forward substitution (entries above the diagonal are zero)
+  for (int c = tid; c < M; c += nt) {
+    for (int i = 0; i < c; ++i) x[(int64_t)i * M + c] = 0.0;
+    for (int i = c; i < M; ++i) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) acc -= a[(int64_t)i * M + k] * x[(int64_t)k * M + c];
+      x[(int64_t)i * M + c] = acc / a[(int64_t)i * M + i];
+    }
+  }
+  __shared__ double red[1024];
+  double ld = 0.0;
+  for (int i = tid; i < M; i += nt) { const double v = a[(int64_t)i * M + i]; ld += log(v * v); }
+  red[tid] = ld;
+  __syncthreads();
+  for (int o = nt / 2; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) logdet[p] = red[0];
+}
+// out = [KL, dKL/dmu, dKL/dSigma]: gradients elementwise; the scalar from one block's fixed-order tree
+__global__ void kl_full_grad_kernel(const double* mu, const double* X, double* out, int M, int P) {
+  const int64_t nmu = (int64_t)M * P, nS = (int64_t)P * M * M;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nmu) out[1 + e] = mu[e];
+  if (e < nS) {
+    const int p = (int)(e / ((int64_t)M * M)), i = (int)((e / M) % M), j = (int)(e % M);
+    const double* x = X + (int64_t)p * M * M;
+    double s = 0.0;
+    for (int k = (i > j ? i : j); k < M; ++k) s = fma(x[(int64_t)k * M + i], x[(int64_t)k * M + j], s);
+    out[1 + nmu + e] = (i == j ? 0.5 : 0.0) - 0.5 * s;
+  }
+}
+__global__ void __launch_bounds__(1024) kl_full_value_kernel(const double* mu, const double* Sigma, const double* logdet, double* out, int M, int P) {
+  __shared__ double red[1024];
+  const int64_t nmu = (int64_t)M * P;
+  double s = 0.0;
+  for (int64_t e = threadIdx.x; e < nmu; e += blockDim.x) s = fma(0.5 * mu[e], mu[e], s);
+  for (int64_t d = threadIdx.x; d < (int64_t)P * M; d += blockDim.x) s += 0.5 * Sigma[(d / M) * M * M + (d % M) * (int64_t)(M + 1)];
+  for (int p = threadIdx.x; p < P; p += blockDim.x) s -= 0.5 * logdet[p];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0] - 0.5 * (double)nmu;
+}
+
 // ------------------------------------------------------------------------------------------------
 // workspace plan
 // ------------------------------------------------------------------------------------------------
@@ -443,7 +516,8 @@ struct Plan {
   int npart;
   // offsets (doubles)
   int64_t o_sw, o_sb, o_dvec, o_vhat_p, o_mu2, o_linv, o_E, o_ET, o_tmp1, o_tmp2, o_tmp3, o_LqP, o_W0, o_W2, o_dE, o_Gz, o_bz,
-      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, o_W2f, o_Zf, total;
+      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, o_W2f, o_Zf, o_Dp, o_xg, total;
+  int KSX;          // cross-Gram splits (features VJP)
   bool f32;         // GPFY_PREC_TF32X3: float hi / lo planes of W2 (o_W2f) and Z (o_Zf) for the tcgen05 contraction
   int npsi;
 };
@@ -475,7 +549,9 @@ static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   return nc < nc_max ? nc : nc_max;
 }
 
-static void make_plan(const Shape& s, int64_t n, int op, Plan* p, bool f32 = false) {
+static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, bool f32 = false) {
+  const bool fvjp = op_in == GPFY_OP_FEATURES_VJP;   // the features VJP shares the ELBO step's buffers plus two of its own
+  const int op = fvjp ? GPFY_OP_ELBO : op_in;
   p->s = s;
   p->f32 = f32;
   p->sms = device_sms();
@@ -539,6 +615,9 @@ static void make_plan(const Shape& s, int64_t n, int op, Plan* p, bool f32 = fal
   // two float planes = one double per element
   p->o_W2f = take(f32 ? (int64_t)s.P * Mp2 : 0);
   p->o_Zf = take(f32 && op != GPFY_OP_FEATURES ? Mp * p->nc : 0);
+  p->KSX = std::max(1, (8 * p->sms) / std::max(1, s.Mp / 16));
+  p->o_Dp = take(fvjp ? Mp * p->nc : 0);
+  p->o_xg = take(fvjp ? (int64_t)p->KSX * Mp * XG_W : 0);
   p->total = o;
 }
 
@@ -988,9 +1067,10 @@ int gpfy_chunk_rows(const GpfyDesc* desc, int64_t n_points, int64_t* rows) {
 int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t* bytes) {
   Shape s;
   GPFY_TRY(make_shape(desc, &s));
-  if (!bytes || n_points < 0 || op < GPFY_OP_FEATURES || op > GPFY_OP_PREDICT) { set_error("bad argument"); return GPFY_EINVAL; }
+  if (!bytes || n_points < 0 || op < GPFY_OP_FEATURES || op > GPFY_OP_FEATURES_VJP) { set_error("bad argument"); return GPFY_EINVAL; }
   Plan p;
-  make_plan(s, n_points, op, &p, want_f32(desc) && op != GPFY_OP_FEATURES);
+  if (op == GPFY_OP_FEATURES_VJP) s.P = 1;
+  make_plan(s, n_points, op, &p, want_f32(desc) && op != GPFY_OP_FEATURES && op != GPFY_OP_FEATURES_VJP);
   *bytes = (size_t)p.total * 8;
   return GPFY_OK;
 }
@@ -1054,6 +1134,113 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     GPFY_K(whiten_kernel, (unsigned)((npts + 127) / 128), 128, 0, st, wa);
     if (r_out) GPFY_CUDA_OK(cudaMemcpyAsync(r_out + c0, ws + p.o_R, npts * 8, cudaMemcpyDeviceToDevice, st));
   }
+  return GPFY_OK;
+}
+
+int gpfy_sh_features_vjp(void* stream, const GpfyDesc* desc, int64_t n, const double* X, int apply_to_sphere, const double* w,
+                         const double* b, const double* vhat, const double* lcat, const double* degree_scale, int mul_r,
+                         const double* dPhi, double* dvhat, double* dlcat, double* dscale, double* dw, double* db, void* workspace,
+                         size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  s.P = 1;   // the feature matrix does not depend on the number of outputs
+  if (s.proj > 0 && apply_to_sphere) { set_error("gpfy_sh_features_vjp is not built for projection weights"); return GPFY_EUNSUPPORTED; }
+  if (!bwd4_ok(s)) { set_error("gpfy_sh_features_vjp: shape outside the fused backward kernel (M = %d, ambient dim %d)", s.M, s.dim); return GPFY_EUNSUPPORTED; }
+  const int Mp = s.Mp;
+  const int64_t Mp2 = (int64_t)Mp * Mp;
+  DegreeTable deg = degree_table(desc);
+  // column window of every 16-row group of the block-diagonal cross Gram matrix
+  XgCols xc;
+  for (int rg = 0; rg < 72; ++rg) xc.col0[rg] = 0;
+  for (int rg = 0; rg * 16 < Mp; ++rg) {
+    const int first = rg * 16, last = std::min(rg * 16 + 15, s.M - 1);
+    if (first >= s.M) continue;
+    int lf = 0, ll = 0;
+    while (first >= s.off[lf + 1]) ++lf;
+    while (last >= s.off[ll + 1]) ++ll;
+    xc.col0[rg] = s.off[lf];
+    if (s.off[ll + 1] - s.off[lf] > XG_W) { set_error("gpfy_sh_features_vjp: degree blocks wider than the %d-column window", XG_W); return GPFY_EUNSUPPORTED; }
+  }
+  Plan p;
+  make_plan(s, n, GPFY_OP_FEATURES_VJP, &p);
+  GPFY_TRY(check_ws(p, workspace, workspace_bytes));
+  double* ws = (double*)workspace;
+  const int d_nw = desc->weight_mode == GPFY_W_SCALAR ? 1 : s.d;
+  if (n == 0) {
+    if (dvhat) GPFY_CUDA_OK(cudaMemsetAsync(dvhat, 0, (size_t)s.M * s.dim * 8, st));
+    if (dlcat) GPFY_CUDA_OK(cudaMemsetAsync(dlcat, 0, (size_t)s.lsize * 8, st));
+    if (dscale) GPFY_CUDA_OK(cudaMemsetAsync(dscale, 0, (size_t)s.F * 8, st));
+    if (dw && apply_to_sphere) GPFY_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)d_nw * 8, st));
+    if (db && apply_to_sphere) GPFY_CUDA_OK(cudaMemsetAsync(db, 0, 8, st));
+    return GPFY_OK;
+  }
+  GPFY_TRY(run_prologue(st, desc, p, ws, apply_to_sphere ? w : vhat, apply_to_sphere ? b : vhat, nullptr, nullptr, vhat, lcat,
+                        nullptr, nullptr, false));
+  // A = diag(scale) Linv (E) and its transpose; mu2 = 0 (it sits behind vhat_p and is staged by the backward kernel)
+  GPFY_K(row_scale_kernel, (Mp + 127) / 128, 128, 0, st, degree_scale, deg, s.M, Mp, ws + p.o_dvec);
+  dim3 tg(Mp / 32, Mp / 32), tb(32, 8);
+  GPFY_K(scale_rows_transpose_kernel, tg, tb, 0, st, ws + p.o_linv, ws + p.o_dvec, ws + p.o_E, ws + p.o_ET, Mp);
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_mu2, 0, (size_t)Mp * 8, st));
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Dp + (int64_t)s.M * p.nc, 0, (size_t)(Mp - s.M) * p.nc * 8, st));
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, (size_t)(p.o_Z - p.o_partials) * 8, st));
+  GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_xg, 0, (size_t)p.KSX * Mp * XG_W * 8, st));
+  RecCoef rc = make_rec_coef(desc->alpha);
+  for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
+    const int64_t npts = std::min(p.nc, n - c0);
+    const int64_t npts_e = (npts + 1) & ~(int64_t)1;
+    ZonalArgs za;
+    za.Yg = nullptr; za.ZPb = ws + p.o_dT; za.Zh = za.Zl = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr;
+    za.proj = apply_to_sphere ? s.proj : 0;
+    za.X = X + c0 * (apply_to_sphere ? s.d : s.dim); za.xcols = apply_to_sphere ? s.d : s.dim; za.apply_to_sphere = apply_to_sphere;
+    za.sw = ws + p.o_sw; za.sb = ws + p.o_sb; za.vhat_p = ws + p.o_vhat_p;
+    za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
+    za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R; za.mz = nullptr; za.P = 1;
+    za.deg = deg; za.rc = rc;
+    GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
+    dim3 cg((unsigned)((npts_e + 255) / 256), s.M);
+    GPFY_K(scale_panel_kernel, cg, 256, 0, st, dPhi + c0, n, s.M, npts, mul_r ? ws + p.o_R : (const double*)nullptr, ws + p.o_Dp, p.nc);
+    {
+      GemmArgs g;   // C = A^T Dp (cotangent of the zonal values), psi = z . C
+      g.A = ws + p.o_ET; g.lda = Mp; g.B = ws + p.o_Dp; g.ldb = p.nc; g.C = ws + p.o_C; g.ldc = p.nc;
+      g.m = Mp; g.k = Mp; g.n = (int)npts_e; g.alpha = 1.0; g.beta = 0.0;
+      g.psi_out = ws + p.o_psi; g.ld_psi = p.nc; g.psi_B = ws + p.o_Z; g.c_blocked = 1;
+      GPFY_TRY(launch_gemm(st, g, p.sms));
+    }
+    GPFY_K(dr_from_psi_kernel, (unsigned)((npts + 255) / 256), 256, 0, st, ws + p.o_psi, p.npsi, p.nc, ws + p.o_R, mul_r, npts, ws + p.o_dr);
+    GPFY_K(fill_kernel, (unsigned)((npts_e + 255) / 256), 256, 0, st, ws + p.o_cq, npts_e, 1.0);
+    GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_wp, 0, (size_t)npts_e * 8, st));
+    {
+      ZonalBwd4Args zb;
+      zb.C = ws + p.o_C; zb.ZP = ws + p.o_dT; zb.wp = ws + p.o_wp; zb.cq = ws + p.o_cq; zb.dr = ws + p.o_dr;
+      zb.XH = ws + p.o_XH; zb.R = ws + p.o_R; zb.vhat_p = ws + p.o_vhat_p; zb.Mp = Mp; zb.M = s.M; zb.d = s.d; zb.npts = npts;
+      zb.partials = ws + p.o_partials; zb.npart = p.npart; zb.dVpart = ws + p.o_dVpart;
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd4<DIMP>(st, zb, p.sms)));
+    }
+    {
+      CrossGramArgs xa;
+      xa.P = ws + p.o_Dp; xa.Q = ws + p.o_Z; xa.ld = p.nc; xa.Mp = Mp; xa.npts = npts;
+      for (int i = 0; i < 72; ++i) xa.col0[i] = xc.col0[i];
+      xa.part = ws + p.o_xg; xa.KS = p.KSX; xa.range = round_up64((p.nc + p.KSX - 1) / p.KSX, 4); xa.accumulate = 1;
+      const int warps = (Mp / 16) * p.KSX;
+      GPFY_K(cross_gram_kernel, (warps + 3) / 4, 128, 0, st, xa);
+    }
+  }
+  const unsigned sqg = (unsigned)((Mp2 + 255) / 256);
+  GPFY_K(cross_gram_reduce_kernel, sqg, 256, 0, st, ws + p.o_xg, xc, p.KSX, Mp, s.M, deg, ws + p.o_dE);
+  GPFY_K(dd_kernel, (s.M + 3) / 4, 128, 0, st, ws + p.o_dE, (const double*)nullptr, (const double*)nullptr, ws + p.o_linv, ws + p.o_dd, s.M, Mp, 0);
+  if (dlcat) {
+    GPFY_K(dl_step1_kernel, s.F, 256, 0, st, ws + p.o_dE, (const double*)nullptr, (const double*)nullptr, ws + p.o_dvec, ws + p.o_linv, ws + p.o_tmp1, Mp, 0, deg);
+    GPFY_K(dl_step2_kernel, s.F, 256, 0, st, ws + p.o_tmp1, ws + p.o_linv, dlcat, Mp, deg);
+  }
+  if (dvhat) GPFY_K(reduce_dv_kernel, (8 * s.M * s.dim + 255) / 256, 256, 0, st, ws + p.o_dVpart, dvhat, s.M, Mp, s.dim, s.dimp, p.KSV);
+  GPFY_K(partial_sums_kernel, p.npart, 256, 0, st, ws + p.o_partials, (int)p.nblocks_c, p.npart, ws + p.o_tmp3);
+  FeatVjpFinalArgs fa;
+  fa.partials = ws + p.o_tmp3; fa.dd = ws + p.o_dd; fa.scale = degree_scale; fa.w = w; fa.b = b; fa.d = s.d;
+  fa.scalar_w = desc->weight_mode == GPFY_W_SCALAR; fa.proj = s.proj; fa.nw = s.nw; fa.apply_to_sphere = apply_to_sphere; fa.deg = deg;
+  fa.dw = dw; fa.db = db; fa.dscale = dscale;
+  GPFY_K(features_vjp_finalize_kernel, 1, 32, 0, st, fa);
   return GPFY_OK;
 }
 
@@ -1313,6 +1500,27 @@ int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, 
   const int64_t nL = (int64_t)s.P * s.M * s.M;
   GPFY_K(kl_tril_grad_kernel, (unsigned)((nL + 255) / 256), 256, 0, (cudaStream_t)stream, mu, sigma, out, s.M, s.P);
   GPFY_K(kl_tril_value_kernel, 1, 1024, 0, (cudaStream_t)stream, mu, sigma, out, s.M, s.P);
+  return GPFY_OK;
+}
+
+int gpfy_prior_kl_valgrad_ws(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out, void* workspace,
+                             size_t workspace_bytes) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (desc->q_kind == GPFY_Q_TRIL) return gpfy_prior_kl_valgrad(stream, desc, mu, sigma, out);
+  const int64_t nS = (int64_t)s.P * s.M * s.M;
+  const size_t need = (size_t)(2 * nS + s.P) * 8;
+  if (!workspace || ((uintptr_t)workspace & 15) != 0 || workspace_bytes < need) {
+    set_error("full-covariance KL needs %zu bytes of 16-byte aligned workspace", need);
+    return GPFY_EWORKSPACE;
+  }
+  double* A = (double*)workspace;
+  double* X = A + nS;
+  double* logdet = X + nS;
+  cudaStream_t st = (cudaStream_t)stream;
+  GPFY_K(kl_full_chol_kernel, s.P, 1024, 0, st, sigma, A, X, logdet, s.M);
+  GPFY_K(kl_full_grad_kernel, (unsigned)((nS + 255) / 256), 256, 0, st, mu, X, out, s.M, s.P);
+  GPFY_K(kl_full_value_kernel, 1, 1024, 0, st, mu, sigma, logdet, out, s.M, s.P);
   return GPFY_OK;
 }
 

@@ -119,6 +119,29 @@ class HotPath:
             _ptr(vhat), _ptr(lcat), _ptr(ds), int(bool(mul_r)), _ptr(out), _ptr(r), _ptr(ws), ws.numel()))
         return out, r
 
+    def features_vjp(self, X, vhat, lcat, dPhi, w=None, b=None, degree_scale=None, mul_r=False, apply_to_sphere=True):
+        """Reverse pass of `features`: cotangents {"vhat" [M, dim], "lcat" [sum m_l^2], "scale" [F], "w", "b"} of the inputs given
+        the cotangent dPhi [M, N] of the feature matrix - what jax.grad builds for polynomial_expansion / Kuf / project_fun
+        (spherical_harmonics.py:290-320, 344-362, 385-387)."""
+        X, dPhi = self._dev(X), self._dev(dPhi)
+        n = X.shape[0]
+        if tuple(dPhi.shape) != (self.M, n):
+            raise _lib.GpfyError("features_vjp: dPhi must be [M, N]")
+        vhat, lcat = self._dev(vhat), self._dev(lcat)
+        w = self._dev(w) if w is not None else None
+        b = self._dev(b) if b is not None else None
+        ds = self._dev(degree_scale) if degree_scale is not None else None
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        out = {"vhat": z(self.M, self.dim), "lcat": z(self.lsize), "scale": z(self.F)}
+        if apply_to_sphere:
+            out["w"], out["b"] = z(1 if self.scalar_w else self.input_dim), z(1)
+        ws = self.workspace(n, _lib.OP_FEATURES_VJP)
+        _lib.check(self.lib.gpfy_sh_features_vjp(
+            _stream(self.device), ctypes.byref(self.desc), n, _ptr(X), int(bool(apply_to_sphere)), _ptr(w), _ptr(b), _ptr(vhat),
+            _ptr(lcat), _ptr(ds), int(bool(mul_r)), _ptr(dPhi), _ptr(out["vhat"]), _ptr(out["lcat"]), _ptr(out["scale"]),
+            _ptr(out.get("w")), _ptr(out.get("b")), _ptr(ws), ws.numel()))
+        return out
+
     def elbo_valgrad_packed(self, X, Y, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out=None):
         """Packed [data term, gradients] for the rows given (sums; see GpfyElboLayout)."""
         X, Y = self._dev(X), self._dev(Y)
@@ -332,11 +355,17 @@ class HotPath:
         return dV
 
     def prior_kl_valgrad(self, mu, sigma):
-        """KL(q || N(0, I)), dKL/dmu [M, P], dKL/dSigma [P, M, M] (TriL) — variational.py:225-240."""
+        """KL(q || N(0, I)), dKL/dmu [M, P], dKL/dSigma [P, M, M] — variational.py:225-240 with :262-286 (TriL) or :375-399
+        (full covariance: Cholesky, logdet and Sigma^-1 on the device)."""
         mu, sigma = self._dev(mu), self._dev(sigma)
         M, P = self.M, self.P
         out = torch.empty((1 + M * P + P * M * M,), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.gpfy_prior_kl_valgrad(_stream(self.device), ctypes.byref(self.desc), _ptr(mu), _ptr(sigma), _ptr(out)))
+        ws = self._ws.get("kl")
+        need = (2 * P * M * M + P) * 8 if self.desc.q_kind == _lib.Q_FULLCOV else 0
+        if need and (ws is None or ws.numel() < need):
+            ws = self._ws["kl"] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.gpfy_prior_kl_valgrad_ws(_stream(self.device), ctypes.byref(self.desc), _ptr(mu), _ptr(sigma), _ptr(out),
+                                                     _ptr(ws) if need else None, need))
         return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
 
 

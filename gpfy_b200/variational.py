@@ -106,7 +106,8 @@ class VariationalDistributionTriL(VariationalDistribution):
 
 @dataclasses.dataclass(frozen=True)
 class VariationalDistributionFullCovariance(VariationalDistribution):
-    """q(u) = N(mu, Sigma) (variational.py:354-464).  The KL needs chol(Sigma): O(M^3), N-independent, host."""
+    """q(u) = N(mu, Sigma) (variational.py:354-464).  The KL (Cholesky, logdet, Sigma^-1: O(M^3), N-independent) runs on the device
+    through gpfy_prior_kl_valgrad_ws; `logdet` / `trace` below are the host mirrors of the reference's methods."""
     name: str = "VariationalDistributionFullCovariance"
     _q_kind = "fullcov"
 
@@ -119,6 +120,10 @@ class VariationalDistributionFullCovariance(VariationalDistribution):
 
     def trace(self, param: Param):
         return np.trace(self.cov_part(param), axis1=-2, axis2=-1)
+
+    def prior_KL_and_grad(self, param: Param):
+        kl, dmu, dsig = self._hot(param).prior_kl_valgrad(self.mu(param), self.cov_part(param))
+        return float(kl), dmu.cpu().numpy(), dsig.cpu().numpy()
 
     def _dkl_dcov(self, S):
         # d/dS [-1/2 logdet S + 1/2 tr S]; the Cholesky VJP symmetrises its cotangent like jnp.linalg.cholesky

@@ -83,7 +83,7 @@ typedef struct GpfyDesc {
 } GpfyDesc;
 
 /* Which scratch size to ask for. */
-enum { GPFY_OP_FEATURES = 0, GPFY_OP_ELBO = 1, GPFY_OP_PREDICT = 2 };
+enum { GPFY_OP_FEATURES = 0, GPFY_OP_ELBO = 1, GPFY_OP_PREDICT = 2, GPFY_OP_FEATURES_VJP = 3 };
 
 /* Layout of the packed ELBO output (doubles); offsets are filled by gpfy_elbo_packed_layout.
  * Everything is a SUM over the N points passed in (no 1/N, no dataset_size scale, no KL), so ranks
@@ -133,6 +133,17 @@ GPFY_API int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n,
                          const double* degree_scale, int mul_r, double* out, double* r_out, void* workspace,
                          size_t workspace_bytes);
 
+/* Reverse pass of gpfy_sh_features_fwd: what `jax.grad` builds for polynomial_expansion / Kuf / project_fun
+ * (spherical_harmonics.py:290-320, 344-362, 385-387), so the feature matrix is differentiable on its own (jax.custom_vjp's bwd).
+ * Same X / apply_to_sphere / w / b / vhat / lcat / degree_scale / mul_r as the forward call; dPhi [M, N] is the cotangent of `out`.
+ * Outputs (each may be NULL): dvhat [M, dim] and dlcat [sum m_l^2] (lower triangles) w.r.t. the inputs `vhat`, `lcat`;
+ * dscale [F] w.r.t. degree_scale; dw [d] or [1] and db [1] w.r.t. weight_variances / bias_variance (apply_to_sphere != 0 only).
+ * Uses GPFY_OP_FEATURES_VJP scratch.  Not built for GPFY_W_PROJECTION weights or degree blocks wider than 112 rows. */
+GPFY_API int gpfy_sh_features_vjp(void* stream, const GpfyDesc* desc, int64_t n, const double* X, int apply_to_sphere, const double* w,
+                         const double* b, const double* vhat, const double* lcat, const double* degree_scale, int mul_r,
+                         const double* dPhi, double* dvhat, double* dlcat, double* dscale, double* dw, double* db, void* workspace,
+                         size_t workspace_bytes);
+
 /* Fused ELBO data term and all its gradients (replaces optimization.py:125-156 `elbo` composed with
  * model.py:201-229 `predict_diag`, and the reverse pass `jax.value_and_grad` builds at
  * optimization.py:113-118), for the N rows given.  Inputs are the CONSTRAINED parameters:
@@ -173,8 +184,13 @@ GPFY_API int gpfy_inducing_basis_vjp(void* stream, const GpfyDesc* desc, const d
 
 /* KL(q || N(0, I)) and its gradients (replaces variational.py:225-240 with :262-286 / :375-399).
  * out: [1 + M*P + P*M*M] = KL, dKL/dmu, dKL/dSigma.  TriL only reads diag/all of L; full covariance
- * needs a Cholesky of Sigma and is left to the host framework (returns GPFY_EUNSUPPORTED). */
+ * needs a Cholesky of Sigma, i.e. scratch: this entry returns GPFY_EUNSUPPORTED for it, gpfy_prior_kl_valgrad_ws serves both. */
 GPFY_API int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out);
+/* The same for either q_kind, with scratch: the full-covariance KL (variational.py:375-399: logdet through
+ * chol(Sigma), trace of Sigma; dKL/dSigma = 1/2 I - 1/2 Sigma^-1, the symmetrised cotangent jnp.linalg.cholesky gives) runs on
+ * the device with 2 P M^2 doubles of workspace (Cholesky factor and its inverse).  TriL ignores the workspace. */
+GPFY_API int gpfy_prior_kl_valgrad_ws(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out,
+                             void* workspace, size_t workspace_bytes);
 
 /* Predictive mean and diagonal variance (replaces model.py:201-229 `GP.predict_diag` with the
  * conditional of :103-145): fmu, fvar are [N, P]. */

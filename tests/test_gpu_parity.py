@@ -67,6 +67,42 @@ def test_features_match_reference_golden(name):
         hp.features(g["X"], vhat, lcat, w=pack["w"], b=pack["b"], out=(bufs[0][:, :-1], bufs[1]))
 
 
+@pytest.mark.parametrize("name", [c for c in ARD_CASES if "proj" not in c])
+def test_features_vjp_matches_oracle_autograd(name):
+    """gpfy_sh_features_vjp: the feature matrix is differentiable on its own, as under jax.grad in the reference
+    (polynomial_expansion / Kuf / project_fun, spherical_harmonics.py:290-320, 344-362, 385-387).  Cotangents of Vhat, the
+    Cholesky factors, the per-degree scale, weight_variances and bias_variance against torch autograd on the oracle."""
+    g, pack = _resolved(name)
+    hp = _hot(pack, g)
+    vhat, lcat = _cat(pack)
+    F = len(pack["V"])
+    rng = np.random.default_rng(3)
+    M, N = hp.M, g["X"].shape[0]
+    dPhi = rng.standard_normal((M, N))
+    scale = np.sqrt(pack["eig"] * pack["v"])
+    # raw X, projection A = scale_l r Phi
+    got = hp.features_vjp(g["X"], vhat, lcat, dPhi, w=pack["w"], b=pack["b"], degree_scale=scale, mul_r=True)
+    V = [O.T(v).requires_grad_(True) for v in pack["V"]]
+    L = [O.T(l).requires_grad_(True) for l in pack["L"]]
+    w, b, sc = O.T(pack["w"]).requires_grad_(True), O.T(pack["b"]).requires_grad_(True), O.T(scale).requires_grad_(True)
+    Xs, r = O.to_sphere(w, b, O.T(g["X"]))
+    Phi = O.polynomial_expansion(V, L, pack["alpha"], Xs)
+    rows = torch.cat([sc[l].expand(v.shape[0]) for l, v in enumerate(pack["V"])])
+    (torch.sum(O.T(dPhi) * Phi * r[None, :] * rows[:, None])).backward()
+    assert rel_err(got["vhat"].cpu().numpy(), np.concatenate([v.grad.numpy() for v in V], 0)) < TOL
+    assert rel_err(got["lcat"].cpu().numpy(), np.concatenate([np.tril(l.grad.numpy()).ravel() for l in L])) < TOL
+    assert rel_err(got["scale"].cpu().numpy(), sc.grad.numpy()) < TOL
+    assert rel_err(got["w"].cpu().numpy(), np.atleast_1d(w.grad.numpy()).ravel()) < TOL
+    assert rel_err(got["b"].cpu().numpy().ravel(), np.atleast_1d(b.grad.numpy())) < TOL
+    # points already on the sphere (what polynomial_expansion receives), no scale, no radius
+    got2 = hp.features_vjp(g["o_x_sphere"], vhat, lcat, dPhi, apply_to_sphere=False)
+    V2 = [O.T(v).requires_grad_(True) for v in pack["V"]]
+    L2 = [O.T(l).requires_grad_(True) for l in pack["L"]]
+    (torch.sum(O.T(dPhi) * O.polynomial_expansion(V2, L2, pack["alpha"], O.T(g["o_x_sphere"])))).backward()
+    assert rel_err(got2["vhat"].cpu().numpy(), np.concatenate([v.grad.numpy() for v in V2], 0)) < TOL
+    assert rel_err(got2["lcat"].cpu().numpy(), np.concatenate([np.tril(l.grad.numpy()).ravel() for l in L2])) < TOL
+
+
 @pytest.mark.parametrize("name", ARD_CASES)
 def test_predict_diag_matches_reference_golden(name):
     g, pack = _resolved(name)
@@ -132,3 +168,30 @@ def test_prior_kl_matches_reference_golden(name):
     assert rel_err(dmu.cpu().numpy(), mu_t.grad.numpy()) < TOL
     # the reference differentiates the dense Sigma; entries above the diagonal get d/dL (1/2 L^2) = L = 0 there
     assert rel_err(dsig.cpu().numpy(), L_t.grad.numpy()) < TOL
+
+
+def test_prior_kl_full_covariance_on_device_matches_reference_golden():
+    """variational.py:375-399 on the device (gpfy_prior_kl_valgrad_ws): Cholesky logdet, trace and the symmetrised dKL/dSigma."""
+    g, pack = _resolved("d4_fullcov_fixedV")
+    hp = _hot(pack, g)
+    kl, dmu, dsig = hp.prior_kl_valgrad(pack["mu"], pack["Sigma"])
+    assert abs(float(kl) - float(g["o_KL"])) <= TOL * abs(float(g["o_KL"]))
+    mu_t = O.T(pack["mu"]).requires_grad_(True)
+    S_t = O.T(pack["Sigma"]).requires_grad_(True)
+    O.prior_KL(mu_t, S_t, tril=False).backward()
+    assert rel_err(dmu.cpu().numpy(), mu_t.grad.numpy()) < TOL
+    sym = 0.5 * (S_t.grad.numpy() + np.swapaxes(S_t.grad.numpy(), -1, -2))
+    assert rel_err(dsig.cpu().numpy(), sym) < TOL
+    # a larger, worse-conditioned covariance: M = 280
+    rng = np.random.default_rng(0)
+    from gpfy_b200.ops import HotPath
+    M = 280
+    hp2 = HotPath(8, [1, 9] + [30] * 9, q_kind="fullcov")
+    B = rng.standard_normal((M, M)) / np.sqrt(M)
+    S = (B @ B.T + 0.05 * np.eye(M))[None]
+    mu = rng.standard_normal((M, 1))
+    kl2, dmu2, dsig2 = hp2.prior_kl_valgrad(mu, S)
+    L = np.linalg.cholesky(S[0])
+    ref = -0.5 * M - np.sum(np.log(np.diag(L))) + 0.5 * np.sum(mu ** 2) + 0.5 * np.trace(S[0])
+    assert abs(float(kl2) - ref) <= TOL * abs(ref)
+    assert rel_err(dsig2.cpu().numpy()[0], 0.5 * np.eye(M) - 0.5 * np.linalg.inv(S[0])) < 1e-9
