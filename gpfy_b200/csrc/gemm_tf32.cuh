@@ -212,12 +212,14 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-// x -> (hi, lo) float planes: hi = x truncated to TF32 (sign, exponent, 10 mantissa bits), lo = tf32(x - hi)
+// x -> (hi, lo) float planes, both exactly representable in TF32 (10 explicit mantissa bits): hi = x rounded to nearest,
+// lo = (x - hi) rounded to nearest.  Rounding (not truncating) matters: a truncated lo is biased towards zero by up to
+// 2^-22 |x|, the bias does not average out over the sum and the eigenvalue gradient - a difference of large terms - amplified
+// it to 1.5e-5 (measured, r02h); rounded, the representation error is +-2^-24 |x| and unbiased.
+__device__ __forceinline__ float tf32_round(float f) { return __uint_as_float((__float_as_uint(f) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void tf32_split(double x, float& hi, float& lo) {
-  const float f = (float)x;
-  hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);
-  const float l = (float)(x - (double)hi);
-  lo = __uint_as_float(__float_as_uint(l) & 0xFFFFE000u);
+  hi = tf32_round((float)x);
+  lo = tf32_round((float)(x - (double)hi));
 }
 __global__ void tf32_split_kernel(const double* __restrict__ x, float* hi, float* lo, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -15,6 +15,7 @@
 #include "zonal_fwd2.cuh"
 #include "basis.cuh"
 #include "features_vjp.cuh"
+#include "syrk_tf32.cuh"
 
 namespace gpfy {
 
@@ -516,8 +517,10 @@ struct Plan {
   int npart;
   // offsets (doubles)
   int64_t o_sw, o_sb, o_dvec, o_vhat_p, o_mu2, o_linv, o_E, o_ET, o_tmp1, o_tmp2, o_tmp3, o_LqP, o_W0, o_W2, o_dE, o_Gz, o_bz,
-      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, o_W2f, o_Zf, o_Dp, o_xg, total;
+      o_dd, o_partials, o_Gpart, o_bzpart, o_dVpart, o_Z, o_C, o_XH, o_R, o_wq, o_wp, o_mz, o_psi, o_cq, o_dr, o_dT, o_W2f, o_Zf, o_Dp, o_xg, o_G32, o_bz32, total;
   int KSX;          // cross-Gram splits (features VJP)
+  bool f32s;        // the weighted Gram matrix also runs on tcgen05 (syrk_tf32x3_kernel): no fp64 Z panel is written at all
+  int H32, NC32, KS32;  // its column parts, columns per part, point splits
   bool f32;         // GPFY_PREC_TF32X3: float hi / lo planes of W2 (o_W2f) and Z (o_Zf) for the tcgen05 contraction
   int npsi;
 };
@@ -615,6 +618,10 @@ static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, bool f32 = 
   // two float planes = one double per element
   p->o_W2f = take(f32 ? (int64_t)s.P * Mp2 : 0);
   p->o_Zf = take(f32 && op != GPFY_OP_FEATURES ? Mp * p->nc : 0);
+  p->f32s = f32 && op == GPFY_OP_ELBO && s.P == 1 && s32_plan(s.Mp, &p->H32, &p->NC32) && !debug_option(DBG_NO_SYRK32);
+  p->KS32 = p->f32s ? std::max(1, p->sms / p->H32) : 0;
+  p->o_G32 = take(p->f32s ? (int64_t)p->KS32 * Mp2 : 0);
+  p->o_bz32 = take(p->f32s ? (int64_t)p->KS32 * Mp : 0);
   p->KSX = std::max(1, (8 * p->sms) / std::max(1, s.Mp / 16));
   p->o_Dp = take(fvjp ? Mp * p->nc : 0);
   p->o_xg = take(fvjp ? (int64_t)p->KSX * Mp * XG_W : 0);
@@ -931,6 +938,29 @@ static int launch_gemm32(cudaStream_t st, const Plan& p, double* ws, int q, int6
   return GPFY_OK;
 }
 
+// G += Z diag(wq) Z^T, bz += Z wp over npts points of the chunk planes, on tcgen05 (P = 1)
+static int launch_syrk32(cudaStream_t st, const Plan& p, double* ws, int64_t npts) {
+  const Shape& s = p.s;
+  const int Mp = s.Mp;
+  float* zh = reinterpret_cast<float*>(ws + p.o_Zf);
+  float* zl = zh + (int64_t)Mp * p.nc;
+  Syrk32Args sa;
+  sa.nbox = (Mp + 255) / 256;
+  while (Mp % sa.nbox || (Mp / sa.nbox) % 8) ++sa.nbox;
+  Syrk32Maps maps;
+  GPFY_TRY(make_map_f32(&maps.zh, zh, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, (uint32_t)(Mp / sa.nbox), CU_TENSOR_MAP_SWIZZLE_128B));
+  GPFY_TRY(make_map_f32(&maps.zl, zl, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, (uint32_t)(Mp / sa.nbox), CU_TENSOR_MAP_SWIZZLE_128B));
+  sa.wq = ws + p.o_wq; sa.wp = ws + p.o_wp; sa.Mp = Mp; sa.NC = p.NC32; sa.H = p.H32; sa.ntile = (Mp + 127) / 128;
+  sa.npts = npts; sa.range = round_up64((npts + p.KS32 - 1) / p.KS32, 32);
+  sa.Gpart = ws + p.o_G32; sa.bzpart = ws + p.o_bz32;
+  const int smem = s32_smem_bytes(Mp, p.NC32);
+  GPFY_TRY(set_smem(syrk_tf32x3_kernel, smem));
+  syrk_tf32x3_kernel<<<p.H32 * p.KS32, S32_THREADS, smem, st>>>(maps, sa);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
 // Shared prologue: sqrt weights, padded Vhat, Linv, E = diag(sqrt(eig v)) Linv, E^T, and per output
 // W0 = L L^T - I (or Sigma - I), W2 = E^T W0 E, mu2 = E^T mu.
 static int run_prologue(cudaStream_t st, const GpfyDesc* desc, const Plan& p, double* ws, const double* w, const double* b,
@@ -1222,7 +1252,7 @@ int gpfy_sh_features_vjp(void* stream, const GpfyDesc* desc, int64_t n, const do
       CrossGramArgs xa;
       xa.P = ws + p.o_Dp; xa.Q = ws + p.o_Z; xa.ld = p.nc; xa.Mp = Mp; xa.npts = npts;
       for (int i = 0; i < 72; ++i) xa.col0[i] = xc.col0[i];
-      xa.part = ws + p.o_xg; xa.KS = p.KSX; xa.range = round_up64((p.nc + p.KSX - 1) / p.KSX, 4); xa.accumulate = 1;
+      xa.part = ws + p.o_xg; xa.KS = p.KSX; xa.range = round_up64((npts + p.KSX - 1) / p.KSX, 4); xa.accumulate = 1;
       const int warps = (Mp / 16) * p.KSX;
       GPFY_K(cross_gram_kernel, (warps + 3) / 4, 128, 0, st, xa);
     }
@@ -1276,6 +1306,7 @@ int gpfy_svgp_elbo_begin(void* stream, const GpfyDesc* desc, int64_t n_capacity,
     GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
     GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)(s.Mp + s.M) * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
   }
+  if (p.f32s) GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_G32, 0, (size_t)(p.o_bz32 - p.o_G32 + (int64_t)p.KS32 * s.Mp) * 8, st));
   return GPFY_OK;
 }
 
@@ -1308,6 +1339,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     if (fuse_lik) { za.Yg = Y + c0; za.s2g = sigma2; za.wq = ws + p.o_wq; za.wp = ws + p.o_wp; za.cq = ws + p.o_cq; }
     za.ZPb = bwd4 ? ws + p.o_dT : nullptr;   // the derivative panel takes the place of the legacy path's dT buffer
     if (p.f32) { za.Zh = reinterpret_cast<float*>(ws + p.o_Zf); za.Zl = za.Zh + (int64_t)Mp * p.nc; }
+    if (p.f32s) za.Z = nullptr;   // both contractions read the float planes: the fp64 panel is not written
     {
       GPFY_TIMED(TK_ZONAL_FWD, st);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
@@ -1376,6 +1408,10 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd<DIMP>(st, zb)));
     }
 
+    if (p.f32s) {
+      GPFY_TIMED(TK_SYRK, st);
+      GPFY_TRY(launch_syrk32(st, p, ws, npts));
+    } else
     for (int q = 0; q < s.P; ++q) {
       GPFY_TIMED(TK_SYRK, st);
       SyrkArgs sa;
@@ -1383,7 +1419,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       sa.wq = ws + p.o_wq + (int64_t)q * p.nc; sa.wp = ws + p.o_wp + (int64_t)q * p.nc;
       sa.Gpart = ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B;
       sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B;
-      sa.split = p.split; sa.chunk = p.nc;
+      sa.split = p.split; sa.chunk = npts;   // the splits cover THIS launch's rows (a short slab still uses every CTA)
       sa.accumulate = 1;
       GPFY_TRY(device_configure_once(DEV_CFG_SYRK, (const void*)syrk_dmma_kernel, SYRK_SMEM));
       GPFY_K(syrk_dmma_kernel, p.split.total(), SYRK_THREADS, SYRK_SMEM, st, sa);
@@ -1392,7 +1428,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     if (!fused && !bwd4) {
       DvhatArgs da;
       da.dT = ws + p.o_dT; da.ldz = p.nc; da.XH = ws + p.o_XH; da.dimp = s.dimp; da.Mp = Mp; da.npts = npts;
-      da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((p.nc + p.KSV - 1) / p.KSV, 16);
+      da.dVpart = ws + p.o_dVpart; da.KS = p.KSV; da.range = round_up64((npts + p.KSV - 1) / p.KSV, 16);
       da.accumulate = 1;
       GPFY_TIMED(TK_DVHAT, st);
       GPFY_TRY(launch_dvhat(st, da));
@@ -1419,8 +1455,12 @@ int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity
   for (int q = 0; q < s.P; ++q) {
     double* Gz = ws + p.o_Gz;
     double* bz = ws + p.o_bz + (int64_t)q * Mp;
-    GPFY_K(reduce_g_kernel, sqg, 256, 0, st, ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B,
-           ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B, Gz, bz, Mp, p.split);
+    if (p.f32s) {
+      GPFY_K(reduce_g32_kernel, sqg, 256, 0, st, ws + p.o_G32, ws + p.o_bz32, Gz, bz, Mp, p.KS32);
+    } else {
+      GPFY_K(reduce_g_kernel, sqg, 256, 0, st, ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B,
+             ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B, Gz, bz, Mp, p.split);
+    }
     GPFY_TRY(gemm_sq(st, ws + p.o_E, Gz, ws + p.o_tmp1, Mp, 1.0, 0.0, p.sms));             // T1 = E Gz
     GPFY_TRY(gemm_sq(st, ws + p.o_tmp1, ws + p.o_ET, ws + p.o_tmp2, Mp, 1.0, 0.0, p.sms));  // dW0 = T1 E^T
     double* dsig = packed + lay.d_sigma + (int64_t)q * s.M * s.M;

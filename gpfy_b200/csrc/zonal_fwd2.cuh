@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
         }
       }
       if (row < a.M) {
-        if (!(args.dbg & 1))
+        if (!(args.dbg & 1) && a.Z)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int64_t n0 = p0 + 8 * nt + 2 * t4;
@@ -202,10 +202,9 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
             tf32_split(z[2 * nt], h0, l0);
             tf32_split(z[2 * nt + 1], h1, l1);
             if (n0 + 1 >= a.npts) { h1 = 0.f; l1 = 0.f; }
-            if (n0 < a.npts) {
-              *reinterpret_cast<float2*>(a.Zh + (int64_t)row * a.ldz + n0) = make_float2(h0, h1);
-              *reinterpret_cast<float2*>(a.Zl + (int64_t)row * a.ldz + n0) = make_float2(l0, l1);
-            }
+            if (n0 >= a.npts) { h0 = 0.f; l0 = 0.f; }   // the rest of the last 32-point block is zero filled (tcgen05 k-blocks)
+            *reinterpret_cast<float2*>(a.Zh + (int64_t)row * a.ldz + n0) = make_float2(h0, h1);
+            *reinterpret_cast<float2*>(a.Zl + (int64_t)row * a.ldz + n0) = make_float2(l0, l1);
           }
         }
         if (a.mz) {

@@ -165,18 +165,18 @@ class HotPath:
 
     @staticmethod
     def slab_bounds(n, cap, unit=1024):
-        """Row boundaries of the streamed slabs.  Nothing can overlap the copy of the FIRST slab, so the slabs ramp up:
-        about cap / 16, cap / 4, then slabs of `cap` rows (one internal chunk each).  With slab = chunk = half a rank's
-        shard (8 GPUs, N = 10 M) half of the H2D time used to be exposed; now it is 1/32 of it.  Every slab but the last
-        is a multiple of `unit` = 192 * SMs rows, a whole number of GEMM tile rounds per SM (no tail wave)."""
+        """Row boundaries of the streamed slabs.  Nothing can overlap the copy of the FIRST slab, so it is small (two tile
+        rounds, 2 * unit rows) and the slabs then grow by 1.5 x up to `cap` rows (one internal chunk): a slab's copy has to
+        land while its predecessor is being processed, and with eight ranks sharing the host's memory bandwidth a copy
+        costs ~0.6 of the compute time of the same rows (measured, r02c: a 5 x ramp stalled the compute stream and made
+        the 8-GPU e2e figure worse than no ramp).  Every slab but the last is a multiple of `unit` = 192 * SMs rows, a
+        whole number of GEMM tile rounds per SM."""
         n, cap, unit = int(n), int(cap), max(1, int(unit))
-        bounds = [0]
-        for frac in (16, 4):
-            step = max(unit, cap // frac // unit * unit)
-            if bounds[-1] + step + cap // 4 < n and step <= cap:
-                bounds.append(bounds[-1] + step)
+        bounds, step = [0], 2 * unit
         while bounds[-1] < n:
-            bounds.append(min(n, bounds[-1] + cap))
+            step = min(cap, max(unit, step // unit * unit))
+            bounds.append(min(n, bounds[-1] + step))
+            step = step * 3 // 2 + unit - 1
         return bounds
 
     def elbo_valgrad_host(self, X_host, Y_host, w, b, variance, eig, vhat, lcat, mu, sigma, sigma2, out_host=None, reduce=None):
@@ -369,7 +369,7 @@ class HotPath:
         return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
 
 
-DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4}
+DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4, "no_syrk32": 5}
 
 
 def debug_option(name, value):

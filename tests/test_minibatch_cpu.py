@@ -47,15 +47,16 @@ def test_bad_arguments_are_reported():
 
 
 def test_streamed_slab_bounds_ramp_and_cover():
-    """HotPath.slab_bounds: slabs cover [0, n) exactly, none exceeds the workspace capacity, and the first one is small
-    (<= cap / 16) whenever there is more than a chunk and a quarter of data (its copy cannot overlap any compute)."""
+    """HotPath.slab_bounds: slabs cover [0, n) exactly, none exceeds the workspace capacity, every slab but the last is a
+    whole number of tile rounds, the first one is two rounds (its copy cannot overlap any compute) and no slab is more than
+    1.5 x (+ one round) its predecessor, so a slab's copy fits under the processing of the one before."""
     from gpfy_b200.ops import HotPath
-    for n, cap in ((10_000_000, 909_312), (1_250_000, 625_152), (1, 1), (31, 128), (1000, 1024), (150_001, 150_016),
+    unit = 192 * 148
+    for n, cap in ((10_000_000, 909_312), (1_250_000, 625_152), (1, 128), (31, 128), (1000, 1024), (150_001, 150_016),
                    (2_000_000, 681_984), (909_312, 909_312), (909_313, 909_312)):
-        unit = 192 * 148
         b = HotPath.slab_bounds(n, cap, unit)
         sizes = [y - x for x, y in zip(b[:-1], b[1:])]
-        assert b[0] == 0 and b[-1] == n and all(0 < s <= cap for s in sizes), (n, cap, b)
-        assert all(s % unit == 0 for s in sizes[:-1]) or len(sizes) == 1
-        if n > 2 * cap:
-            assert sizes[0] <= max(unit, cap // 16) and sizes[1] <= cap // 4
+        assert b[0] == 0 and b[-1] == n and all(0 < s <= max(cap, unit) for s in sizes), (n, cap, b)
+        assert all(s % unit == 0 or s == cap for s in sizes[:-1])
+        assert sizes[0] <= 2 * unit
+        assert all(y <= 1.5 * x + unit for x, y in zip(sizes[:-1], sizes[1:-1] or sizes[1:]))

@@ -136,6 +136,72 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ M
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// variant 4: both operands K-major with the 64-byte swizzle (layout type 4, rows of 16 tf32 = 64 B, 8-row atoms of 512 B):
+// k-blocks of 16 instead of 32, i.e. half the bytes per pipeline stage (the weighted-Gram kernel wants 4 stages).
+__global__ void __launch_bounds__(128, 1) probe_sw64_kernel(const __grid_constant__ Maps maps, float* D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_hi = smem;                  // [128 x 16] = 8 KB
+  uint8_t* a_lo = smem + 8192;
+  uint8_t* b_hi = smem + 16384;          // [288 x 16] = 18 KB
+  uint8_t* b_lo = smem + 16384 + 18432;
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { mbar_init(&bar_full, 1); mbar_init(&bar_mma, 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  if (tid == 0) {
+    for (int kb = 0; kb < K / 16; ++kb) {
+      mbar_expect_tx(&bar_full, 2 * 8192 + 2 * 18432);
+      tma_load_2d(a_hi, &maps.a_hi, kb * 16, 0, &bar_full);
+      tma_load_2d(a_lo, &maps.a_lo, kb * 16, 0, &bar_full);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_2d(b_hi + h * 144 * 64, &maps.b_hi, kb * 16, h * 144, &bar_full);
+        tma_load_2d(b_lo + h * 144 * 64, &maps.b_lo, kb * 16, h * 144, &bar_full);
+      }
+      mbar_wait(&bar_full, kb & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      for (int ks = 0; ks < 2; ++ks)
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t d = tmem + h * NH;
+          const uint64_t dah = smem_desc(smem_u32(a_hi) + ks * 32, 16, 512, 4), dal = smem_desc(smem_u32(a_lo) + ks * 32, 16, 512, 4);
+          const uint64_t dbh = smem_desc(smem_u32(b_hi) + h * 144 * 64 + ks * 32, 16, 512, 4);
+          const uint64_t dbl = smem_desc(smem_u32(b_lo) + h * 144 * 64 + ks * 32, 16, 512, 4);
+          umma_tf32(d, dal, dbh, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32(d, dah, dbl, idesc, 1u);
+          umma_tf32(d, dah, dbh, idesc, 1u);
+        }
+      umma_commit(&bar_mma);
+      mbar_wait(&bar_mma, kb & 1);
+    }
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -180,19 +246,24 @@ int main() {
   CK(cudaMalloc(&dBh, N * K * 4)); CK(cudaMalloc(&dBl, N * K * 4)); CK(cudaMalloc(&dAh, M * K * 4)); CK(cudaMalloc(&dAl, M * K * 4)); CK(cudaMalloc(&dD, M * N * 4));
   CK(cudaMemcpy(dBh, Bh.data(), N * K * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dBl, Bl.data(), N * K * 4, cudaMemcpyHostToDevice));
   const int smem = 32768 + 2 * 36864 + 1024;
-  const uint32_t cand[4][2] = {{0, 0}, {4096, 512}, {512, 4096}, {4096, 1024}};   // (LBO, SBO) candidates of the MN-major operand
-  for (int variant = 0; variant < 4; ++variant) {
+  const uint32_t cand[5][2] = {{0, 0}, {4096, 512}, {512, 4096}, {4096, 1024}, {16, 512}};   // (LBO, SBO) candidates of the MN-major operand
+  for (int variant = 0; variant < 5; ++variant) {
     std::vector<double> Ax(M * K);
-    if (variant == 0) Ax = A;
+    if (variant == 0 || variant == 4) Ax = A;
     else for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) Ax[k * M + m] = A[m * K + k];   // [k][m]: MN-major
     std::vector<float> Ah, Al; split(Ax, Ah, Al);
     CK(cudaMemcpy(dAh, Ah.data(), M * K * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dAl, Al.data(), M * K * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dD, 0, M * N * 4));
     Maps maps;
     if (variant == 0) { maps.a_hi = make_map(enc, dAh, K, M, 32, 128); maps.a_lo = make_map(enc, dAl, K, M, 32, 128); }
+    else if (variant == 4) { maps.a_hi = make_map(enc, dAh, K, M, 16, 128, CU_TENSOR_MAP_SWIZZLE_64B); maps.a_lo = make_map(enc, dAl, K, M, 16, 128, CU_TENSOR_MAP_SWIZZLE_64B); }
     else { maps.a_hi = make_map(enc, dAh, M, K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); maps.a_lo = make_map(enc, dAl, M, K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); }
     maps.b_hi = make_map(enc, dBh, K, N, 32, 144); maps.b_lo = make_map(enc, dBl, K, N, 32, 144);
-    if (variant == 0) {
+    if (variant == 4) {
+      maps.b_hi = make_map(enc, dBh, K, N, 16, 144, CU_TENSOR_MAP_SWIZZLE_64B); maps.b_lo = make_map(enc, dBl, K, N, 16, 144, CU_TENSOR_MAP_SWIZZLE_64B);
+      CK(cudaFuncSetAttribute(probe_sw64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      probe_sw64_kernel<<<1, 128, smem>>>(maps, dD);
+    } else if (variant == 0) {
       CK(cudaFuncSetAttribute(probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       probe_kernel<0><<<1, 128, smem>>>(maps, dD, 0, 0);
     } else {
@@ -206,7 +277,7 @@ int main() {
     double maxerr = 0, maxref = 0; int bad = 0;
     for (int i = 0; i < M * N; ++i) { double e = fabs(D[i] - ref[i]); if (e > maxerr) maxerr = e; if (fabs(ref[i]) > maxref) maxref = fabs(ref[i]); if (e > 1e-4) ++bad; }
     printf("variant %d (%s, LBO %u SBO %u): max abs err %.3e, max |ref| %.3e, rel %.3e, entries off by > 1e-4: %d  D[0..3] = %g %g %g %g  ref = %g %g %g %g\n", variant,
-           variant ? "A MN-major" : "A K-major", cand[variant][0], cand[variant][1], maxerr, maxref, maxerr / maxref, bad, D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+           variant == 4 ? "A, B K-major 64 B swizzle" : (variant ? "A MN-major" : "A K-major"), cand[variant][0], cand[variant][1], maxerr, maxref, maxerr / maxref, bad, D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
     fflush(stdout);
   }
   return 0;
