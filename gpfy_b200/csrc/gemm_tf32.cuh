@@ -30,13 +30,13 @@ constexpr int G32_THREADS = 192, G32_BM = 128, G32_BK = 32, G32_NSA = 2;
 constexpr int G32_A_STAGE = 2 * 4 * 4096;   // two planes x four 32-point chunks x (32 features x 128 B)
 
 struct Gemm32Maps {
-  CUtensorMap zh, zl;   // [Mp rows (feature)][ld cols (point)] float, box 32 points x 32 features, 128 B swizzle
+  CUtensorMap zh, zl;   // tile-contiguous planes [n / 32][Mp][32] viewed as [tiles * Mp rows][32 cols], box 32 points x 32 features
   CUtensorMap wh, wl;   // [Mp rows][Mp cols] float, box 32 (k) x Mp / 2 rows, 128 B swizzle
 };
 
 struct Gemm32Args {
-  const float* Zh;      // for the psi epilogue (the same panels the TMA maps describe)
-  const float* Zl;
+  const float* Zh;      // for the psi epilogue (the same planes the TMA maps describe): element (row, n) at
+  const float* Zl;      //   ((n >> 5) * Mp + row) * 32 + (n & 31)   - every 32-point block of all Mp rows is contiguous
   int64_t ldz;
   double* C;            // [tiles32][Mp][32] blocked + swizzled (the layout of GemmArgs::c_blocked), or null (psi only)
   double* psi;          // [ldz] z_n . C_n, or null
@@ -68,6 +68,16 @@ __device__ __forceinline__ uint64_t g32_desc(uint32_t addr, uint32_t lbo_bytes, 
 __device__ __forceinline__ void g32_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// The single issuing thread is the bottleneck of these kernels unless an MMA costs it only a handful of instructions
+// (measured r02h: ~300 cycles of issue per MMA with the descriptors rebuilt each time, 72 cycles of tensor work): the
+// descriptor is split into its constant high word and a low word = (address >> 4) | (LBO >> 4) << 16, advanced by adds.
+__device__ __forceinline__ uint32_t g32_desc_hi(uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29); }
+__device__ __forceinline__ uint32_t g32_desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ void g32_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n"
+               ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void g32_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g32_smem_u32(bar)) : "memory");
@@ -123,9 +133,10 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
             uint8_t* dst = sA + st * G32_A_STAGE;
             mbar_expect_tx(&a_full[st], G32_A_STAGE);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              g32_tma_2d(dst + c * 4096, &maps.zh, p0 + 32 * c, kb * G32_BK, &a_full[st]);
-              g32_tma_2d(dst + 16384 + c * 4096, &maps.zl, p0 + 32 * c, kb * G32_BK, &a_full[st]);
+            for (int c = 0; c < 4; ++c) {   // chunk c = the 32-point block (p0 / 32 + c): 32 consecutive rows of it are 4 KB of HBM
+              const int row = ((p0 >> 5) + c) * Mp + kb * G32_BK;
+              g32_tma_2d(dst + c * 4096, &maps.zh, 0, row, &a_full[st]);
+              g32_tma_2d(dst + 16384 + c * 4096, &maps.zl, 0, row, &a_full[st]);
             }
             ++ia;
           }
@@ -146,6 +157,7 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B tf32, A MN-major, B K-major, N = NH, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(G32_BM >> 4) << 24);
+      const uint32_t hiA = g32_desc_hi(512, 1), hiB = g32_desc_hi(1024, 2);
       int ia = 0, ib = 0;
       for (int it = 0; it < n_my; ++it) {
         if (it > 0) mbar_wait(&d_empty, (unsigned)((it - 1) & 1));   // the epilogue has drained the accumulator
@@ -160,14 +172,14 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t bh = g32_smem_u32(sB + sb * b_stage), bl = bh + NH * 128;
             const uint32_t d = tmem + (uint32_t)(h * NH);
+            // A (MN-major, layout 1): 8 features = one 1 KB group of a chunk (+64 in the address field), chunks 4 KB apart;
+            // B (K-major, layout 2): 8 k = 32 B inside the swizzled row (+2)
+            const uint32_t ahl = g32_desc_lo(ah, 4096), all = g32_desc_lo(al, 4096), bhl = g32_desc_lo(bh, 16), bll = g32_desc_lo(bl, 16);
 #pragma unroll
             for (int ks = 0; ks < G32_BK / 8; ++ks) {
-              // A (MN-major): 8 features = one 1 KB group of a chunk, chunks 4 KB apart; B (K-major): 8 k = 32 B inside the swizzled row
-              const uint64_t dah = g32_desc(ah + ks * 1024, 4096, 512, 1), dal = g32_desc(al + ks * 1024, 4096, 512, 1);
-              const uint64_t dbh = g32_desc(bh + ks * 32, 16, 1024, 2), dbl = g32_desc(bl + ks * 32, 16, 1024, 2);
-              g32_mma(d, dal, dbh, idesc, (kb | ks) ? 1u : 0u);
-              g32_mma(d, dah, dbl, idesc, 1u);
-              g32_mma(d, dah, dbh, idesc, 1u);
+              g32_mma2(d, all + 64 * ks, hiA, bhl + 2 * ks, hiB, idesc, (kb | ks) ? 1u : 0u);
+              g32_mma2(d, ahl + 64 * ks, hiA, bll + 2 * ks, hiB, idesc, 1u);
+              g32_mma2(d, ahl + 64 * ks, hiA, bhl + 2 * ks, hiB, idesc, 1u);
             }
             g32_commit(&b_empty[sb]);      // frees the B stage once the MMAs above have read it
             ++ib;
@@ -191,14 +203,14 @@ __global__ void __launch_bounds__(G32_THREADS, 1) gemm_tf32x3_kernel(const __gri
       for (int c0 = 0; c0 < Mp; c0 += 32) {
         uint32_t v[32];
         g32_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
-        const float* zh = a.Zh + (int64_t)c0 * a.ldz + n;
-        const float* zl = a.Zl + (int64_t)c0 * a.ldz + n;
+        const float* zh = a.Zh + ((p0 >> 5) * (int64_t)Mp + c0) * 32 + lane;
+        const float* zl = a.Zl + ((p0 >> 5) * (int64_t)Mp + c0) * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int row = c0 + j;
           const float cv = __uint_as_float(v[j]);
           if (ctile) ctile[row * 32 + (lane ^ ((row & 3) << 2))] = (double)cv;
-          if (a.psi) psi = fma((double)zh[(int64_t)j * a.ldz] + (double)zl[(int64_t)j * a.ldz], (double)cv, psi);
+          if (a.psi) psi = fma((double)zh[j * 32] + (double)zl[j * 32], (double)cv, psi);
         }
       }
       if (a.psi && n < a.npts) a.psi[n] = psi;

@@ -620,7 +620,7 @@ static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, bool f32 = 
   p->o_Zf = take(f32 && op != GPFY_OP_FEATURES ? Mp * p->nc : 0);
   p->f32s = f32 && op == GPFY_OP_ELBO && s.P == 1 && s32_plan(s.Mp, &p->H32, &p->NC32) && !debug_option(DBG_NO_SYRK32);
   p->KS32 = p->f32s ? std::max(1, p->sms / p->H32) : 0;
-  p->o_G32 = take(p->f32s ? (int64_t)p->KS32 * Mp2 : 0);
+  p->o_G32 = take(p->f32s ? (int64_t)p->KS32 * ((Mp + 127) / 128) * Mp * 128 : 0);
   p->o_bz32 = take(p->f32s ? (int64_t)p->KS32 * Mp : 0);
   p->KSX = std::max(1, (8 * p->sms) / std::max(1, s.Mp / 16));
   p->o_Dp = take(fvjp ? Mp * p->nc : 0);
@@ -923,8 +923,9 @@ static int launch_gemm32(cudaStream_t st, const Plan& p, double* ws, int q, int6
   float* wh = reinterpret_cast<float*>(ws + p.o_W2f) + 2 * q * Mp2;
   float* wl = wh + Mp2;
   Gemm32Maps maps;
-  GPFY_TRY(make_map_f32(&maps.zh, zh, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  GPFY_TRY(make_map_f32(&maps.zl, zl, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  const uint64_t prow = (uint64_t)(p.nc / 32) * Mp;   // the tile-contiguous planes as [tiles * Mp rows][32 columns]
+  GPFY_TRY(make_map_f32(&maps.zh, zh, 32, prow, 32, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  GPFY_TRY(make_map_f32(&maps.zl, zl, 32, prow, 32, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   GPFY_TRY(make_map_f32(&maps.wh, wh, (uint64_t)Mp, (uint64_t)Mp, (uint64_t)Mp, 32, (uint32_t)(Mp / 2), CU_TENSOR_MAP_SWIZZLE_128B));
   GPFY_TRY(make_map_f32(&maps.wl, wl, (uint64_t)Mp, (uint64_t)Mp, (uint64_t)Mp, 32, (uint32_t)(Mp / 2), CU_TENSOR_MAP_SWIZZLE_128B));
   Gemm32Args ga;
@@ -948,11 +949,14 @@ static int launch_syrk32(cudaStream_t st, const Plan& p, double* ws, int64_t npt
   sa.nbox = (Mp + 255) / 256;
   while (Mp % sa.nbox || (Mp / sa.nbox) % 8) ++sa.nbox;
   Syrk32Maps maps;
-  GPFY_TRY(make_map_f32(&maps.zh, zh, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, (uint32_t)(Mp / sa.nbox), CU_TENSOR_MAP_SWIZZLE_128B));
-  GPFY_TRY(make_map_f32(&maps.zl, zl, (uint64_t)p.nc, (uint64_t)Mp, (uint64_t)p.nc, 32, (uint32_t)(Mp / sa.nbox), CU_TENSOR_MAP_SWIZZLE_128B));
+  const uint64_t prow = (uint64_t)(p.nc / 32) * Mp;
+  const CUtensorMapSwizzle swz = S32_KP == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  GPFY_TRY(make_map_f32(&maps.zh, zh, 32, prow, 32, S32_KP, (uint32_t)(Mp / sa.nbox), swz));
+  GPFY_TRY(make_map_f32(&maps.zl, zl, 32, prow, 32, S32_KP, (uint32_t)(Mp / sa.nbox), swz));
   sa.wq = ws + p.o_wq; sa.wp = ws + p.o_wp; sa.Mp = Mp; sa.NC = p.NC32; sa.H = p.H32; sa.ntile = (Mp + 127) / 128;
   sa.npts = npts; sa.range = round_up64((npts + p.KS32 - 1) / p.KS32, 32);
   sa.Gpart = ws + p.o_G32; sa.bzpart = ws + p.o_bz32;
+  sa.kf = debug_option(DBG_SYRK32_KF) > 0 ? debug_option(DBG_SYRK32_KF) : S32_KF;
   const int smem = s32_smem_bytes(Mp, p.NC32);
   GPFY_TRY(set_smem(syrk_tf32x3_kernel, smem));
   syrk_tf32x3_kernel<<<p.H32 * p.KS32, S32_THREADS, smem, st>>>(maps, sa);
@@ -1301,11 +1305,6 @@ int gpfy_svgp_elbo_begin(void* stream, const GpfyDesc* desc, int64_t n_capacity,
   // pad rows of Z are never written by the zonal kernel; accumulators start at zero
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp + 32 - s.M) * p.nc * 8, st));
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_partials, 0, (size_t)(p.o_Z - p.o_partials) * 8, st));  // partials, Gpart, bzpart, dVpart
-  if (p.f32 && s.Mp > s.M) {   // padding rows of the two float planes
-    float* zh = reinterpret_cast<float*>(ws + p.o_Zf);
-    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
-    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)(s.Mp + s.M) * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
-  }
   if (p.f32s) GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_G32, 0, (size_t)(p.o_bz32 - p.o_G32 + (int64_t)p.KS32 * s.Mp) * 8, st));
   return GPFY_OK;
 }
@@ -1456,7 +1455,7 @@ int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n_capacity
     double* Gz = ws + p.o_Gz;
     double* bz = ws + p.o_bz + (int64_t)q * Mp;
     if (p.f32s) {
-      GPFY_K(reduce_g32_kernel, sqg, 256, 0, st, ws + p.o_G32, ws + p.o_bz32, Gz, bz, Mp, p.KS32);
+      GPFY_K(reduce_g32_kernel, sqg, 256, 0, st, ws + p.o_G32, ws + p.o_bz32, Gz, bz, Mp, p.KS32, (Mp + 127) / 128);
     } else {
       GPFY_K(reduce_g_kernel, sqg, 256, 0, st, ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B,
              ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B, Gz, bz, Mp, p.split);
@@ -1581,11 +1580,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
   DegreeTable deg = degree_table(desc);
   RecCoef rc = make_rec_coef(desc->alpha);
   GPFY_TRY(run_prologue(st, desc, p, ws, w, b, variance, eig, vhat, lcat, mu, sigma, true));
-  if (p.f32 && s.Mp > s.M) {
-    float* zh = reinterpret_cast<float*>(ws + p.o_Zf);
-    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)s.M * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
-    GPFY_CUDA_OK(cudaMemsetAsync(zh + (int64_t)(s.Mp + s.M) * p.nc, 0, (size_t)(s.Mp - s.M) * p.nc * 4, st));
-  }
+
   // only the quadratic form z^T W2 z is needed: fold W2 onto its lower triangle (W_ij + W_ji below the diagonal, zero
   // above) and let the GEMM skip the k range right of each row tile's diagonal block
   for (int q = 0; q < s.P; ++q)

@@ -41,7 +41,7 @@ struct ZonalArgs {
   double* wp;           // [ldz] p r
   double* cq;           // [ldz] 2 q r^2
   double* ZPb;          // [tiles][Mp][32] blocked + swizzled derivative panel d/dt C_l^alpha(t) for zonal_bwd4, or null
-  float* Zh;            // [Mp][ldz] hi / lo TF32 planes of Z for the tcgen05 contraction (GPFY_PREC_TF32X3), or null
+  float* Zh;            // hi / lo TF32 planes of Z, tile-contiguous [n / 32][Mp][32], for the tcgen05 contractions (GPFY_PREC_TF32X3), or null
   float* Zl;
   DegreeTable deg;
   RecCoef rc;

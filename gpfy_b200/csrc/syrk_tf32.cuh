@@ -2,8 +2,9 @@
 //     G = sum_n wq_n z_n z_n^T  [Mp, Mp],     bz = sum_n wp_n z_n  [Mp]          (dSigma, dmu, dE come from these)
 // Operands are the hi / lo TF32 planes Zh / Zl [Mp][ld] the forward kernel writes (points contiguous = K-major for this
 // product, whose contraction index is the point).  A CTA (h, ks) owns the column part h (NC columns of G) and the point
-// range ks of the chunk.  Per 32-point k-block:
-//   TMA    : all Mp rows x 32 points of both planes -> the A stage (128 B swizzled rows, UTMALDG)
+// range ks of the chunk.  Per 16-point k-block (four of them in flight: the kernel is bound by the latency of the
+// TMA -> scale -> MMA chain, not by bandwidth - with two 32-point stages ncu showed 13 % issue activity and 22 ms per step):
+//   TMA    : all Mp rows x 16 points of both planes -> the A stage (64 B swizzled rows, SWIZZLE_64B, UTMALDG)
 //   scale  : four warps read the part's NC rows back from the A stage, multiply by wq_n in fp64, split into TF32 hi / lo
 //            again and write the B stage in the same swizzled layout (the weighted operand never exists in HBM); the
 //            same pass accumulates bz for the part's rows in fp64 registers
@@ -17,9 +18,12 @@
 
 namespace gpfy {
 
-constexpr int S32_THREADS = 192, S32_KF = 32, S32_NS = 2;
+// S32_KP points per k-block: 32 (128 B rows, SWIZZLE_128B, 2 stages) or 16 (64 B rows, SWIZZLE_64B, 4 stages; measured slower:
+// the fixed cost per k-block dominates, not the pipeline depth)
+constexpr int S32_THREADS = 192, S32_KP = 32, S32_RB = S32_KP * 4, S32_KF = 1024 / S32_KP, S32_NS = 64 / S32_KP;
+constexpr uint32_t S32_SBO = 8 * S32_RB, S32_LAYOUT = S32_KP == 32 ? 2u : 4u;   // 8-row atoms; layout type of the swizzle
 
-struct Syrk32Maps { CUtensorMap zh, zl; };   // [Mp rows][ld cols] float, box 32 points x (Mp / nbox) rows, 128 B swizzle
+struct Syrk32Maps { CUtensorMap zh, zl; };   // blocked planes viewed as [tiles * Mp rows][32 cols] float, box S32_KP x (Mp / nbox) rows
 
 struct Syrk32Args {
   const double* wq;    // [ld]
@@ -29,11 +33,13 @@ struct Syrk32Args {
   int ntile;           // 128-row tiles of G: row offsets 0, 128, ..., the last one at Mp - 128
   int64_t npts;        // valid points of this launch
   int64_t range;       // points per split (multiple of 32)
-  double* Gpart;       // [KS][Mp][Mp] fp64, accumulated
+  int kf;              // k-blocks between two drains of the fp32 accumulators
+  double* Gpart;       // [KS][ntile][Mp cols][128 rows of the tile] fp64, accumulated ("TMEM-native": for one column the 32
+                       // lanes of a flushing warp are contiguous, so the read-modify-write is coalesced)
   double* bzpart;      // [KS][Mp]
 };
 
-__host__ __device__ static inline int s32_stage_bytes(int Mp, int NC) { return 2 * Mp * 128 + 2 * NC * 128; }
+__host__ __device__ static inline int s32_stage_bytes(int Mp, int NC) { return 2 * Mp * S32_RB + 2 * NC * S32_RB; }
 static inline int s32_smem_bytes(int Mp, int NC) { return 2048 + S32_NS * s32_stage_bytes(Mp, NC); }
 // column parts: the fewest H (<= 4) whose two stages fit in shared memory and whose tiles fit in the 512 TMEM columns
 static inline bool s32_plan(int Mp, int* H_out, int* NC_out) {
@@ -55,7 +61,7 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
   uint8_t* smem = (uint8_t*)(((uintptr_t)s32_smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_a[S32_NS], full_b[S32_NS], empty[S32_NS], d_full, d_empty;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) double wsm[4][2][32];   // per scale warp: wq / wp of the k-block's 32 points
+  __shared__ __align__(16) float wsm[4][2][32];    // per scale warp: wq / wp of the k-block's points, rounded to fp32
   const int Mp = a.Mp, NC = a.NC;
   const int stage_bytes = s32_stage_bytes(Mp, NC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -63,8 +69,11 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
   const int64_t p0 = (int64_t)ks * a.range;
   int64_t p1 = p0 + a.range;
   if (p1 > a.npts) p1 = a.npts;
-  const int kt = p1 > p0 ? (int)((p1 - p0 + 31) / 32) : 0;          // 32-point k-blocks of this CTA
-  const int nflush = (kt + S32_KF - 1) / S32_KF;
+  const int kt = p1 > p0 ? (int)((p1 - p0 + S32_KP - 1) / S32_KP) : 0;   // k-blocks of this CTA
+  const int KF = a.kf;
+  const int foff = (int)(((unsigned)blockIdx.x * 7u) % (unsigned)KF);   // this CTA's offset inside the drain period
+  const int nskip = 0;
+  const int nflush = (kt + KF - 1) / KF;
 
   if (tid == 0) {
     for (int s = 0; s < S32_NS; ++s) { mbar_init(&full_a[s], 1); mbar_init(&full_b[s], 4); mbar_init(&empty[s], 1); }
@@ -88,11 +97,13 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
         const int st = kb % S32_NS;
         if (kb >= S32_NS) mbar_wait(&empty[st], (unsigned)(((kb / S32_NS) - 1) & 1));
         uint8_t* dst = smem + st * stage_bytes;
-        mbar_expect_tx(&full_a[st], (unsigned)(2 * Mp * 128));
-        const int c0 = (int)(p0 + 32 * (int64_t)kb);
+        mbar_expect_tx(&full_a[st], (unsigned)(2 * Mp * S32_RB));
+        // planes are tile-contiguous ([n / 32][Mp][32]): the k-block's rows are ONE contiguous slab of HBM per plane
+        const int64_t n0 = p0 + S32_KP * (int64_t)kb;
+        const int col = (int)(n0 & 31), row0 = (int)((n0 >> 5) * Mp);
         for (int b = 0; b < a.nbox; ++b) {
-          g32_tma_2d(dst + b * rows_box * 128, &maps.zh, c0, b * rows_box, &full_a[st]);
-          g32_tma_2d(dst + Mp * 128 + b * rows_box * 128, &maps.zl, c0, b * rows_box, &full_a[st]);
+          g32_tma_2d(dst + b * rows_box * S32_RB, &maps.zh, col, row0 + b * rows_box, &full_a[st]);
+          g32_tma_2d(dst + Mp * S32_RB + b * rows_box * S32_RB, &maps.zl, col, row0 + b * rows_box, &full_a[st]);
         }
       }
     }
@@ -101,108 +112,114 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
     if (lane == 0) {
       // both operands K-major (the contraction runs over the points), D f32, M = 128, N = NC
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t hiD = g32_desc_hi(S32_SBO, S32_LAYOUT);
+      uint32_t toff[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) toff[t] = (uint32_t)((((t == a.ntile - 1) ? Mp - 128 : 128 * t) * S32_RB) >> 4);
       for (int kb = 0; kb < kt; ++kb) {
         const int st = kb % S32_NS;
-        const int inflush = kb % S32_KF;
-        if (inflush == 0 && kb > 0) mbar_wait(&d_empty, (unsigned)(((kb / S32_KF) - 1) & 1));   // accumulators drained
+        // drains are staggered over the CTAs (foff): 148 CTAs draining at once turned the read-modify-write of Gpart into
+        // an L2 storm (ncu r02k: 30 % of the kernel's samples on the drain's loads)
+        const int inflush = (kb + foff) % KF;
+        if (inflush == 0 && kb > 0) mbar_wait(&d_empty, (unsigned)((((kb + foff) / KF) - 1 - nskip) & 1));   // accumulators drained
         mbar_wait(&full_a[st], (unsigned)((kb / S32_NS) & 1));
         mbar_wait(&full_b[st], (unsigned)((kb / S32_NS) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t ah = g32_smem_u32(smem + st * stage_bytes), al = ah + Mp * 128;
-        const uint32_t bh = ah + 2 * Mp * 128, bl = bh + NC * 128;
+        const uint32_t ah = g32_smem_u32(smem + st * stage_bytes), al = ah + Mp * S32_RB;
+        const uint32_t bh = ah + 2 * Mp * S32_RB, bl = bh + NC * S32_RB;
+        // K-major operands (swizzled rows of S32_RB bytes, 8-row atoms): 8 points = 32 B inside a row (+2 in the descriptor's
+        // address field); tile t of the A operand starts r0 rows further down (+toff[t])
+        const uint32_t ahl = g32_desc_lo(ah, 16), all = g32_desc_lo(al, 16), bhl = g32_desc_lo(bh, 16), bll = g32_desc_lo(bl, 16);
 #pragma unroll
-        for (int k8 = 0; k8 < 4; ++k8) {
-          const uint64_t dbh = g32_desc(bh + k8 * 32, 16, 1024, 2), dbl = g32_desc(bl + k8 * 32, 16, 1024, 2);
-          for (int t = 0; t < a.ntile; ++t) {
-            const int r0 = (t == a.ntile - 1) ? Mp - 128 : 128 * t;
-            const uint64_t dah = g32_desc(ah + r0 * 128 + k8 * 32, 16, 1024, 2), dal = g32_desc(al + r0 * 128 + k8 * 32, 16, 1024, 2);
-            const uint32_t d = tmem + (uint32_t)(t * NC);
-            g32_mma(d, dal, dbh, idesc, (inflush | k8) ? 1u : 0u);
-            g32_mma(d, dah, dbl, idesc, 1u);
-            g32_mma(d, dah, dbh, idesc, 1u);
+        for (int k8 = 0; k8 < S32_KP / 8; ++k8) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < a.ntile) {
+              const uint32_t d = tmem + (uint32_t)(t * NC);
+              g32_mma2(d, all + toff[t] + 2 * k8, hiD, bhl + 2 * k8, hiD, idesc, ((inflush && kb) | k8) ? 1u : 0u);
+              g32_mma2(d, ahl + toff[t] + 2 * k8, hiD, bll + 2 * k8, hiD, idesc, 1u);
+              g32_mma2(d, ahl + toff[t] + 2 * k8, hiD, bhl + 2 * k8, hiD, idesc, 1u);
+            }
           }
         }
         g32_commit(&empty[st]);
-        if (inflush == S32_KF - 1 || kb == kt - 1) g32_commit(&d_full);
+        if (inflush == KF - 1 || kb == kt - 1) g32_commit(&d_full);
       }
     }
   } else {
     // ================= scale + flush warps (2..5) =================
     const int q = warp & 3, t128 = (warp - 2) * 32 + lane;           // q: TMEM lane quadrant; t128: 0..127
-    const int items = NC * 8;                                         // (row of the part, 16-byte chunk)
-    double bzacc[16];
+    constexpr int CH = S32_RB / 16;                                   // 16-byte chunks (4 points) per row
+    const int items = NC * CH;                                        // (row of the part, chunk); a multiple of 64
+    constexpr int NI = 2 * CH;                                        // items per thread at most (NC <= 256)
+    double bzacc[NI];
+    float bzf[NI];                            // fp32 partial sums of one drain period, widened at the drain
 #pragma unroll
-    for (int i = 0; i < 16; ++i) bzacc[i] = 0.0;
-    double* gp = a.Gpart + (int64_t)ks * Mp * Mp;
-    double (*wv)[32] = wsm[warp - 2];
+    for (int i = 0; i < NI; ++i) { bzacc[i] = 0.0; bzf[i] = 0.f; }
+    double* gp = a.Gpart + (int64_t)ks * a.ntile * Mp * 128;
+    float (*wv)[32] = wsm[warp - 2];
     // the per-point weights of the next k-block are fetched one k-block ahead (one coalesced load per warp) and handed to
     // the items through a per-warp shared-memory copy: the item loop itself touches no global memory
+    int nfl = 0;                              // drains done so far (parity of d_full)
     double wq_n = 0.0, wp_n = 0.0;
-    if (kt > 0 && p0 + lane < a.npts) { wq_n = a.wq[p0 + lane]; wp_n = a.wp[p0 + lane]; }
+    if (kt > 0 && lane < S32_KP && p0 + lane < a.npts) { wq_n = a.wq[p0 + lane]; wp_n = a.wp[p0 + lane]; }
     for (int kb = 0; kb < kt; ++kb) {
       const int st = kb % S32_NS;
       uint8_t* sa = smem + st * stage_bytes;
-      uint8_t* sb = sa + 2 * Mp * 128;
-      const int64_t n0 = p0 + 32 * (int64_t)kb;
+      uint8_t* sb = sa + 2 * Mp * S32_RB;
+      const int64_t n0 = p0 + S32_KP * (int64_t)kb;
       __syncwarp();
-      wv[0][lane] = wq_n; wv[1][lane] = wp_n;
+      wv[0][lane] = (float)wq_n; wv[1][lane] = (float)wp_n;
       __syncwarp();
       wq_n = 0.0; wp_n = 0.0;
-      if (kb + 1 < kt && n0 + 32 + lane < a.npts) { wq_n = a.wq[n0 + 32 + lane]; wp_n = a.wp[n0 + 32 + lane]; }
+      if (kb + 1 < kt && lane < S32_KP && n0 + S32_KP + lane < a.npts) { wq_n = a.wq[n0 + S32_KP + lane]; wp_n = a.wp[n0 + S32_KP + lane]; }
       mbar_wait(&full_a[st], (unsigned)((kb / S32_NS) & 1));
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {          // fully unrolled so that bzacc stays in registers (items <= 16 * 128)
+      for (int i = 0; i < NI; ++i) {          // fully unrolled so that bzacc stays in registers (items <= NI * 128)
         const int it = t128 + 128 * i;
-        if (it >= items) break;
-        const int rl = it >> 3, cp = it & 7;
+        if (it >= items) break;               // whole warps drop out (items is a multiple of 64)
+        const int rl = it / CH, cp = it % CH;
         const int j = h * NC + rl;
         float4 oh = make_float4(0.f, 0.f, 0.f, 0.f), ol = oh;
         if (j < Mp) {
-          const float4 vh = *reinterpret_cast<const float4*>(sa + j * 128 + cp * 16);
-          const float4 vl = *reinterpret_cast<const float4*>(sa + Mp * 128 + j * 128 + cp * 16);
-          const int pc = 4 * (cp ^ (j & 7));                          // the four points of this (swizzled) chunk
-          const double2 w01 = *reinterpret_cast<const double2*>(&wv[0][pc]), w23 = *reinterpret_cast<const double2*>(&wv[0][pc + 2]);
-          const double2 u01 = *reinterpret_cast<const double2*>(&wv[1][pc]), u23 = *reinterpret_cast<const double2*>(&wv[1][pc + 2]);
-          const double w[4] = {w01.x, w01.y, w23.x, w23.y}, u[4] = {u01.x, u01.y, u23.x, u23.y};
-          const double z0 = (double)vh.x + (double)vl.x, z1 = (double)vh.y + (double)vl.y;
-          const double z2 = (double)vh.z + (double)vl.z, z3 = (double)vh.w + (double)vl.w;
-          tf32_split(z0 * w[0], oh.x, ol.x);
-          tf32_split(z1 * w[1], oh.y, ol.y);
-          tf32_split(z2 * w[2], oh.z, ol.z);
-          tf32_split(z3 * w[3], oh.w, ol.w);
-          bzacc[i] += (z0 * u[0] + z1 * u[1]) + (z2 * u[2] + z3 * u[3]);
+          const float4 vh = *reinterpret_cast<const float4*>(sa + j * S32_RB + cp * 16);
+          const float4 vl = *reinterpret_cast<const float4*>(sa + Mp * S32_RB + j * S32_RB + cp * 16);
+          const int pc = 4 * (cp ^ (S32_KP == 32 ? (j & 7) : ((j >> 1) & 3)));   // the four points of this (swizzled) chunk
+          // hi + lo is exact in fp32 (22 significant bits), the weighting is one fp32 multiply (relative 6e-8, below the
+          // 2^-22 the re-split keeps) and the split is exact fp32 arithmetic: the scale pass runs on the FP32 pipe - the
+          // fp64 version spent its time in F2F conversions (ncu r02i: 14 % of the samples)
+          const float4 w = *reinterpret_cast<const float4*>(&wv[0][pc]), u = *reinterpret_cast<const float4*>(&wv[1][pc]);
+          const float z0 = vh.x + vl.x, z1 = vh.y + vl.y, z2 = vh.z + vl.z, z3 = vh.w + vl.w;
+          const float s0 = z0 * w.x, s1 = z1 * w.y, s2 = z2 * w.z, s3 = z3 * w.w;
+          oh.x = tf32_round(s0); ol.x = tf32_round(s0 - oh.x);
+          oh.y = tf32_round(s1); ol.y = tf32_round(s1 - oh.y);
+          oh.z = tf32_round(s2); ol.z = tf32_round(s2 - oh.z);
+          oh.w = tf32_round(s3); ol.w = tf32_round(s3 - oh.w);
+          bzf[i] += (z0 * u.x + z1 * u.y) + (z2 * u.z + z3 * u.w);
         }
-        *reinterpret_cast<float4*>(sb + rl * 128 + cp * 16) = oh;
-        *reinterpret_cast<float4*>(sb + NC * 128 + rl * 128 + cp * 16) = ol;
+        *reinterpret_cast<float4*>(sb + rl * S32_RB + cp * 16) = oh;
+        *reinterpret_cast<float4*>(sb + NC * S32_RB + rl * S32_RB + cp * 16) = ol;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of B visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_b[st]);
 
-      if ((kb % S32_KF) == S32_KF - 1 || kb == kt - 1) {
+      if (((kb + foff) % KF) == KF - 1 || kb == kt - 1) {
         // ---- flush: TMEM -> += Gpart (fp64).  Tile t covers rows r0 .. r0 + 127; the last tile only contributes the rows
         // its predecessor does not cover ----
-        const int fl = kb / S32_KF;
-        mbar_wait(&d_full, (unsigned)(fl & 1));
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { bzacc[i] += (double)bzf[i]; bzf[i] = 0.f; }
+        mbar_wait(&d_full, (unsigned)(nfl & 1));
+        ++nfl;
         asm volatile("tcgen05.fence::after_thread_sync;");
         for (int t = 0; t < a.ntile; ++t) {
-          const int r0 = (t == a.ntile - 1) ? Mp - 128 : 128 * t;
-          const int row = r0 + 32 * q + lane;
-          const bool mine = (t < a.ntile - 1) || a.ntile == 1 || row >= 128 * (a.ntile - 1);
+          double* gt = gp + ((int64_t)t * Mp + h * NC) * 128 + 32 * q + lane;   // [col][lane]: 256 B per warp and column
           for (int c0 = 0; c0 < NC; c0 += 32) {
             uint32_t v[32];
             g32_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * NC + c0), v);
-            if (mine) {
-              double* dst = gp + (int64_t)row * Mp + h * NC + c0;
 #pragma unroll
-              for (int jj = 0; jj < 32; jj += 2) {
-                if (c0 + jj < NC && h * NC + c0 + jj < Mp) {
-                  double2 o = *reinterpret_cast<double2*>(dst + jj);
-                  o.x += (double)__uint_as_float(v[jj]);
-                  o.y += (double)__uint_as_float(v[jj + 1]);
-                  *reinterpret_cast<double2*>(dst + jj) = o;
-                }
-              }
+            for (int jj = 0; jj < 32; ++jj) {
+              if (c0 + jj < NC && h * NC + c0 + jj < Mp) gt[(int64_t)(c0 + jj) * 128] += (double)__uint_as_float(v[jj]);
             }
           }
         }
@@ -214,15 +231,15 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
     // ---- bz of the part's rows: sum the 8 chunk lanes of every row (aligned groups of 8 lanes) ----
     double* bzp = a.bzpart + (int64_t)ks * Mp;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int it = t128 + 128 * i;
-      if (it >= items) break;                 // items is a multiple of 128: uniform over the warp
+      if (it >= items) break;
       double s = bzacc[i];
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      const int j = h * NC + (it >> 3);
-      if ((it & 7) == 0 && j < Mp) bzp[j] += s;
+      if (CH == 8) s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const int j = h * NC + it / CH;
+      if ((it % CH) == 0 && j < Mp) bzp[j] += s;
     }
   }
   (void)nflush;
@@ -231,14 +248,21 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-// Gz [Mp][Mp] = sum_ks Gpart[ks], bz [Mp] = sum_ks bzpart[ks]   (fixed order: deterministic)
-__global__ void reduce_g32_kernel(const double* Gpart, const double* bzpart, double* Gz, double* bz, int Mp, int KS) {
+// Gz [Mp][Mp] = sum_ks Gpart[ks] (tile-native layout -> row-major; the last tile contributes only the rows its predecessors
+// do not cover), bz [Mp] = sum_ks bzpart[ks]   (fixed order: deterministic)
+__global__ void reduce_g32_kernel(const double* Gpart, const double* bzpart, double* Gz, double* bz, int Mp, int KS, int ntile) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t MM = (int64_t)Mp * Mp;
   if (e < MM) {
+    const int col = (int)(e / Mp), row = (int)(e % Mp);          // consecutive threads walk the rows: coalesced reads
+    int t = row / 128;
+    if (t >= ntile - 1) t = ntile - 1;
+    const int r0 = (t == ntile - 1) ? Mp - 128 : 128 * t;
+    const double* src = Gpart + ((int64_t)t * Mp + col) * 128 + (row - r0);
+    const int64_t slot = (int64_t)ntile * Mp * 128;
     double s = 0.0;
-    for (int k = 0; k < KS; ++k) s += Gpart[(int64_t)k * MM + e];
-    Gz[e] = s;
+    for (int k = 0; k < KS; ++k) s += src[(int64_t)k * slot];
+    Gz[(int64_t)row * Mp + col] = s;
   }
   if (e < Mp) {
     double s = 0.0;

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
   stage_params_tma(vs, a.vhat_p, (unsigned)((Mp * DIMP + (a.mz ? a.P * Mp : 0)) * 8), &bar);
   __syncthreads();
 
-  const int ntile = ZPOUT ? Mp / 8 : (a.M + 7) / 8;   // the derivative panel is written for the padding rows too (zeros)
+  const int ntile = (ZPOUT || a.Zh) ? Mp / 8 : (a.M + 7) / 8;   // the derivative panel / float planes cover the padding rows too (zeros)
   for (int it = 0; it < n_my; ++it) {
     if (warp == 0) {  // helper warp: the next tile's points while the seven compute warps work, then this tile's outputs
       if (it + 1 < n_my) project_tile(it + 1);
@@ -182,6 +182,22 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
           for (int u = 0; u < 8; ++u) z[u] = l >= 1 ? ld * p[u] : (l == 0 ? 1.0 : 0.0);
         }
       }
+      if (a.Zh) {   // the same values as two TF32 planes (hi + lo), tile-contiguous [n / 32][Mp][32], for the tcgen05 contractions;
+                    // padding rows (z = 0) and the columns past the end of the chunk are written as zeros
+        float* zhrow = a.Zh + ((p0 >> 5) * (int64_t)Mp + row) * 32;
+        float* zlrow = a.Zl + ((p0 >> 5) * (int64_t)Mp + row) * 32;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int64_t n0 = p0 + 8 * nt + 2 * t4;
+          float h0, l0, h1, l1;
+          tf32_split(row < a.M ? z[2 * nt] : 0.0, h0, l0);
+          tf32_split(row < a.M ? z[2 * nt + 1] : 0.0, h1, l1);
+          if (n0 + 1 >= a.npts) { h1 = 0.f; l1 = 0.f; }
+          if (n0 >= a.npts) { h0 = 0.f; l0 = 0.f; }
+          *reinterpret_cast<float2*>(zhrow + 8 * nt + 2 * t4) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(zlrow + 8 * nt + 2 * t4) = make_float2(l0, l1);
+        }
+      }
       if (row < a.M) {
         if (!(args.dbg & 1) && a.Z)
 #pragma unroll
@@ -192,19 +208,6 @@ __global__ void __launch_bounds__(256, 2) zonal_fwd2_kernel(const __grid_constan
           else if (n0 < a.npts) {
             dst[0] = z[2 * nt];
             if (n0 + 1 < npts_e) dst[1] = 0.0;  // keep the even-padded tail column finite
-          }
-        }
-        if (a.Zh) {   // the same values as two TF32 planes (hi + lo) for the tcgen05 contraction
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            const int64_t n0 = p0 + 8 * nt + 2 * t4;
-            float h0, l0, h1, l1;
-            tf32_split(z[2 * nt], h0, l0);
-            tf32_split(z[2 * nt + 1], h1, l1);
-            if (n0 + 1 >= a.npts) { h1 = 0.f; l1 = 0.f; }
-            if (n0 >= a.npts) { h0 = 0.f; l0 = 0.f; }   // the rest of the last 32-point block is zero filled (tcgen05 k-blocks)
-            *reinterpret_cast<float2*>(a.Zh + (int64_t)row * a.ldz + n0) = make_float2(h0, h1);
-            *reinterpret_cast<float2*>(a.Zl + (int64_t)row * a.ldz + n0) = make_float2(l0, l1);
           }
         }
         if (a.mz) {
