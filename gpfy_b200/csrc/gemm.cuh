@@ -21,7 +21,8 @@ struct GemmArgs {
   int64_t ldb;
   double* C;    // may be null when only the psi epilogue is wanted (predict_diag): the product is not stored
   int64_t ldc;
-  int m, n, k;  // k must be a multiple of 16 (operands zero padded); n even; lda, ldb, ldc even
+  int m, n, k;  // k must be a multiple of 16 (operands zero padded); n even; lda, ldb, ldc even.  C / psi_out are written for
+                // whole 192-column tiles (zeros beyond n): their panels must hold ceil(n / 192) * 192 columns
   double alpha, beta;
   // optional fused epilogue (needs m == k, alpha = 1, beta = 0): per-column partial sums of
   // B[i, n] * C[i, n] over the rows of each (row tile, warp row) slab,

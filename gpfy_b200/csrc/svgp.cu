@@ -542,7 +542,7 @@ static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
     mult = (fused_bwd_ok(s) || bwd4_ok(s)) ? (int)std::min<int64_t>(32, std::max<int64_t>(8, cap)) : 8;
   }
   const int64_t unit = (int64_t)192 * sms, nc_max = unit * mult;
-  const int64_t need = round_up64(n, 128);
+  const int64_t need = round_up64(n, 384);   // whole 128-point tcgen05 tiles and whole 192-column GEMM tiles
   if (need <= nc_max) return need;
   // equal chunks: k = ceil(n / nc_max) chunks of ceil(n / k) rows rounded up to whole tile rounds, so the last chunk is
   // not a sliver (n = 2 M: 3 x 0.68 M instead of 0.91 + 0.91 + 0.18 M)
