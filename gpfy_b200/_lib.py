@@ -10,7 +10,7 @@ LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1
 Q_TRIL, Q_FULLCOV = 0, 1
 W_ARD, W_SCALAR, W_PROJECTION = 0, 1, 2
 OP_FEATURES, OP_ELBO, OP_PREDICT, OP_FEATURES_VJP = 0, 1, 2, 3
-PREC_F64, PREC_TF32X3 = 0, 1
+PREC_F64, PREC_TF32X3, PREC_F64_I8 = 0, 1, 2
 
 
 class GpfyDesc(ctypes.Structure):

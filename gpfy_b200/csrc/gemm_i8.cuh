@@ -1,0 +1,387 @@
+// K_G8  the dense contraction  C = W2 Z  (variational.py:323-328 folded) in float64 accuracy on the 5th-generation
+// tensor cores: an Ozaki-style error-free split of both float64 operands into signed radix-256 digits, the digit products as
+// tcgen05 kind::i8 MMAs with exact int32 accumulators in TMEM, recombined in float64 in the epilogue.
+//
+//   z'[k, n]  = Z[k, n] / s_k          s_k  = power of two >= 2.04 max_t |C_l^alpha(t)|  (per feature row, i.e. per degree)
+//   w'[o, k]  = W2[o, k] s_k / r_o     r_o  = power of two >= 2.04 max_k |W2[o, k] s_k|  (per output row)
+//   x         = sum_{i = 1..S} x_i 256^-i + e,   x_i in [-128, 127],  |e| <= 2^-49         (S = 6 digits, |x| <= 0.4902)
+//   C[o, n]   = r_o sum_{g = 2..S+1} 256^-g  sum_{i + j = g} sum_k a_i[n, k] b_j[o, k]     (21 digit products, 6 accumulators)
+//
+// Every digit product is exact (|sum| <= 6 * 352 * 2^14 < 2^26 in int32); the error is the two operands' truncation (2^-49 of the row /
+// column maximum each) plus the dropped products i + j >= S + 2 (<= 5 * K * 2^14 * 256^-8 = 2^-39.5 K-worst-case, ~2^-46 typical) -
+// normwise ~1e-14 of max|C| against ~1e-15 for the DMMA kernel and the 1e-10 contract (tests/test_gpu_i8.py).
+//
+// Shape: TMEM lanes = 128 points of a tile, TMEM columns = S accumulators x NB output rows of one OUT-BLOCK (NB <= 80, NB % 16 = 0:
+// 6 x 80 = 480 of the 512 columns).  A CTA owns one out-block for the whole launch: the block's digit planes of W2 (S x NB x Mp
+// bytes) stay resident in shared memory, the digit planes of Z stream through a ring of 24 KB stages (one 32-feature k-block of all
+// S digits = ONE TMA bulk copy: the slicing kernel writes them in exactly the un-swizzled canonical K-major order the MMA reads,
+// 8 x 16-byte core matrices, LBO = 2 KB between the two 16-feature halves, SBO = 128 B between 8-point groups).  The SMs are dealt
+// to the out-blocks in proportion to a block's MMA time, max(NB / 2, 32 + NB / 4) cycles per product (measured, tools/i8_probe.cu:
+// below N = 128 an MMA is bound by the 128 B/clk shared-memory read of its operands, 4 KB of A + 32 NB of B).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane; two issuing warps were measured SLOWER: 89 cycles per
+// MMA against 52), warps 2..9 = epilogue, two per TMEM lane quarter each taking half of the block's columns (tcgen05.ld, digits -> float64 by Horner, row scale, C stored in the tile-contiguous swizzled
+// layout zonal_bwd3 / zonal_bwd4 read; optional psi = z . C partial sums).  The accumulator of digit group g is handed back to the
+// MMA warp as soon as the epilogue has read it, so the next tile's first k-block overlaps the drain.
+#pragma once
+#include "common.cuh"
+#include "gemm_tf32.cuh"
+
+namespace gpfy {
+
+constexpr int GI8_S = 6;                       // digits per operand
+constexpr int GI8_BM = 128;                    // points per tile
+constexpr int GI8_THREADS = 320;               // producer warp, MMA warp, eight epilogue warps
+constexpr int GI8_A_STAGE = GI8_S * 4096;      // bytes of one k-block (32 features) of a tile, all digits
+constexpr int GI8_MAXBLK = 8;
+constexpr int GI8_MAXNB = 80;
+constexpr double GI8_HEADROOM = 2.04;          // |x| <= 1 / 2.04 = 0.4902 < (127 + 127/256 + ...) / 256
+
+struct GemmI8Blocks {
+  int nblk;
+  int row0[GI8_MAXBLK], rows[GI8_MAXBLK];
+  int cta0[GI8_MAXBLK + 1];      // CTAs cta0[b] .. cta0[b + 1] - 1 work on block b
+  int64_t woff[GI8_MAXBLK];      // byte offset of block b's digit planes [S][Mp / 16][rows / 8][8][16] inside the W2 image
+};
+
+struct GemmI8Args {
+  const int8_t* Zs;     // digit planes of Z: [tiles of 128 points][Mp / 32 k-blocks][S][2 halves][16 point groups][8][16]
+  const int8_t* Ws;     // digit planes of W2 (GemmI8Blocks::woff)
+  const double* rs;     // [Mp] r_o * 2^-16
+  const double* Z;      // float64 panel [Mp][ldz] for the psi epilogue (null when psi is null)
+  int64_t ldz;
+  double* C;            // [tiles32][Mp][32] blocked + swizzled (GemmArgs::c_blocked), or null
+  double* psi;          // [nblk][ld_psi] partial sums of z_n . C_n over each out-block's rows, or null
+  int64_t ld_psi;
+  int Mp;
+  int64_t npts;
+  int nsa;              // stages of the Z ring
+  GemmI8Blocks blk;
+};
+
+// out-blocks: ceil(Mp / 80) blocks of whole 16-row units, as equal as possible; SMs in proportion to the MMA time per tile
+static inline bool gi8_plan(int Mp, int sms, GemmI8Blocks* b, int* nsa) {
+  if (Mp % 32 || Mp < 32) return false;
+  const int units = Mp / 16;
+  const int nblk = (Mp + GI8_MAXNB - 1) / GI8_MAXNB;
+  if (nblk > GI8_MAXBLK || sms < nblk) return false;
+  b->nblk = nblk;
+  int r0 = 0, maxrows = 0;
+  int64_t off = 0;
+  double wsum = 0.0, w[GI8_MAXBLK];
+  for (int i = 0; i < nblk; ++i) {
+    const int u = units / nblk + (i < units % nblk ? 1 : 0);
+    b->row0[i] = r0;
+    b->rows[i] = 16 * u;
+    b->woff[i] = off;
+    r0 += 16 * u;
+    off += (int64_t)GI8_S * 16 * u * Mp;
+    maxrows = 16 * u > maxrows ? 16 * u : maxrows;
+    w[i] = 16 * u / 2.0 > 32.0 + 16 * u / 4.0 ? 16 * u / 2.0 : 32.0 + 16 * u / 4.0;
+    wsum += w[i];
+  }
+  int given = 0;
+  for (int i = 0; i < nblk; ++i) {   // largest remainder
+    b->cta0[i] = given;
+    int c = (int)(sms * w[i] / wsum);
+    if (c < 1) c = 1;
+    given += c;
+  }
+  b->cta0[nblk] = given;
+  // leftover SMs to the blocks in order (heaviest first: blocks are sorted by size)
+  int left = sms - given;
+  for (int i = 0; left > 0; i = (i + 1) % nblk, --left)
+    for (int j = i + 1; j <= nblk; ++j) b->cta0[j] += 1;
+  if (b->cta0[nblk] > sms) return false;
+  const int avail = 227 * 1024 - 2048 - GI8_S * maxrows * Mp;
+  *nsa = avail / GI8_A_STAGE;
+  if (*nsa > 4) *nsa = 4;
+  return *nsa >= 2;
+}
+static inline int gi8_smem_bytes(int Mp, const GemmI8Blocks& b, int nsa) {
+  int maxrows = 0;
+  for (int i = 0; i < b.nblk; ++i) maxrows = b.rows[i] > maxrows ? b.rows[i] : maxrows;
+  return 1024 + GI8_S * maxrows * Mp + nsa * GI8_A_STAGE;
+}
+static inline int64_t gi8_w_image_bytes(int Mp) { return (int64_t)GI8_S * Mp * Mp; }
+static inline int64_t gi8_z_image_bytes(int Mp, int64_t nc) { return (nc + GI8_BM - 1) / GI8_BM * (int64_t)(Mp / 32) * GI8_A_STAGE; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t gi8_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }   // version 1, no swizzle
+__device__ __forceinline__ void gi8_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n}\n"
+               ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void gi8_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void gi8_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+
+// 16 values -> their S signed radix-256 digits, digit s of all 16 packed into one 16-byte vector (= one row of a core matrix).
+// q = round(x 2^48) by the magic-number add; T = q + 0x80..80 makes every digit unsigned (digit + 128), XOR 0x80 turns the bytes
+// back into two's-complement digits; byte 5 of T is the most significant digit (s = 1).
+struct Digits16 { uint32_t w[GI8_S][4]; };
+__device__ __forceinline__ uint64_t gi8_digits(double x, double scale) {
+  const double lim = 0.498 * 281474976710656.0;   // 0.498 * 2^48: out-of-contract values saturate instead of wrapping
+  double v = x * scale;
+  v = fmin(fmax(v, -lim), lim);
+  const double magic = 6755399441055744.0;        // 1.5 * 2^52
+  const long long q = __double_as_longlong(v + magic) - __double_as_longlong(magic);
+  return (uint64_t)(q + 0x0000808080808080ll) ^ 0x0000808080808080ull;
+}
+__device__ __forceinline__ void gi8_pack4(const uint64_t (&t)[4], Digits16& d, int word) {
+  const uint32_t l0 = (uint32_t)t[0], l1 = (uint32_t)t[1], l2 = (uint32_t)t[2], l3 = (uint32_t)t[3];
+  const uint32_t h0 = (uint32_t)(t[0] >> 32), h1 = (uint32_t)(t[1] >> 32), h2 = (uint32_t)(t[2] >> 32), h3 = (uint32_t)(t[3] >> 32);
+  // low words hold digits 6 (byte 0) .. 3 (byte 3), high words digits 2 (byte 0) and 1 (byte 1)
+#pragma unroll
+  for (int by = 0; by < 4; ++by) {
+    const uint32_t sel = (uint32_t)by | ((uint32_t)(4 + by) << 4);
+    const uint32_t p01 = __byte_perm(l0, l1, sel), p23 = __byte_perm(l2, l3, sel);
+    d.w[5 - by][word] = __byte_perm(p01, p23, 0x5410);
+  }
+#pragma unroll
+  for (int by = 0; by < 2; ++by) {
+    const uint32_t sel = (uint32_t)by | ((uint32_t)(4 + by) << 4);
+    const uint32_t p01 = __byte_perm(h0, h1, sel), p23 = __byte_perm(h2, h3, sel);
+    d.w[1 - by][word] = __byte_perm(p01, p23, 0x5410);
+  }
+}
+
+// Z [Mp][ldz] float64 -> digit planes.  grid (tiles of 128 points, Mp / 16), 128 threads: thread = one point x 16 features; the 16
+// row reads are coalesced over the warp's points and each digit vector is one 16-byte store, 512 contiguous bytes per warp.
+__global__ void __launch_bounds__(128) z_slice_i8_kernel(const double* __restrict__ Z, int64_t ldz, int Mp, int64_t npts,
+                                                         const double* __restrict__ kscale, int8_t* out) {
+  const int kc = blockIdx.y, p = threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * GI8_BM + p;
+  const bool ok = n < npts;
+  Digits16 d;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint64_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * 16 + 4 * w + j;
+      const double z = ok ? Z[(int64_t)k * ldz + n] : 0.0;
+      t[j] = gi8_digits(z, kscale[k]);
+    }
+    gi8_pack4(t, d, w);
+  }
+  int8_t* dst = out + ((int64_t)blockIdx.x * (Mp / 32) + (kc >> 1)) * GI8_A_STAGE + (kc & 1) * 2048 + p * 16;
+#pragma unroll
+  for (int s = 0; s < GI8_S; ++s) *reinterpret_cast<uint4*>(dst + s * 4096) = make_uint4(d.w[s][0], d.w[s][1], d.w[s][2], d.w[s][3]);
+}
+
+// W2 [Mp][Mp] float64 (row = output) -> per-row scale + digit planes in the out-block images; also the per-feature scales of Z.
+// One warp per output row; bound[k] = max |z_k| over the sphere (C_l^alpha(1) of the row's degree, 1 for padding rows).
+__global__ void __launch_bounds__(128) w2_slice_i8_kernel(const double* __restrict__ W2, int Mp, const double* __restrict__ bound,
+                                                          GemmI8Blocks blk, int8_t* Ws, double* rs, double* kscale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 4 + warp;
+  if (o >= Mp) return;
+  const double* row = W2 + (int64_t)o * Mp;
+  double mx = 0.0;
+  for (int k = lane; k < Mp; k += 32) {
+    int e;
+    frexp(GI8_HEADROOM * bound[k], &e);
+    const double sk = ldexp(1.0, e);           // power of two > 2.04 bound
+    if (o == 0) kscale[k] = 281474976710656.0 / sk;   // 2^48 / s_k
+    mx = fmax(mx, fabs(row[k]) * sk);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  int e = 0;
+  if (mx > 0.0) frexp(GI8_HEADROOM * mx, &e);
+  const double r = ldexp(1.0, e);
+  if (lane == 0) rs[o] = r * (1.0 / 65536.0);
+  int b = 0;
+  while (b + 1 < blk.nblk && o >= blk.row0[b + 1]) ++b;
+  const int NB = blk.rows[b], lr = o - blk.row0[b];
+  const double sc = 281474976710656.0 / r;
+  for (int kc = lane; kc < Mp / 16; kc += 32) {
+    Digits16 d;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      uint64_t t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kc * 16 + 4 * w + j;
+        int ek;
+        frexp(GI8_HEADROOM * bound[k], &ek);
+        t[j] = gi8_digits(row[k] * ldexp(1.0, ek), sc);
+      }
+      gi8_pack4(t, d, w);
+    }
+    int8_t* dst = Ws + blk.woff[b] + (int64_t)kc * NB * 16 + (lr >> 3) * 128 + (lr & 7) * 16;
+#pragma unroll
+    for (int s = 0; s < GI8_S; ++s) *reinterpret_cast<uint4*>(dst + (int64_t)s * NB * Mp) = make_uint4(d.w[s][0], d.w[s][1], d.w[s][2], d.w[s][3]);
+  }
+}
+
+// epilogue of one tile, one warp: thread = one point (TMEM lane), c[] = its outputs for NU 16-column units starting at column
+// col0 of the out-block.  All loads of a digit group are issued before the single wait; the accumulator is handed back to
+// the MMA warp as soon as it has been read.  rs_s = the block's row scales in shared memory.
+template <int NU>
+__device__ __forceinline__ double gi8_epilogue(const GemmI8Args& a, uint32_t tmem_lane, int NB, int row0, int col0, int64_t p0, int lane,
+                                               uint64_t* d_empty, const double* rs_s) {
+  double c[NU > 0 ? 16 * NU : 1];
+#pragma unroll
+  for (int g = GI8_S - 1; g >= 0; --g) {          // accumulator g holds digit group g + 2; lowest weight first
+    if constexpr (NU > 0) {
+      uint32_t v[NU][16];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) gi8_ld16_nowait(tmem_lane + (uint32_t)(g * NB + col0 + 16 * u), v[u]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double x = (double)(int)v[u][j];
+          c[16 * u + j] = (g == GI8_S - 1) ? x : fma(c[16 * u + j], 1.0 / 256.0, x);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&d_empty[g]);      // the MMA warp may overwrite this accumulator
+  }
+  double psi = 0.0;
+  if constexpr (NU > 0) {
+    const int Mp = a.Mp;
+    const int64_t n = p0 + lane;
+    const bool store = a.C != nullptr && p0 < ((a.npts + 31) & ~(int64_t)31);
+    double* ctile = a.C + (p0 >> 5) * (int64_t)Mp * 32;
+#pragma unroll
+    for (int j = 0; j < 16 * NU; ++j) {
+      const int row = row0 + col0 + j;
+      const double cv = c[j] * rs_s[col0 + j];
+      if (store) ctile[row * 32 + (lane ^ ((row & 3) << 2))] = cv;
+      if (a.psi) psi = fma(n < a.npts ? a.Z[(int64_t)row * a.ldz + n] : 0.0, cv, psi);
+    }
+  }
+  return psi;
+}
+
+__global__ void __launch_bounds__(GI8_THREADS, 1) gemm_i8_kernel(const __grid_constant__ GemmI8Args a) {
+  extern __shared__ __align__(1024) uint8_t gi8_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gi8_smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t a_full[4], a_empty[4], b_full, d_full, d_empty[GI8_S];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double rs_s[GI8_MAXNB];
+  __shared__ double psi_s[2][4][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int b = 0;
+  while (b + 1 < a.blk.nblk && (int)blockIdx.x >= a.blk.cta0[b + 1]) ++b;
+  const int NB = a.blk.rows[b], row0 = a.blk.row0[b];
+  const int gsize = a.blk.cta0[b + 1] - a.blk.cta0[b], gidx = (int)blockIdx.x - a.blk.cta0[b];
+  const int Mp = a.Mp, KB = Mp / 32, NSA = a.nsa;
+  const int tiles = (int)((a.npts + GI8_BM - 1) / GI8_BM);
+  const int n_my = gidx < tiles ? (tiles - gidx + gsize - 1) / gsize : 0;
+  const int b_slice = NB * Mp;                                  // bytes of one digit plane of the block
+  uint8_t* sB = smem;                                           // [S][Mp / 16][NB / 8][8][16]
+  uint8_t* sA = smem + ((GI8_S * b_slice + 1023) & ~1023);      // [NSA][S][2][16][8][16]
+
+  if (tid == 0) {
+    for (int s = 0; s < NSA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(&b_full, 1);
+    mbar_init(&d_full, 1);
+    for (int g = 0; g < GI8_S; ++g) mbar_init(&d_empty[g], 8);
+  }
+  if (tid < NB) rs_s[tid] = a.rs[row0 + tid];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g32_smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0 && n_my > 0) {
+      mbar_expect_tx(&b_full, (unsigned)(GI8_S * b_slice));
+      for (int s = 0; s < GI8_S; ++s) tma_bulk_g2s(sB + s * b_slice, a.Ws + a.blk.woff[b] + (int64_t)s * b_slice, (unsigned)b_slice, &b_full);
+      int ia = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int8_t* src = a.Zs + (int64_t)(gidx + it * gsize) * KB * GI8_A_STAGE;
+        for (int kb = 0; kb < KB; ++kb, ++ia) {
+          const int st = ia % NSA;
+          if (ia >= NSA) mbar_wait(&a_empty[st], (unsigned)(((ia / NSA) - 1) & 1));
+          mbar_expect_tx(&a_full[st], GI8_A_STAGE);
+          tma_bulk_g2s(sA + st * GI8_A_STAGE, src + (int64_t)kb * GI8_A_STAGE, GI8_A_STAGE, &a_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0 && n_my > 0) {
+      // instruction descriptor: D s32 (2 << 4), A / B signed 8 bit (1 << 7, 1 << 10), both K-major, N = NB, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(GI8_BM >> 4) << 24);
+      const uint32_t hi = gi8_desc_hi(128);
+      const uint32_t bstep = (uint32_t)b_slice >> 4;            // digit-plane stride of B in descriptor units
+      const uint32_t b_lo0 = g32_desc_lo(g32_smem_u32(sB), (uint32_t)NB * 16);
+      mbar_wait(&b_full, 0);
+      int ia = 0;
+      for (int it = 0; it < n_my; ++it) {
+        for (int kb = 0; kb < KB; ++kb, ++ia) {
+          const int st = ia % NSA;
+          mbar_wait(&a_full[st], (unsigned)((ia / NSA) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t a_lo = g32_desc_lo(g32_smem_u32(sA + st * GI8_A_STAGE), 2048);
+          const uint32_t b_lo = b_lo0 + (uint32_t)(kb * 2 * NB);   // k-block kb = 16-feature chunks 2 kb, 2 kb + 1 (NB * 16 bytes each)
+#pragma unroll
+          for (int g = GI8_S - 1; g >= 0; --g) {                // digit group g + 2, in the order the epilogue drains them
+            if (kb == 0 && it > 0) {
+              mbar_wait(&d_empty[g], (unsigned)((it - 1) & 1));
+              asm volatile("tcgen05.fence::after_thread_sync;");
+            }
+#pragma unroll
+            for (int i = 0; i <= g; ++i)                        // digits i + 1 of Z and g - i + 1 of W2
+              gi8_mma(tmem + (uint32_t)(g * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)(g - i), hi, idesc, (kb | i) ? 1u : 0u);
+          }
+          g32_commit(&a_empty[st]);
+        }
+        g32_commit(&d_full);
+      }
+    }
+  } else {
+    // ================= epilogue: warps 2..9; warp w reads TMEM lanes 32 (w % 4) .. + 31, column half (w - 2) / 4 =================
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int nu0 = (NB / 16 + 1) / 2;                      // 16-column units of the first half: 80 -> 3 + 2, 64 -> 2 + 2, 48 -> 2 + 1
+    const int nu = h == 0 ? nu0 : NB / 16 - nu0, col0 = h == 0 ? 0 : 16 * nu0;
+    for (int it = 0; it < n_my; ++it) {
+      const int64_t p0 = (int64_t)(gidx + it * gsize) * GI8_BM + 32 * q;
+      mbar_wait(&d_full, (unsigned)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+      double psi;
+      switch (nu) {
+        case 0: psi = gi8_epilogue<0>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
+        case 1: psi = gi8_epilogue<1>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
+        case 2: psi = gi8_epilogue<2>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
+        default: psi = gi8_epilogue<3>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
+      }
+      if (a.psi) {   // the two column halves of a lane quarter: the second parks its sum, the first adds it and stores (fixed order);
+                     // psi_s is double-buffered over the tiles, so one 64-thread named barrier per tile is enough
+        if (h == 1) psi_s[it & 1][q][lane] = psi;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        if (h == 0 && p0 + lane < a.npts) a.psi[(int64_t)b * a.ld_psi + p0 + lane] = psi + psi_s[it & 1][q][lane];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+#endif  // __CUDACC__
+
+}  // namespace gpfy

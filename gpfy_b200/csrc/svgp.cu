@@ -16,6 +16,7 @@
 #include "basis.cuh"
 #include "features_vjp.cuh"
 #include "syrk_tf32.cuh"
+#include "gemm_i8.cuh"
 
 namespace gpfy {
 
@@ -61,11 +62,11 @@ int device_configure_once(unsigned bit, const void* kernel, int smem_bytes) {
 // Optional per-kernel device timing (bench.py's roofline line): when enabled, the per-chunk kernels
 // of the ELBO step are bracketed by cudaEvents on the launching stream; gpfy_debug_kernel_time
 // synchronises those events and returns the summed durations.  Off by default: zero cost.
-enum { TK_ZONAL_FWD = 0, TK_GEMM = 1, TK_LIK = 2, TK_ZONAL_BWD = 3, TK_SYRK = 4, TK_DVHAT = 5, TK_COUNT = 6 };
+enum { TK_ZONAL_FWD = 0, TK_GEMM = 1, TK_LIK = 2, TK_ZONAL_BWD = 3, TK_SYRK = 4, TK_DVHAT = 5, TK_SLICE = 6, TK_COUNT = 7 };
 struct KernelTimer {
   bool on = false;
   std::vector<cudaEvent_t> ev[TK_COUNT];   // pairs (start, stop)
-  size_t used[TK_COUNT] = {0, 0, 0, 0, 0, 0};
+  size_t used[TK_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t get(int k) {
     if (used[k] == ev[k].size()) {
       cudaEvent_t e;
@@ -135,7 +136,7 @@ int make_shape(const GpfyDesc* desc, Shape* s) {
   if (desc->likelihood != GPFY_LIK_GAUSSIAN && desc->likelihood != GPFY_LIK_BERNOULLI) { set_error("unknown likelihood %d", desc->likelihood); return GPFY_EINVAL; }
   if (desc->q_kind != GPFY_Q_TRIL && desc->q_kind != GPFY_Q_FULLCOV) { set_error("unknown q_kind %d", desc->q_kind); return GPFY_EINVAL; }
   if (desc->weight_mode < GPFY_W_ARD || desc->weight_mode > GPFY_W_PROJECTION) { set_error("unknown weight_mode %d", desc->weight_mode); return GPFY_EINVAL; }
-  if (desc->precision != GPFY_PREC_F64 && desc->precision != GPFY_PREC_TF32X3) { set_error("unknown precision %d", desc->precision); return GPFY_EINVAL; }
+  if (desc->precision != GPFY_PREC_F64 && desc->precision != GPFY_PREC_TF32X3 && desc->precision != GPFY_PREC_F64_I8) { set_error("unknown precision %d", desc->precision); return GPFY_EINVAL; }
   if (s->nw > 1024) { set_error("projection with %d weights > 1024 is not built", s->nw); return GPFY_EUNSUPPORTED; }
   if (s->mmax > 1024) { set_error("m_l = %d > 1024 is not built", s->mmax); return GPFY_EUNSUPPORTED; }
   return GPFY_OK;
@@ -522,6 +523,10 @@ struct Plan {
   bool f32s;        // the weighted Gram matrix also runs on tcgen05 (syrk_tf32x3_kernel): no fp64 Z panel is written at all
   int H32, NC32, KS32;  // its column parts, columns per part, point splits
   bool f32;         // GPFY_PREC_TF32X3: float hi / lo planes of W2 (o_W2f) and Z (o_Zf) for the tcgen05 contraction
+  bool i8;          // GPFY_PREC_F64_I8: C = W2 Z as exact int8 digit products on tcgen05 (gemm_i8.cuh); float64 results
+  GemmI8Blocks i8blk;
+  int i8nsa;
+  int64_t o_Zi8, o_Wi8, o_rs8, o_ks8, o_bd8;
   int npsi;
 };
 
@@ -552,7 +557,8 @@ static int64_t choose_chunk(int sms, int64_t n, const Shape& s) {
   return nc < nc_max ? nc : nc_max;
 }
 
-static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, bool f32 = false) {
+static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, int prec = GPFY_PREC_F64) {
+  const bool f32 = prec == GPFY_PREC_TF32X3;
   const bool fvjp = op_in == GPFY_OP_FEATURES_VJP;   // the features VJP shares the ELBO step's buffers plus two of its own
   const int op = fvjp ? GPFY_OP_ELBO : op_in;
   p->s = s;
@@ -625,6 +631,16 @@ static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, bool f32 = 
   p->KSX = std::max(1, (8 * p->sms) / std::max(1, s.Mp / 16));
   p->o_Dp = take(fvjp ? Mp * p->nc : 0);
   p->o_xg = take(fvjp ? (int64_t)p->KSX * Mp * XG_W : 0);
+  // int8 digit planes (GPFY_PREC_F64_I8): built for one output and the blocked C layout of the fused backward kernels (or psi only);
+  // every other shape keeps the DMMA contraction - the results are float64-accurate either way
+  p->i8 = prec == GPFY_PREC_F64_I8 && !fvjp && op != GPFY_OP_FEATURES && s.P == 1 && (op == GPFY_OP_PREDICT || fused_bwd_ok(s) || bwd4_ok(s)) &&
+          gi8_plan(s.Mp, p->sms, &p->i8blk, &p->i8nsa) && !debug_option(DBG_NO_I8);
+  p->o_Zi8 = take(p->i8 ? (gi8_z_image_bytes(s.Mp, p->nc) + 7) / 8 : 0);
+  p->o_Wi8 = take(p->i8 ? (gi8_w_image_bytes(s.Mp) + 7) / 8 : 0);
+  p->o_rs8 = take(p->i8 ? Mp : 0);
+  p->o_ks8 = take(p->i8 ? Mp : 0);
+  p->o_bd8 = take(p->i8 ? Mp : 0);
+  if (p->i8) p->npsi = std::max(p->npsi, p->i8blk.nblk);
   p->total = o;
 }
 
@@ -939,6 +955,58 @@ static int launch_gemm32(cudaStream_t st, const Plan& p, double* ws, int q, int6
   return GPFY_OK;
 }
 
+// ---- float64-accurate contraction on the int8 tensor cores (GPFY_PREC_F64_I8): gemm_i8.cuh ----
+// max over the sphere of |C_l^alpha(t)| = C_l^alpha(1) = prod_{i = 1..l} (2 alpha + i - 1) / i   (gegenbauer.py:27-60 at t = 1)
+struct I8Bounds { double deg[GPFY_MAX_DEGREES]; };
+__global__ void i8_bound_rows_kernel(I8Bounds bd, DegreeTable deg, int M, int Mp, double* bound) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Mp) return;
+  double v = 1.0;   // padding rows hold zeros: any scale
+  if (k < M) {
+    int o = 0, l = 0;
+    while (k >= o + deg.m[l]) { o += deg.m[l]; ++l; }
+    v = bd.deg[l];
+  }
+  bound[k] = v;
+}
+// digit planes + row scales of W2 and the per-feature scales of Z (once per step)
+static int slice_w2_i8(cudaStream_t st, const GpfyDesc* desc, const Plan& p, double* ws) {
+  const Shape& s = p.s;
+  I8Bounds bd;
+  for (int l = 0; l < GPFY_MAX_DEGREES; ++l) {
+    double v = 1.0;
+    for (int i = 1; i <= l; ++i) v *= (2.0 * desc->alpha + i - 1.0) / i;
+    bd.deg[l] = v > 1.0 ? v : 1.0;
+  }
+  DegreeTable deg = degree_table(desc);
+  GPFY_K(i8_bound_rows_kernel, (s.Mp + 127) / 128, 128, 0, st, bd, deg, s.M, s.Mp, ws + p.o_bd8);
+  GPFY_K(w2_slice_i8_kernel, (s.Mp + 3) / 4, 128, 0, st, ws + p.o_W2, s.Mp, ws + p.o_bd8, p.i8blk, reinterpret_cast<int8_t*>(ws + p.o_Wi8),
+         ws + p.o_rs8, ws + p.o_ks8);
+  return GPFY_OK;
+}
+// Z panel -> digit planes, then C (blocked, may be null) and / or the psi slabs for npts points of the chunk
+static int launch_gemm_i8(cudaStream_t st, const Plan& p, double* ws, int64_t npts, double* C, double* psi) {
+  const Shape& s = p.s;
+  const int Mp = s.Mp;
+  int8_t* zs = reinterpret_cast<int8_t*>(ws + p.o_Zi8);
+  const int tiles = (int)((npts + GI8_BM - 1) / GI8_BM);
+  {
+    GPFY_TIMED(TK_SLICE, st);
+    GPFY_K(z_slice_i8_kernel, dim3((unsigned)tiles, (unsigned)(Mp / 16)), GI8_BM, 0, st, ws + p.o_Z, p.nc, Mp, npts, ws + p.o_ks8, zs);
+  }
+  GemmI8Args ga;
+  ga.Zs = zs; ga.Ws = reinterpret_cast<const int8_t*>(ws + p.o_Wi8); ga.rs = ws + p.o_rs8;
+  ga.Z = psi ? ws + p.o_Z : nullptr; ga.ldz = p.nc; ga.C = C; ga.psi = psi; ga.ld_psi = p.nc;
+  ga.Mp = Mp; ga.npts = npts; ga.nsa = p.i8nsa; ga.blk = p.i8blk;
+  const int smem = gi8_smem_bytes(Mp, p.i8blk, p.i8nsa);
+  GPFY_TRY(set_smem(gemm_i8_kernel, smem));
+  GPFY_TIMED(TK_GEMM, st);
+  gemm_i8_kernel<<<p.i8blk.cta0[p.i8blk.nblk], GI8_THREADS, smem, st>>>(ga);
+  GPFY_COUNT_LAUNCH();
+  GPFY_LAUNCH_OK();
+  return GPFY_OK;
+}
+
 // G += Z diag(wq) Z^T, bz += Z wp over npts points of the chunk planes, on tcgen05 (P = 1)
 static int launch_syrk32(cudaStream_t st, const Plan& p, double* ws, int64_t npts) {
   const Shape& s = p.s;
@@ -1003,6 +1071,7 @@ static int run_prologue(cudaStream_t st, const GpfyDesc* desc, const Plan& p, do
       float* wh = reinterpret_cast<float*>(ws + p.o_W2f) + 2 * q * Mp2;
       GPFY_K(tf32_split_kernel, sqg, 256, 0, st, ws + p.o_W2 + q * Mp2, wh, wh + Mp2, Mp2);
     }
+    if (p.i8) GPFY_TRY(slice_w2_i8(st, desc, p, ws));   // digit planes of W2 for the int8 contraction (P = 1)
     // mu2_q = E^T mu[:, q]
     GPFY_K(gemv_kernel, (Mp + 3) / 4, 128, 0, st, ws + p.o_E, Mp, 1, mu + q, s.P, s.M, ws + p.o_mu2 + (int64_t)q * Mp, 1, Mp);
   }
@@ -1104,7 +1173,7 @@ int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t*
   if (!bytes || n_points < 0 || op < GPFY_OP_FEATURES || op > GPFY_OP_FEATURES_VJP) { set_error("bad argument"); return GPFY_EINVAL; }
   Plan p;
   if (op == GPFY_OP_FEATURES_VJP) s.P = 1;
-  make_plan(s, n_points, op, &p, want_f32(desc) && op != GPFY_OP_FEATURES && op != GPFY_OP_FEATURES_VJP);
+  make_plan(s, n_points, op, &p, (op != GPFY_OP_FEATURES && op != GPFY_OP_FEATURES_VJP) ? desc->precision : GPFY_PREC_F64);
   *bytes = (size_t)p.total * 8;
   return GPFY_OK;
 }
@@ -1285,7 +1354,7 @@ int gpfy_sh_features_vjp(void* stream, const GpfyDesc* desc, int64_t n, const do
 static int elbo_plan(const GpfyDesc* desc, int64_t n_capacity, void* workspace, size_t workspace_bytes, Shape* s, Plan* p) {
   GPFY_TRY(make_shape(desc, s));
   if (n_capacity < 0) { set_error("n_capacity < 0"); return GPFY_EINVAL; }
-  make_plan(*s, n_capacity, GPFY_OP_ELBO, p, want_f32(desc));
+  make_plan(*s, n_capacity, GPFY_OP_ELBO, p, desc->precision);
   if (p->f32) {
     GPFY_TRY(check_f32_shape(*s));
     if (!fused_bwd_ok(*s) && !bwd4_ok(*s)) { set_error("GPFY_PREC_TF32X3 needs one of the fused backward kernels for this shape"); return GPFY_EUNSUPPORTED; }
@@ -1347,6 +1416,8 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     if (p.f32) {  // C = W2 Z on tcgen05 in 3 x TF32 (P = 1); psi goes out as one slab
       GPFY_TIMED(TK_GEMM, st);
       GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi));
+    } else if (p.i8) {  // C = W2 Z as exact int8 digit products on tcgen05 (P = 1); psi in one slab per out-block
+      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi));
     } else
     for (int q = 0; q < s.P; ++q) {  // C_q = W2_q Z
       GPFY_TIMED(TK_GEMM, st);
@@ -1363,7 +1434,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
 
     if (!fuse_lik) {
       LikPointArgs lp;
-      lp.psi_part = ws + p.o_psi; lp.npsi = p.f32 ? 1 : p.npsi; lp.mz = ws + p.o_mz; lp.ldz = p.nc;
+      lp.psi_part = ws + p.o_psi; lp.npsi = p.f32 ? 1 : (p.i8 ? p.i8blk.nblk : p.npsi); lp.mz = ws + p.o_mz; lp.ldz = p.nc;
       lp.R = ws + p.o_R; lp.Y = Y + c0 * s.P; lp.vptr = variance; lp.s2ptr = sigma2;
       lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
       lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
@@ -1571,7 +1642,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
   GPFY_TRY(make_shape(desc, &s));
   if (n == 0) return GPFY_OK;
   Plan p;
-  make_plan(s, n, GPFY_OP_PREDICT, &p, want_f32(desc));
+  make_plan(s, n, GPFY_OP_PREDICT, &p, desc->precision);
   if (p.f32) GPFY_TRY(check_f32_shape(s));
   GPFY_TRY(check_ws(p, workspace, workspace_bytes));
   double* ws = (double*)workspace;
@@ -1583,7 +1654,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
 
   // only the quadratic form z^T W2 z is needed: fold W2 onto its lower triangle (W_ij + W_ji below the diagonal, zero
   // above) and let the GEMM skip the k range right of each row tile's diagonal block
-  for (int q = 0; q < s.P; ++q)
+  for (int q = 0; q < s.P && !p.i8; ++q)   // (the int8 contraction forms the full product: its digit planes were cut from the unfolded W2)
     GPFY_K(fold_lower_kernel, dim3((Mp + 31) / 32, (Mp + 31) / 32), dim3(32, 8), 0, st, ws + p.o_W2 + q * Mp2, Mp);
   GPFY_CUDA_OK(cudaMemsetAsync(ws + p.o_Z + (int64_t)s.M * p.nc, 0, (size_t)(Mp + 32 - s.M) * p.nc * 8, st));
   for (int64_t c0 = 0; c0 < n; c0 += p.nc) {
@@ -1600,6 +1671,8 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
     if (p.f32) {
       GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, nullptr, ws + p.o_psi));   // psi only, 3 x TF32 on tcgen05
+    } else if (p.i8) {
+      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, nullptr, ws + p.o_psi));  // psi only, int8 digit products on tcgen05
     } else
     for (int q = 0; q < s.P; ++q) {
       GemmArgs g;
@@ -1613,7 +1686,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
       GPFY_TRY(launch_gemm(st, g, p.sms));
     }
     PredictArgs pa;
-    pa.psi_part = ws + p.o_psi; pa.npsi = p.f32 ? 1 : p.npsi; pa.mz = ws + p.o_mz; pa.ldz = p.nc;
+    pa.psi_part = ws + p.o_psi; pa.npsi = p.f32 ? 1 : (p.i8 ? p.i8blk.nblk : p.npsi); pa.mz = ws + p.o_mz; pa.ldz = p.nc;
     pa.R = ws + p.o_R; pa.vptr = variance; pa.P = s.P; pa.order = desc->kernel_order; pa.npts = npts;
     pa.fmu = fmu + c0 * s.P; pa.fvar = fvar + c0 * s.P;
     GPFY_TRY(launch_predict(st, pa));

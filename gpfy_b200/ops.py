@@ -76,7 +76,7 @@ class HotPath:
             _lib.LIK_GAUSSIAN if likelihood == "gaussian" else _lib.LIK_BERNOULLI,
             _lib.Q_TRIL if q_kind == "tril" else _lib.Q_FULLCOV,
             {"scalar": _lib.W_SCALAR, "projection": _lib.W_PROJECTION}.get(weight_mode, _lib.W_ARD), self.projection_dim,
-            {"f64": _lib.PREC_F64, "f32": _lib.PREC_TF32X3, "tf32x3": _lib.PREC_TF32X3}[precision])
+            {"f64": _lib.PREC_F64, "f32": _lib.PREC_TF32X3, "tf32x3": _lib.PREC_TF32X3, "f64i8": _lib.PREC_F64_I8}[precision])
         self.precision = precision
         self.nw = self.input_dim * self.projection_dim if self.projection_dim else (1 if self.scalar_w else self.input_dim)
         self.layout = _lib.GpfyElboLayout()
@@ -369,7 +369,7 @@ class HotPath:
         return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
 
 
-DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4, "no_syrk32": 5, "syrk32_kf": 6}
+DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4, "no_syrk32": 5, "syrk32_kf": 6, "no_i8": 7}
 
 
 def debug_option(name, value):
@@ -384,7 +384,7 @@ def launch_count():
     return int(_lib.load().gpfy_debug_launch_count())
 
 
-KERNEL_CLASSES = ("zonal_fwd", "gemm_dmma", "lik_point", "zonal_bwd", "syrk_dmma", "dvhat_dmma")
+KERNEL_CLASSES = ("zonal_fwd", "gemm_dmma", "lik_point", "zonal_bwd", "syrk_dmma", "dvhat_dmma", "i8_slice")
 
 
 def kernel_timing(enable):
