@@ -18,8 +18,8 @@
 // 8 x 16-byte core matrices, LBO = 2 KB between the two 16-feature halves, SBO = 128 B between 8-point groups).  The SMs are dealt
 // to the out-blocks in proportion to a block's MMA time, max(NB / 2, 32 + NB / 4) cycles per product (measured, tools/i8_probe.cu:
 // below N = 128 an MMA is bound by the 128 B/clk shared-memory read of its operands, 4 KB of A + 32 NB of B).
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane; two issuing warps were measured SLOWER: 89 cycles per
-// MMA against 52), warps 2..9 = epilogue, two per TMEM lane quarter each taking half of the block's columns (tcgen05.ld, digits -> float64 by Horner, row scale, C stored in the tile-contiguous swizzled
+// Roles (704 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane; two issuing warps were measured SLOWER: 89 cycles per
+// MMA against 52), warps 2..21 = epilogue, one per TMEM lane quarter and 16 columns of the block (tcgen05.ld, digits -> float64 by Horner, row scale, C stored in the tile-contiguous swizzled
 // layout zonal_bwd3 / zonal_bwd4 read; optional psi = z . C partial sums).  The accumulator of digit group g is handed back to the
 // MMA warp as soon as the epilogue has read it, so the next tile's first k-block overlaps the drain.
 #pragma once
@@ -30,10 +30,13 @@ namespace gpfy {
 
 constexpr int GI8_S = 6;                       // digits per operand
 constexpr int GI8_BM = 128;                    // points per tile
-constexpr int GI8_THREADS = 320;               // producer warp, MMA warp, eight epilogue warps
+constexpr int GI8_THREADS = 704;               // producer warp, MMA warp, 20 epilogue warps (one per TMEM lane quarter and 16 columns)
 constexpr int GI8_A_STAGE = GI8_S * 4096;      // bytes of one k-block (32 features) of a tile, all digits
 constexpr int GI8_MAXBLK = 8;
 constexpr int GI8_MAXNB = 80;
+#ifndef GI8_SLEEP_NS
+#define GI8_SLEEP_NS 64
+#endif
 constexpr double GI8_HEADROOM = 2.04;          // |x| <= 1 / 2.04 = 0.4902 < (127 + 127/256 + ...) / 256
 
 struct GemmI8Blocks {
@@ -46,7 +49,7 @@ struct GemmI8Blocks {
 struct GemmI8Args {
   const int8_t* Zs;     // digit planes of Z: [tiles of 128 points][Mp / 32 k-blocks][S][2 halves][16 point groups][8][16]
   const int8_t* Ws;     // digit planes of W2 (GemmI8Blocks::woff)
-  const double* rs;     // [Mp] r_o * 2^-16
+  const double* rs;     // [Mp] r_o * 2^-24
   const double* Z;      // float64 panel [Mp][ldz] for the psi epilogue (null when psi is null)
   int64_t ldz;
   double* C;            // [tiles32][Mp][32] blocked + swizzled (GemmArgs::c_blocked), or null
@@ -55,6 +58,9 @@ struct GemmI8Args {
   int Mp;
   int64_t npts;
   int nsa;              // stages of the Z ring
+#ifdef GI8_PROFILE
+  long long* prof;      // [grid][8] cycle counters (development builds, tools/i8_gemm_bench.cu)
+#endif
   GemmI8Blocks blk;
 };
 
@@ -120,6 +126,18 @@ __device__ __forceinline__ void gi8_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ bool gi8_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.b32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// waits of the warps that are NOT on the critical path back off between polls: nine warps spinning on mbarriers
+// were measured to slow the MMA warp's issue rate (tools/i8_gemm_bench.cu)
+__device__ __forceinline__ void gi8_wait_relaxed(uint64_t* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(GI8_SLEEP_NS);
+}
+
 __device__ __forceinline__ void gi8_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
@@ -132,13 +150,16 @@ __device__ __forceinline__ void gi8_ld16_nowait(uint32_t taddr, uint32_t (&v)[16
 // back into two's-complement digits; byte 5 of T is the most significant digit (s = 1).
 struct Digits16 { uint32_t w[GI8_S][4]; };
 __device__ __forceinline__ uint64_t gi8_digits(double x, double scale) {
-  const double lim = 0.498 * 281474976710656.0;   // 0.498 * 2^48: out-of-contract values saturate instead of wrapping
-  double v = x * scale;
-  v = fmin(fmax(v, -lim), lim);
+  // one FMA: x * scale (a power of two: exact) + 1.5 * 2^52 rounds to the nearest integer in the low mantissa bits.  |x scale| <=
+  // 2^48 / 2.04 by construction of the scales (measured on B200: DMUL issues at a fraction of the DFMA rate, so no separate multiply)
   const double magic = 6755399441055744.0;        // 1.5 * 2^52
-  const long long q = __double_as_longlong(v + magic) - __double_as_longlong(magic);
+  const long long q = __double_as_longlong(fma(x, scale, magic)) - __double_as_longlong(magic);
   return (uint64_t)(q + 0x0000808080808080ll) ^ 0x0000808080808080ull;
 }
+// x * y as an FMA with -0.0 (bit-identical to the product; the compiler would turn fma(x, y, 0) back into the slow DMUL)
+__device__ __forceinline__ double gi8_mul(double x, double y, double neg_zero) { return fma(x, y, neg_zero); }
+// -0.0 the compiler cannot constant-fold (flag is zero at run time)
+__device__ __forceinline__ double gi8_neg_zero(int flag_zero) { return __longlong_as_double((long long)(0x8000000000000000ull | (unsigned long long)(flag_zero != 0))); }
 __device__ __forceinline__ void gi8_pack4(const uint64_t (&t)[4], Digits16& d, int word) {
   const uint32_t l0 = (uint32_t)t[0], l1 = (uint32_t)t[1], l2 = (uint32_t)t[2], l3 = (uint32_t)t[3];
   const uint32_t h0 = (uint32_t)(t[0] >> 32), h1 = (uint32_t)(t[1] >> 32), h2 = (uint32_t)(t[2] >> 32), h3 = (uint32_t)(t[3] >> 32);
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(128) w2_slice_i8_kernel(const double* __restri
   int e = 0;
   if (mx > 0.0) frexp(GI8_HEADROOM * mx, &e);
   const double r = ldexp(1.0, e);
-  if (lane == 0) rs[o] = r * (1.0 / 65536.0);
+  if (lane == 0) rs[o] = r * (1.0 / 16777216.0);   // 256^-2 of the leading digit pair, 256^-1 of the pairwise fold
   int b = 0;
   while (b + 1 < blk.nblk && o >= blk.row0[b + 1]) ++b;
   const int NB = blk.rows[b], lr = o - blk.row0[b];
@@ -217,7 +238,7 @@ __global__ void __launch_bounds__(128) w2_slice_i8_kernel(const double* __restri
         const int k = kc * 16 + 4 * w + j;
         int ek;
         frexp(GI8_HEADROOM * bound[k], &ek);
-        t[j] = gi8_digits(row[k] * ldexp(1.0, ek), sc);
+        t[j] = gi8_digits(row[k], sc * ldexp(1.0, ek));
       }
       gi8_pack4(t, d, w);
     }
@@ -227,45 +248,47 @@ __global__ void __launch_bounds__(128) w2_slice_i8_kernel(const double* __restri
   }
 }
 
-// epilogue of one tile, one warp: thread = one point (TMEM lane), c[] = its outputs for NU 16-column units starting at column
-// col0 of the out-block.  All loads of a digit group are issued before the single wait; the accumulator is handed back to
-// the MMA warp as soon as it has been read.  rs_s = the block's row scales in shared memory.
-template <int NU>
-__device__ __forceinline__ double gi8_epilogue(const GemmI8Args& a, uint32_t tmem_lane, int NB, int row0, int col0, int64_t p0, int lane,
-                                               uint64_t* d_empty, const double* rs_s) {
-  double c[NU > 0 ? 16 * NU : 1];
+// epilogue of one tile, one warp: thread = one point (TMEM lane), c[] = its outputs for the 16 columns col0 .. col0 + 15 of the
+// out-block.  The six int32 accumulators are folded pairwise in INTEGER arithmetic (acc_2p * 256 + acc_2p+1, one IMAD.WIDE),
+// converted with the 1.5 * 2^52 magic-number add and chained by one FMA per pair: 6 FP64-pipe instructions per output instead of
+// 13 (I2F.F64 + DFMA per accumulator: measured, the conversions made the epilogue - not the MMAs - the bottleneck).  Both
+// accumulators of a pair are handed back to the MMA warp as soon as they have been read.  rs_s = the block's row scales.
+__device__ __forceinline__ double gi8_epilogue16(const GemmI8Args& a, uint32_t tmem_lane, int NB, int row0, int col0, int64_t p0, int lane,
+                                                 uint64_t* d_empty, const double* rs_s) {
+  double c[16];
 #pragma unroll
-  for (int g = GI8_S - 1; g >= 0; --g) {          // accumulator g holds digit group g + 2; lowest weight first
-    if constexpr (NU > 0) {
-      uint32_t v[NU][16];
+  for (int pr = GI8_S / 2 - 1; pr >= 0; --pr) {   // accumulators 2 pr (weight 256) and 2 pr + 1; lowest weights first
+    uint32_t vh[16], vl[16];
+#if defined(GI8_KO) && (GI8_KO & 2)   // development knock-out: no TMEM loads
 #pragma unroll
-      for (int u = 0; u < NU; ++u) gi8_ld16_nowait(tmem_lane + (uint32_t)(g * NB + col0 + 16 * u), v[u]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int u = 0; u < NU; ++u)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const double x = (double)(int)v[u][j];
-          c[16 * u + j] = (g == GI8_S - 1) ? x : fma(c[16 * u + j], 1.0 / 256.0, x);
-        }
-    }
+    for (int j = 0; j < 16; ++j) { vh[j] = (uint32_t)(pr + j + lane); vl[j] = vh[j] * 3u; }
+#else
+    gi8_ld16_nowait(tmem_lane + (uint32_t)((2 * pr + 1) * NB + col0), vl);
+    gi8_ld16_nowait(tmem_lane + (uint32_t)((2 * pr) * NB + col0), vh);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncwarp();
-    if (lane == 0) mbar_arrive(&d_empty[g]);      // the MMA warp may overwrite this accumulator
-  }
-  double psi = 0.0;
-  if constexpr (NU > 0) {
-    const int Mp = a.Mp;
-    const int64_t n = p0 + lane;
-    const bool store = a.C != nullptr && p0 < ((a.npts + 31) & ~(int64_t)31);
-    double* ctile = a.C + (p0 >> 5) * (int64_t)Mp * 32;
+    if (lane == 0) { mbar_arrive(&d_empty[2 * pr + 1]); mbar_arrive(&d_empty[2 * pr]); }   // the MMA warp may overwrite them
 #pragma unroll
-    for (int j = 0; j < 16 * NU; ++j) {
-      const int row = row0 + col0 + j;
-      const double cv = c[j] * rs_s[col0 + j];
-      if (store) ctile[row * 32 + (lane ^ ((row & 3) << 2))] = cv;
-      if (a.psi) psi = fma(n < a.npts ? a.Z[(int64_t)row * a.ldz + n] : 0.0, cv, psi);
+    for (int j = 0; j < 16; ++j) {
+      const long long pair = (long long)(int)vh[j] * 256 + (long long)(int)vl[j];
+      const double pd = __longlong_as_double(pair + 0x4338000000000000ll) - 6755399441055744.0;   // exact: |pair| < 2^51
+      c[j] = (pr == GI8_S / 2 - 1) ? pd : fma(c[j], 1.0 / 65536.0, pd);
     }
+  }
+  const int Mp = a.Mp;
+  const int64_t n = p0 + lane;
+  const bool store = a.C != nullptr && p0 < ((a.npts + 31) & ~(int64_t)31);
+  double* ctile = a.C + (p0 >> 5) * (int64_t)Mp * 32;
+  double psi = 0.0;
+  const double nz = gi8_neg_zero(Mp == 0);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int row = row0 + col0 + j;
+    const double cv = gi8_mul(c[j], rs_s[col0 + j], nz);
+    if (store) ctile[row * 32 + (lane ^ ((row & 3) << 2))] = cv;
+    if (a.psi) psi = fma(n < a.npts ? a.Z[(int64_t)row * a.ldz + n] : 0.0, cv, psi);
   }
   return psi;
 }
@@ -276,8 +299,9 @@ __global__ void __launch_bounds__(GI8_THREADS, 1) gemm_i8_kernel(const __grid_co
   __shared__ uint64_t a_full[4], a_empty[4], b_full, d_full, d_empty[GI8_S];
   __shared__ uint32_t tmem_base_s;
   __shared__ double rs_s[GI8_MAXNB];
-  __shared__ double psi_s[2][4][32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ double psi_s[2][GI8_MAXNB / 16][4][32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: the role branches are divergence-free
   int b = 0;
   while (b + 1 < a.blk.nblk && (int)blockIdx.x >= a.blk.cta0[b + 1]) ++b;
   const int NB = a.blk.rows[b], row0 = a.blk.row0[b];
@@ -293,7 +317,7 @@ __global__ void __launch_bounds__(GI8_THREADS, 1) gemm_i8_kernel(const __grid_co
     for (int s = 0; s < NSA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(&b_full, 1);
     mbar_init(&d_full, 1);
-    for (int g = 0; g < GI8_S; ++g) mbar_init(&d_empty[g], 8);
+    for (int g = 0; g < GI8_S; ++g) mbar_init(&d_empty[g], 4 * (NB / 16));
   }
   if (tid < NB) rs_s[tid] = a.rs[row0 + tid];
   if (warp == 1) {
@@ -303,27 +327,41 @@ __global__ void __launch_bounds__(GI8_THREADS, 1) gemm_i8_kernel(const __grid_co
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0 && n_my > 0) {
-      mbar_expect_tx(&b_full, (unsigned)(GI8_S * b_slice));
-      for (int s = 0; s < GI8_S; ++s) tma_bulk_g2s(sB + s * b_slice, a.Ws + a.blk.woff[b] + (int64_t)s * b_slice, (unsigned)b_slice, &b_full);
+    if (n_my > 0) {
+      if (gi8_elect_one()) {
+        mbar_expect_tx(&b_full, (unsigned)(GI8_S * b_slice));
+        for (int s = 0; s < GI8_S; ++s) tma_bulk_g2s(sB + s * b_slice, a.Ws + a.blk.woff[b] + (int64_t)s * b_slice, (unsigned)b_slice, &b_full);
+      }
+      __syncwarp();
       int ia = 0;
       for (int it = 0; it < n_my; ++it) {
         const int8_t* src = a.Zs + (int64_t)(gidx + it * gsize) * KB * GI8_A_STAGE;
         for (int kb = 0; kb < KB; ++kb, ++ia) {
           const int st = ia % NSA;
-          if (ia >= NSA) mbar_wait(&a_empty[st], (unsigned)(((ia / NSA) - 1) & 1));
-          mbar_expect_tx(&a_full[st], GI8_A_STAGE);
-          tma_bulk_g2s(sA + st * GI8_A_STAGE, src + (int64_t)kb * GI8_A_STAGE, GI8_A_STAGE, &a_full[st]);
+          if (ia >= NSA) gi8_wait_relaxed(&a_empty[st], (unsigned)(((ia / NSA) - 1) & 1));
+          if (gi8_elect_one()) {
+#if defined(GI8_KO) && (GI8_KO & 4)   // development knock-out: no Z traffic (the MMAs read whatever is in the ring)
+            mbar_expect_tx(&a_full[st], 0);
+            (void)src;
+#else
+            mbar_expect_tx(&a_full[st], GI8_A_STAGE);
+            tma_bulk_g2s(sA + st * GI8_A_STAGE, src + (int64_t)kb * GI8_A_STAGE, GI8_A_STAGE, &a_full[st]);
+#endif
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0 && n_my > 0) {
+    // The whole warp walks the loop and waits on the barriers; ONE elected lane issues.  With the issue under `if (lane == 0)`
+    // the operands live in per-thread registers and the compiler wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY
+    // "uniformisation" loop: ~75 cycles per MMA measured against the 52 of the tensor pipe itself.
+    if (n_my > 0) {
       // instruction descriptor: D s32 (2 << 4), A / B signed 8 bit (1 << 7, 1 << 10), both K-major, N = NB, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(GI8_BM >> 4) << 24);
       const uint32_t hi = gi8_desc_hi(128);
@@ -331,50 +369,89 @@ __global__ void __launch_bounds__(GI8_THREADS, 1) gemm_i8_kernel(const __grid_co
       const uint32_t b_lo0 = g32_desc_lo(g32_smem_u32(sB), (uint32_t)NB * 16);
       mbar_wait(&b_full, 0);
       int ia = 0;
+#ifdef GI8_PROFILE
+      long long t_a = 0, t_d = 0, t_all = clock64();
+#define GI8_T0 const long long t0__ = clock64()
+#define GI8_T1(acc) acc += clock64() - t0__
+#else
+#define GI8_T0
+#define GI8_T1(acc)
+#endif
       for (int it = 0; it < n_my; ++it) {
         for (int kb = 0; kb < KB; ++kb, ++ia) {
           const int st = ia % NSA;
-          mbar_wait(&a_full[st], (unsigned)((ia / NSA) & 1));
+          { GI8_T0; mbar_wait(&a_full[st], (unsigned)((ia / NSA) & 1)); GI8_T1(t_a); }
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t a_lo = g32_desc_lo(g32_smem_u32(sA + st * GI8_A_STAGE), 2048);
           const uint32_t b_lo = b_lo0 + (uint32_t)(kb * 2 * NB);   // k-block kb = 16-feature chunks 2 kb, 2 kb + 1 (NB * 16 bytes each)
+          if (kb == 0 && it > 0) {
+            // first k-block of a tile: digit group by digit group in the order the epilogue drains the previous tile's
+            // accumulators (consecutive MMAs on ONE accumulator run at ~80 cycles each instead of 52, hidden behind the drain)
 #pragma unroll
-          for (int g = GI8_S - 1; g >= 0; --g) {                // digit group g + 2, in the order the epilogue drains them
-            if (kb == 0 && it > 0) {
-              mbar_wait(&d_empty[g], (unsigned)((it - 1) & 1));
+            for (int g = GI8_S - 1; g >= 0; --g) {
+              { GI8_T0; mbar_wait(&d_empty[g], (unsigned)((it - 1) & 1)); GI8_T1(t_d); }
               asm volatile("tcgen05.fence::after_thread_sync;");
-            }
+              if (gi8_elect_one()) {
 #pragma unroll
-            for (int i = 0; i <= g; ++i)                        // digits i + 1 of Z and g - i + 1 of W2
-              gi8_mma(tmem + (uint32_t)(g * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)(g - i), hi, idesc, (kb | i) ? 1u : 0u);
+                for (int i = 0; i <= g; ++i)                    // digits i + 1 of Z and g - i + 1 of W2
+                  gi8_mma(tmem + (uint32_t)(g * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)(g - i), hi, idesc, i ? 1u : 0u);
+              }
+              __syncwarp();
+            }
+          } else {
+            // every other k-block: consecutive MMAs go to DIFFERENT accumulators (digit i + 1 of Z against digits 1 .. S - i of W2),
+            // the order tools/i8_probe.cu measured at the shared-memory floor of 32 + NB / 4 cycles per MMA
+            if (gi8_elect_one()) {
+#pragma unroll
+              for (int i = 0; i < GI8_S; ++i)
+#pragma unroll
+                for (int j = 0; j < GI8_S - i; ++j)
+                  gi8_mma(tmem + (uint32_t)((i + j) * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)j, hi, idesc, (kb | i) ? 1u : 0u);
+            }
+            __syncwarp();
           }
-          g32_commit(&a_empty[st]);
+          if (gi8_elect_one()) g32_commit(&a_empty[st]);
+          __syncwarp();
         }
-        g32_commit(&d_full);
+        if (gi8_elect_one()) g32_commit(&d_full);
+        __syncwarp();
       }
+#ifdef GI8_PROFILE
+      if (lane == 0) {
+      a.prof[blockIdx.x * 8 + 0] = clock64() - t_all;
+      a.prof[blockIdx.x * 8 + 1] = t_a;
+      a.prof[blockIdx.x * 8 + 2] = t_d;
+      a.prof[blockIdx.x * 8 + 3] = n_my;
+      }
+#endif
     }
   } else {
-    // ================= epilogue: warps 2..9; warp w reads TMEM lanes 32 (w % 4) .. + 31, column half (w - 2) / 4 =================
-    const int q = warp & 3, h = (warp - 2) >> 2;
-    const int nu0 = (NB / 16 + 1) / 2;                      // 16-column units of the first half: 80 -> 3 + 2, 64 -> 2 + 2, 48 -> 2 + 1
-    const int nu = h == 0 ? nu0 : NB / 16 - nu0, col0 = h == 0 ? 0 : 16 * nu0;
+    // ================= epilogue: warps 2..21; warp w reads TMEM lanes 32 (w % 4) .. + 31, columns 16 u .. 16 u + 15, u = (w - 2) / 4 ====
+    const int q = warp & 3, u = (warp - 2) >> 2, nunits = NB / 16;
+    if (u < nunits)
     for (int it = 0; it < n_my; ++it) {
       const int64_t p0 = (int64_t)(gidx + it * gsize) * GI8_BM + 32 * q;
-      mbar_wait(&d_full, (unsigned)(it & 1));
+#ifdef GI8_PROFILE
+      const long long e0 = clock64();
+#endif
+      gi8_wait_relaxed(&d_full, (unsigned)(it & 1));
+#ifdef GI8_PROFILE
+      const long long e1 = clock64();
+#endif
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
-      double psi;
-      switch (nu) {
-        case 0: psi = gi8_epilogue<0>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
-        case 1: psi = gi8_epilogue<1>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
-        case 2: psi = gi8_epilogue<2>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
-        default: psi = gi8_epilogue<3>(a, tl, NB, row0, col0, p0, lane, d_empty, rs_s); break;
-      }
-      if (a.psi) {   // the two column halves of a lane quarter: the second parks its sum, the first adds it and stores (fixed order);
-                     // psi_s is double-buffered over the tiles, so one 64-thread named barrier per tile is enough
-        if (h == 1) psi_s[it & 1][q][lane] = psi;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        if (h == 0 && p0 + lane < a.npts) a.psi[(int64_t)b * a.ld_psi + p0 + lane] = psi + psi_s[it & 1][q][lane];
+      const double psi = gi8_epilogue16(a, tmem + ((uint32_t)(32 * q) << 16), NB, row0, 16 * u, p0, lane, d_empty, rs_s);
+#ifdef GI8_PROFILE
+      if (warp == 2 && lane == 0) { a.prof[blockIdx.x * 8 + 4] += e1 - e0; a.prof[blockIdx.x * 8 + 5] += clock64() - e1; }
+#endif
+      if (a.psi) {   // the column units of a lane quarter park their sums, unit 0 adds them in a fixed order and stores;
+                     // psi_s is double-buffered over the tiles, so one named barrier (quarter q, 32 nunits threads) per tile is enough
+        psi_s[it & 1][u][q][lane] = psi;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * nunits) : "memory");
+        if (u == 0 && p0 + lane < a.npts) {
+          double t = 0.0;
+          for (int k = 0; k < nunits; ++k) t += psi_s[it & 1][k][q][lane];
+          a.psi[(int64_t)b * a.ld_psi + p0 + lane] = t;
+        }
       }
     }
   }
