@@ -42,6 +42,13 @@ CONFIGS = {
                  kernel="PolynomialDecay(truncation_level=10)"),
 }
 PREFIX_ROWS = 200_000   # rows of the sharded-vs-single / two-device self-checks
+PRECISION = {"f64": "f64i8", "f64dmma": "f64", "f32": "f32"}   # --dtype -> HotPath precision
+CONTRACTION = {
+    "f64": "C = W2 Z on the FP64 tensor cores (DMMA m8n8k4)",
+    "f64i8": "C = W2 Z as an error-free split into 6 x 6 signed radix-256 digits, 21 tcgen05 kind::i8 products into exact int32 TMEM "
+             "accumulators, recombined in float64 (normwise ~1e-14; GPFY_PREC_F64_I8); everything else float64",
+    "f32": "C = W2 Z and the weighted Gram matrix as 3 x TF32 on tcgen05 (GPFY_PREC_TF32X3); everything else float64",
+}
 
 
 def parse():
@@ -53,8 +60,10 @@ def parse():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--n", type=float, default=None, help="total rows over all ranks (default: the config's N)")
     ap.add_argument("--T", type=int, default=None, help="phase truncation (default: the config's T)")
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
-                    help="f64: the reference's precision (headline).  f32: the dense contraction as 3 x TF32 on tcgen05 (GPFY_PREC_TF32X3)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f64dmma", "f32"],
+                    help="f64: the reference's precision (headline): float64 results, the dense contraction as exact int8 digit products "
+                         "on tcgen05 where built (GPFY_PREC_F64_I8), DMMA elsewhere.  f64dmma: DMMA only (GPFY_PREC_F64).  "
+                         "f32: the contraction as 3 x TF32 on tcgen05 (GPFY_PREC_TF32X3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the Phi-only / predict_diag / train-step side measurements")
@@ -65,6 +74,7 @@ def parse():
         c["N"] = int(a.n)
     if a.T is not None:
         c["T"] = int(a.T)
+    c["precision"] = PRECISION[a.dtype]
     a.cfg = c
     return a
 
@@ -199,7 +209,7 @@ def sharded_prefix_check(c, dev, rank, world, allreduce):
     import torch
     from gpfy_b200 import synthetic
     n = min(PREFIX_ROWS, c["N"])
-    kw = dict(d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev)
+    kw = dict(d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev, precision=c.get("precision", "f64"))
     mine = synthetic.headline_problem(n, rank=rank, world=world, **kw)
     part = mine["hot"].elbo_valgrad_packed(*mine["args"]).clone()
     allreduce(part)
@@ -217,7 +227,7 @@ def two_device_threads_check(c, devices):
     import torch
     from gpfy_b200 import synthetic
     n = min(PREFIX_ROWS, c["N"])
-    kw = dict(d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"])
+    kw = dict(d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], precision=c.get("precision", "f64"))
     res, err = [None, None], [None, None]
 
     def work(i):
@@ -266,7 +276,7 @@ def run_ours(a):
         dist.init_process_group(backend="nccl", device_id=dev)
     N = int(c["N"])
     prob = synthetic.headline_problem(N, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev,
-                                      rank=rank, world=world, precision=a.dtype)
+                                      rank=rank, world=world, precision=PRECISION[a.dtype])
     hp, args = prob["hot"], prob["args"]
     X, Y = args[0], args[1]
     n_local = X.shape[0]
@@ -373,54 +383,86 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (FP64 tensor-core GEMM  C = W2 Z), timed live with CUDA events ----
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream (gpfy_debug_kernel_timing) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))
     except OSError:
         pass
     fp64_peak = float(peaks.get("dmma884_bps8_tflops", 37.1))
-    g_ms, g_n = ktimes["gemm_dmma"]
-    M, P = prob["M"], hp.P
-    pts_per_launch = n_local * a.steps / max(g_n, 1)
-    # algorithmic flops of the contraction the kernel carries: L_q^T a (M^2) and L_q (L_q^T a) (M^2) per row and
-    # output, counting the triangular structure; the kernel executes 2 Mp^2 on the folded dense matrix
-    gemm_alg_flops = 2.0 * M * M * pts_per_launch
-    g_avg_s = g_ms * 1e-3 / max(g_n, 1)
-    achieved = gemm_alg_flops / g_avg_s * 1e-12
-    traffic = None
+    fp64_src = ("measured FP64 DMMA peak on this pool's B200 (profiles/fp64_peak_r01.json, tools/fp64_peak.cu); "
+                "MEASURED_PEAKS.json has no FP64 entry and tcgen05 has no f64 kind")
+    measured = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("gemm_dmma_kernel", {}).get("dram_bytes_per_launch")
+        measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    if a.config != "cfg3" or a.dtype != "f64":
-        traffic = None   # the committed ncu capture is of the headline shape
+    M, P = prob["M"], hp.P
+    Mp = (M + 31) // 32 * 32
+    path = hp.contraction_path(n_local)
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    except (OSError, ValueError):
+        pass
+
+    def kernel_line(key, name, alg_per_point, peak, unit, bound, src, ncu_key=None):
+        k_ms, k_n = ktimes.get(key, (0.0, 0))
+        if k_n == 0 or k_ms <= 0.0:
+            return None
+        pts = n_local * a.steps / k_n
+        avg_s = k_ms * 1e-3 / k_n
+        ach = alg_per_point * pts / avg_s * (1e-12 if unit.startswith("TFLOP") else 1e-9)
+        traffic = ncu.get(ncu_key, {}).get("dram_bytes_per_launch") if (ncu_key and a.config == "cfg3" and ncu.get("dtype", "f64dmma") == a.dtype) else None
+        return {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
+                "peak_source": src, "avg_launch_ms": avg_s * 1e3, "launches": k_n, "points_per_launch": pts,
+                "alg_per_point_kernel": alg_per_point, "kernel_share_of_step": k_ms / (ms * a.steps)}
+
+    classes = {}
+    if path == "f64i8":
+        # the float64 contraction as 21 int8 digit products: algorithmic flops 2 M^2 per point, against the int8 tensor peak expressed
+        # in float64-equivalent flops (8192 int8 MAC/clk/SM measured by tools/i8_probe.cu at N = 256 = 4.77 POP/s at 1.965 GHz, / 21)
+        i8_peak = 2.0 * 8192 * 148 * 1.965e9 * 1e-12
+        classes["gemm"] = kernel_line("gemm_dmma", "gemm_i8_kernel (tcgen05 kind::i8, 21 digit products per float64 product, TMEM accumulators, TMA bulk loads)",
+                                      2.0 * M * M, i8_peak / 21.0, "TFLOP/s", "tensor",
+                                      "int8 dense peak measured on this pool's B200 (tools/i8_probe.cu: 8191 MAC/clk/SM back to back = 4 765 TOP/s at 1 965 MHz) "
+                                      "/ 21 digit products per float64-accurate product; achieved counts the algorithmic 2 M^2 flops per point once",
+                                      "gemm_i8_kernel")
+        classes["i8_slice"] = kernel_line("i8_slice", "z_slice_i8_kernel (float64 panel -> six int8 digit planes)", 14.0 * Mp,
+                                          float(measured.get("hbm_gbs", 6549.8)), "GB/s", "hbm",
+                                          "MEASURED_PEAKS.json hbm_gbs; bytes = 8 Mp read + 6 Mp written per point", "z_slice_i8_kernel")
+    elif path == "f32":
+        bf16 = float(measured.get("bf16_tflops", 1638.0))
+        classes["gemm"] = kernel_line("gemm_dmma", "gemm_tf32x3_kernel (tcgen05 kind::tf32, 3 MMAs per product, TMEM accumulators, TMA tensor loads)",
+                                      2.0 * M * M, bf16 / 2.0 / 3.0, "TFLOP/s", "tensor",
+                                      "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate) / 3 (three TF32 MMAs per "
+                                      "fp32-accurate product); achieved counts the algorithmic 2 M^2 flops per point once")
+    else:
+        # algorithmic flops of the contraction: L_q^T a (M^2) and L_q (L_q^T a) (M^2) per row and output; the kernel
+        # executes 2 Mp^2 on the folded dense matrix
+        classes["gemm"] = kernel_line("gemm_dmma", "gemm_dmma_kernel (FP64 DMMA m8n8k4)", 2.0 * M * M, fp64_peak, "TFLOP/s", "tensor", fp64_src,
+                                      "gemm_dmma_kernel")
+    # weighted Gram matrix G = Z diag(wq) Z^T: M^2 algorithmic flops per point (the symmetric half)
+    classes["syrk"] = kernel_line("syrk_dmma", "syrk_dmma_kernel (FP64 DMMA m8n8k4)" if path != "f32" else "syrk_tf32x3_kernel / syrk_dmma_kernel",
+                                  1.0 * M * M, fp64_peak, "TFLOP/s", "tensor", fp64_src, "syrk_dmma_kernel")
+    z_ms = ktimes["zonal_fwd"][0] + ktimes["zonal_bwd"][0] + ktimes["lik_point"][0] + ktimes["dvhat_dmma"][0]
+    classes = {k: v for k, v in classes.items() if v}
+    dominant = max(classes.values(), key=lambda v: v["kernel_share_of_step"])
     step_tflops = prob["alg_flops_per_point"] * value / world * 1e-12
-    kernel_name, kernel_peak = "gemm_dmma_kernel (FP64 DMMA m8n8k4)", fp64_peak
-    peak_source = ("measured FP64 DMMA peak on this pool's B200 (profiles/fp64_peak_r01.json, tools/fp64_peak.cu); "
-                   "MEASURED_PEAKS.json has no FP64 entry and tcgen05 has no f64 kind")
-    if a.dtype == "f32":
-        bf16 = 1638.0
-        try:
-            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-        except (OSError, ValueError, KeyError):
-            pass
-        kernel_name = "gemm_tf32x3_kernel (tcgen05 kind::tf32, 3 MMAs per product, TMEM accumulators, TMA tensor loads)"
-        kernel_peak = bf16 / 2.0 / 3.0
-        peak_source = ("MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate) / 3 (three TF32 MMAs per "
-                       "fp32-accurate product); achieved counts the algorithmic 2 M^2 flops per point once")
-    roofline = {
-        "bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": kernel_peak,
-        "unit": "TFLOP/s", "frac": achieved / kernel_peak, "traffic": traffic,
-        "peak_source": peak_source,
-        "avg_launch_ms": g_avg_s * 1e3, "launches": g_n, "points_per_launch": pts_per_launch,
-        "alg_flops_per_point_kernel": 2.0 * M * M, "kernel_share_of_step": g_ms / (ms * a.steps),
-        "step": {"alg_flops_per_point": prob["alg_flops_per_point"], "achieved_tflops_per_gpu": step_tflops,
-                 "frac_of_fp64_peak": step_tflops / fp64_peak,
-                 "hbm_alg_bytes_per_point": prob["alg_bytes_per_point"],
-                 "hbm_alg_gbs_per_gpu": prob["alg_bytes_per_point"] * value / world * 1e-9},
-        "kernels_ms_per_step": {k: v[0] / a.steps for k, v in ktimes.items()},
-    }
+    roofline = dict(dominant)
+    roofline["contraction_path"] = path
+    roofline["kernels"] = {k: {kk: v[kk] for kk in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "kernel_share_of_step")}
+                           for k, v in classes.items()}
+    roofline["kernels"]["zonal"] = {"kernel": "zonal_fwd2 + zonal_bwd3/4 (+ lik_point, dvhat)", "bound": "fp64",
+                                    "achieved": (prob["alg_flops_per_point"] - 3.0 * M * M) * n_local / (z_ms * 1e-3 / a.steps) * 1e-12 if z_ms > 0 else None,
+                                    "peak": fp64_peak, "unit": "TFLOP/s", "kernel_share_of_step": z_ms / (ms * a.steps)}
+    roofline["step"] = {"alg_flops_per_point": prob["alg_flops_per_point"], "achieved_tflops_per_gpu": step_tflops,
+                        "frac_of_fp64_peak": step_tflops / fp64_peak,
+                        "note": ("algorithmic float64 flops per second over the FP64 pipe's peak; with the contraction on the int8 tensor cores "
+                                 "(contraction_path f64i8) 2 M^2 of them no longer run on that pipe, so this ratio can exceed what the FP64 pipe alone allows"),
+                        "hbm_alg_bytes_per_point": prob["alg_bytes_per_point"],
+                        "hbm_alg_gbs_per_gpu": prob["alg_bytes_per_point"] * value / world * 1e-9}
+    roofline["kernels_ms_per_step"] = {k: v[0] / a.steps for k, v in ktimes.items()}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -450,20 +492,22 @@ def run_ours(a):
                "grad_rel_diff_gpu_vs_oracle_on_sample": gerr}
 
     f32_err = None
-    if a.dtype == "f32" and world == 1:
-        # the f32 instantiation against the f64 path on the same rows (tolerance of BASELINE.json north_star: 1e-5)
+    if (a.dtype == "f32" or path == "f64i8") and world == 1:
+        # the f32 instantiation against the f64 (DMMA) path on the same rows (tolerance of BASELINE.json north_star: 1e-5); the int8
+        # digit-product contraction is a float64 path: held to 1e-11 against DMMA
+        tol_alt = 1e-5 if a.dtype == "f32" else 1e-11
         S = min(PREFIX_ROWS, N)
         p64 = synthetic.headline_problem(S, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev)
         ref = p64["hot"].unpack(p64["hot"].elbo_valgrad_packed(*p64["args"]))
         got = hp.unpack(hp.elbo_valgrad_packed(X[:S], Y[:S], *args[2:]))
-        f32_err = {"rows": S, "tolerance": 1e-5}
+        f32_err = {"rows": S, "tolerance": tol_alt}
         for k in ref:
             den = float(ref[k].abs().max())
             if den > 0:
                 diff = (got[k] - ref[k]).abs()
                 f32_err[k] = {"max_rel": float(diff.max()) / den, "mean_rel": float(diff.mean()) / den}
-        if max(v["max_rel"] for v in f32_err.values() if isinstance(v, dict)) > 1e-5:
-            raise SystemExit(f"bench.py: the f32 path is outside 1e-5 of the f64 path: {f32_err}")
+        if max(v["max_rel"] for v in f32_err.values() if isinstance(v, dict)) > tol_alt:
+            raise SystemExit(f"bench.py: the {a.dtype} path is outside {tol_alt} of the f64 (DMMA) path: {f32_err}")
         del p64
 
     extras = {}
@@ -472,13 +516,13 @@ def run_ours(a):
 
     line = {
         "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": workload_config(a.config, c, M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if a.dtype == "f64dmma" else a.dtype, "data": "synthetic",
+        "config": dict(workload_config(a.config, c, M, world), contraction=CONTRACTION[path]), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "elbo_data_term": data_term, "kl": float(kl[0]), "checksum": checksum,
         "checks": checks,
     }
     if f32_err is not None:
-        line["f32_vs_f64"] = f32_err
+        line["f32_vs_f64" if a.dtype == "f32" else "i8_vs_dmma"] = f32_err
     line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -111,6 +111,7 @@ _SIGNATURES = {
                                                    _P, _P, _P]),
     "gpfy_step_advance": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int64, _P, _P, ctypes.c_int64]),
     "gpfy_chunk_rows": (ctypes.c_int, [ctypes.POINTER(GpfyDesc), ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "gpfy_contraction_path": (ctypes.c_int, [ctypes.POINTER(GpfyDesc), ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]),
     "gpfy_kmat_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(GpfyDesc), ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "gpfy_shape_function": (ctypes.c_int, [_P, ctypes.POINTER(GpfyShapeFn), ctypes.c_double, _P, ctypes.c_int64, _P]),
     "gpfy_kernel_matrix": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyShapeFn), ctypes.c_int64, _P, ctypes.c_int64, _P,

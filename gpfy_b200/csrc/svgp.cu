@@ -1167,6 +1167,16 @@ int gpfy_chunk_rows(const GpfyDesc* desc, int64_t n_points, int64_t* rows) {
   return GPFY_OK;
 }
 
+int gpfy_contraction_path(const GpfyDesc* desc, int64_t n_points, int op, int32_t* path) {
+  Shape s;
+  GPFY_TRY(make_shape(desc, &s));
+  if (!path || n_points < 0 || (op != GPFY_OP_ELBO && op != GPFY_OP_PREDICT)) { set_error("bad argument"); return GPFY_EINVAL; }
+  Plan p;
+  make_plan(s, n_points, op, &p, desc->precision);
+  *path = p.f32 ? GPFY_PREC_TF32X3 : (p.i8 ? GPFY_PREC_F64_I8 : GPFY_PREC_F64);
+  return GPFY_OK;
+}
+
 int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op, size_t* bytes) {
   Shape s;
   GPFY_TRY(make_shape(desc, &s));

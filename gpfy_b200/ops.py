@@ -156,6 +156,13 @@ class HotPath:
             _ptr(out), _ptr(ws), ws.numel()))
         return out
 
+    def contraction_path(self, n, op=_lib.OP_ELBO):
+        """'f64' (DMMA), 'f64i8' (int8 digit products on tcgen05, float64-accurate) or 'f32' (3 x TF32): the arithmetic the
+        dense contraction C = W2 Z runs in for `n` rows on this device (gpfy_contraction_path)."""
+        path = ctypes.c_int32(0)
+        _lib.check(self.lib.gpfy_contraction_path(ctypes.byref(self.desc), int(max(n, 1)), int(op), ctypes.byref(path)))
+        return {_lib.PREC_F64: "f64", _lib.PREC_TF32X3: "f32", _lib.PREC_F64_I8: "f64i8"}[path.value]
+
     # ---- host-resident data: rows are streamed through the device slab by slab ----
     def slab_rows(self, n):
         """Rows per streamed slab: one internal chunk of the kernels (gpfy_chunk_rows; 0.9 M rows at the headline shape)."""

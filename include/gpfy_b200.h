@@ -121,6 +121,11 @@ GPFY_API int gpfy_workspace_bytes(const GpfyDesc* desc, int64_t n_points, int op
  * callers that stream slabs through gpfy_svgp_elbo_rows size their slabs as multiples of it. */
 GPFY_API int gpfy_chunk_rows(const GpfyDesc* desc, int64_t n_points, int64_t* rows /* host */);
 
+/* Which arithmetic the dense contraction of `op` (GPFY_OP_ELBO / GPFY_OP_PREDICT) runs in for this descriptor on the current
+ * device: GPFY_PREC_F64_I8 is a request - shapes the int8 kernel is not built for run the DMMA contraction (GPFY_PREC_F64), with
+ * the same float64 contract.  Host call, no GPU work. */
+GPFY_API int gpfy_contraction_path(const GpfyDesc* desc, int64_t n_points, int op, int32_t* path /* host: GPFY_PREC_* */);
+
 /* Elementwise Gegenbauer polynomial and its derivative 2*alpha*C_{level-1}^{alpha+1}
  * (replaces gegenbauer.py:27-85: `gegenbauer`, `gegenbauer_fwd`).  `dout` may be NULL. */
 GPFY_API int gpfy_gegenbauer(void* stream, int level, double alpha, const double* x, int64_t n, double* out, double* dout);
