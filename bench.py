@@ -42,7 +42,7 @@ CONFIGS = {
                  kernel="PolynomialDecay(truncation_level=10)"),
 }
 PREFIX_ROWS = 200_000   # rows of the sharded-vs-single / two-device self-checks
-PRECISION = {"f64": "f64i8", "f64dmma": "f64", "f32": "f32"}   # --dtype -> HotPath precision
+PRECISION = {"f64": "f64", "f64dmma": "f64dmma", "f32": "f32"}   # --dtype -> HotPath precision
 CONTRACTION = {
     "f64": "C = W2 Z on the FP64 tensor cores (DMMA m8n8k4)",
     "f64i8": "C = W2 Z as an error-free split into 6 x 6 signed radix-256 digits, 21 tcgen05 kind::i8 products into exact int32 TMEM "
@@ -497,7 +497,7 @@ def run_ours(a):
         # digit-product contraction is a float64 path: held to 1e-11 against DMMA
         tol_alt = 1e-5 if a.dtype == "f32" else 1e-11
         S = min(PREFIX_ROWS, N)
-        p64 = synthetic.headline_problem(S, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev)
+        p64 = synthetic.headline_problem(S, d=c["d"], F=c["F"], T=c["T"], likelihood=c["lik"], seed=c["seed"], device=dev, precision="f64dmma")
         ref = p64["hot"].unpack(p64["hot"].elbo_valgrad_packed(*p64["args"]))
         got = hp.unpack(hp.elbo_valgrad_packed(X[:S], Y[:S], *args[2:]))
         f32_err = {"rows": S, "tolerance": tol_alt}

@@ -34,6 +34,7 @@ constexpr int GI8_THREADS = 704;               // producer warp, MMA warp, 20 ep
 constexpr int GI8_A_STAGE = GI8_S * 4096;      // bytes of one k-block (32 features) of a tile, all digits
 constexpr int GI8_MAXBLK = 8;
 constexpr int GI8_MAXNB = 80;
+constexpr int GI8_STATIC_SMEM = 12 * 1024;    // barriers, row scales, psi staging (2 x 5 x 4 x 32 doubles): see gemm_i8_kernel
 #ifndef GI8_SLEEP_NS
 #define GI8_SLEEP_NS 64
 #endif
@@ -98,7 +99,7 @@ static inline bool gi8_plan(int Mp, int sms, GemmI8Blocks* b, int* nsa) {
   for (int i = 0; left > 0; i = (i + 1) % nblk, --left)
     for (int j = i + 1; j <= nblk; ++j) b->cta0[j] += 1;
   if (b->cta0[nblk] > sms) return false;
-  const int avail = 227 * 1024 - 2048 - GI8_S * maxrows * Mp;
+  const int avail = 227 * 1024 - 1024 - GI8_STATIC_SMEM - GI8_S * maxrows * Mp;   // alignment slack, static shared memory, resident W2 planes
   *nsa = avail / GI8_A_STAGE;
   if (*nsa > 4) *nsa = 4;
   return *nsa >= 2;

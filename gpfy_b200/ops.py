@@ -54,6 +54,12 @@ def shape_function(fn, alpha, x, device=None):
     return out
 
 
+# precision of the dense contraction C = W2 Z (include/gpfy_b200.h GPFY_PREC_*).  "f64" - the default, float64 results to the
+# reference's 1e-10 contract - runs it as exact int8 digit products on tcgen05 where that kernel is built (P = 1, M <= 352, one of
+# the fused backward kernels; ~1e-14 normwise) and on the FP64 tensor cores elsewhere; "f64dmma" forces the DMMA kernel everywhere.
+PRECISIONS = {"f64": _lib.PREC_F64_I8, "f64i8": _lib.PREC_F64_I8, "f64dmma": _lib.PREC_F64, "f32": _lib.PREC_TF32X3, "tf32x3": _lib.PREC_TF32X3}
+
+
 class HotPath:
     """One descriptor + cached scratch.  Mirrors the static configuration of
     (SphericalHarmonics, kernel, q, likelihood) in the reference."""
@@ -76,7 +82,7 @@ class HotPath:
             _lib.LIK_GAUSSIAN if likelihood == "gaussian" else _lib.LIK_BERNOULLI,
             _lib.Q_TRIL if q_kind == "tril" else _lib.Q_FULLCOV,
             {"scalar": _lib.W_SCALAR, "projection": _lib.W_PROJECTION}.get(weight_mode, _lib.W_ARD), self.projection_dim,
-            {"f64": _lib.PREC_F64, "f32": _lib.PREC_TF32X3, "tf32x3": _lib.PREC_TF32X3, "f64i8": _lib.PREC_F64_I8}[precision])
+            PRECISIONS[precision])
         self.precision = precision
         self.nw = self.input_dim * self.projection_dim if self.projection_dim else (1 if self.scalar_w else self.input_dim)
         self.layout = _lib.GpfyElboLayout()

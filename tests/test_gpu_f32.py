@@ -36,7 +36,7 @@ def test_f32_elbo_gradients_and_predictions_match_f64_on_goldens(name):
     vhat, lcat = _cat(pack)
     sigma = pack.get("Lq", pack.get("Sigma"))
     args = (g["X"], g["Y"], pack["w"], pack["b"], pack["v"], pack["eig"], vhat, lcat, pack["mu"], sigma, pack.get("sigma2"))
-    h64, h32 = _hot(pack, g, "f64"), _hot(pack, g, "f32")
+    h64, h32 = _hot(pack, g, "f64dmma"), _hot(pack, g, "f32")
     a = {k: v.cpu().numpy() for k, v in h64.unpack(h64.elbo_valgrad_packed(*args)).items()}
     b = {k: v.cpu().numpy() for k, v in h32.unpack(h32.elbo_valgrad_packed(*args)).items()}
     for k in a:
@@ -61,7 +61,7 @@ def test_f32_matches_f64_at_the_bench_shapes(d, F, T, lik, N):
     fp32-level error of G by cond(L_l)^2 - 4.5e-4 measured - which no fp32 evaluation can avoid; the reference's own
     well-conditioned fundamental systems on S^2 are covered by the golden cases above.)"""
     from gpfy_b200.synthetic import headline_problem
-    p64 = headline_problem(N, d=d, F=F, T=T, likelihood=lik, device="cuda")
+    p64 = headline_problem(N, d=d, F=F, T=T, likelihood=lik, device="cuda", precision="f64dmma")
     p32 = headline_problem(N, d=d, F=F, T=T, likelihood=lik, device="cuda", precision="f32")
     a = p64["hot"].unpack(p64["hot"].elbo_valgrad_packed(*p64["args"]))
     b = p32["hot"].unpack(p32["hot"].elbo_valgrad_packed(*p32["args"]))

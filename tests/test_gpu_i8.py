@@ -30,7 +30,7 @@ def test_i8_elbo_gradients_and_predictions_match_goldens_and_dmma(name):
     vhat, lcat = _cat(pack)
     sigma = pack.get("Lq", pack.get("Sigma"))
     args = (g["X"], g["Y"], pack["w"], pack["b"], pack["v"], pack["eig"], vhat, lcat, pack["mu"], sigma, pack.get("sigma2"))
-    h64, h8 = _hot(pack, g, "f64"), _hot(pack, g, "f64i8")
+    h64, h8 = _hot(pack, g, "f64dmma"), _hot(pack, g, "f64i8")
     a = {k: v.cpu().numpy() for k, v in h64.unpack(h64.elbo_valgrad_packed(*args)).items()}
     b = {k: v.cpu().numpy() for k, v in h8.unpack(h8.elbo_valgrad_packed(*args)).items()}
     for k in a:
@@ -50,7 +50,7 @@ def test_i8_elbo_gradients_and_predictions_match_goldens_and_dmma(name):
 def test_i8_matches_dmma_at_the_bench_shapes(d, F, T, lik, N):
     """cfg3 / cfg4 / cfg5 shapes, S^2 and an M = 200 case (four out-blocks of 64 / 48 rows), tail tiles included."""
     from gpfy_b200.synthetic import headline_problem
-    p64 = headline_problem(N, d=d, F=F, T=T, likelihood=lik, device="cuda")
+    p64 = headline_problem(N, d=d, F=F, T=T, likelihood=lik, device="cuda", precision="f64dmma")
     p8 = headline_problem(N, d=d, F=F, T=T, likelihood=lik, device="cuda", precision="f64i8")
     a = p64["hot"].unpack(p64["hot"].elbo_valgrad_packed(*p64["args"]))
     b = p8["hot"].unpack(p8["hot"].elbo_valgrad_packed(*p8["args"]))
@@ -73,7 +73,7 @@ def test_i8_is_exactly_zero_at_the_prior():
     M = p["M"]
     args[9] = torch.eye(M, dtype=torch.float64, device="cuda").reshape(1, M, M)
     pa = [args[i] for i in (0, 2, 3, 4, 5, 6, 7, 8, 9)]
-    p64 = headline_problem(5000, device="cuda")
+    p64 = headline_problem(5000, device="cuda", precision="f64dmma")
     _, v8 = p["hot"].predict_diag(*pa)
     _, v64 = p64["hot"].predict_diag(*pa)
     assert torch.equal(v8, v64)
