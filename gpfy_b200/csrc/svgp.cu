@@ -985,12 +985,12 @@ static int slice_w2_i8(cudaStream_t st, const GpfyDesc* desc, const Plan& p, dou
   return GPFY_OK;
 }
 // Z panel -> digit planes, then C (blocked, may be null) and / or the psi slabs for npts points of the chunk
-static int launch_gemm_i8(cudaStream_t st, const Plan& p, double* ws, int64_t npts, double* C, double* psi) {
+static int launch_gemm_i8(cudaStream_t st, const Plan& p, double* ws, int64_t npts, double* C, double* psi, bool sliced = false) {
   const Shape& s = p.s;
   const int Mp = s.Mp;
   int8_t* zs = reinterpret_cast<int8_t*>(ws + p.o_Zi8);
   const int tiles = (int)((npts + GI8_BM - 1) / GI8_BM);
-  {
+  if (!sliced) {   // (on the fused Gaussian path the weighted-Gram kernel, launched first, has already written the digit planes)
     GPFY_TIMED(TK_SLICE, st);
     GPFY_K(z_slice_i8_kernel, dim3((unsigned)tiles, (unsigned)(Mp / 16)), GI8_BM, 0, st, ws + p.o_Z, p.nc, Mp, npts, ws + p.o_ks8, zs);
   }
@@ -1423,11 +1423,36 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal<DIMP>(st, za)));
     }
 
+    // G += Z diag(wq) Z^T, bz += Z wp (P outputs).  On the fused Gaussian path the weights are known after the forward kernel, so
+    // the weighted Gram matrix can run BEFORE the contraction - and then its diagonal-block CTAs also cut Z into the int8 digit planes.
+    auto launch_syrk = [&](bool slice) -> int {
+      if (p.f32s) {
+        GPFY_TIMED(TK_SYRK, st);
+        return launch_syrk32(st, p, ws, npts);
+      }
+      for (int q = 0; q < s.P; ++q) {
+        GPFY_TIMED(TK_SYRK, st);
+        SyrkArgs sa;
+        sa.Z = ws + p.o_Z; sa.ldz = p.nc; sa.Mp = Mp; sa.npts = npts;
+        sa.wq = ws + p.o_wq + (int64_t)q * p.nc; sa.wp = ws + p.o_wp + (int64_t)q * p.nc;
+        sa.Gpart = ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B;
+        sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B;
+        sa.split = p.split; sa.chunk = npts;   // the splits cover THIS launch's rows (a short slab still uses every CTA)
+        sa.accumulate = 1;
+        if (slice) { sa.zs_out = reinterpret_cast<int8_t*>(ws + p.o_Zi8); sa.kscale = ws + p.o_ks8; }
+        GPFY_TRY(device_configure_once(DEV_CFG_SYRK, (const void*)syrk_dmma_kernel, SYRK_SMEM));
+        GPFY_K(syrk_dmma_kernel, p.split.total(), SYRK_THREADS, SYRK_SMEM, st, sa);
+      }
+      return GPFY_OK;
+    };
+    const bool syrk_first = p.i8 && fuse_lik && !debug_option(DBG_NO_SYRK_SLICE);
+    if (syrk_first) GPFY_TRY(launch_syrk(true));
+
     if (p.f32) {  // C = W2 Z on tcgen05 in 3 x TF32 (P = 1); psi goes out as one slab
       GPFY_TIMED(TK_GEMM, st);
       GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi));
     } else if (p.i8) {  // C = W2 Z as exact int8 digit products on tcgen05 (P = 1); psi in one slab per out-block
-      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi));
+      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi, syrk_first));
     } else
     for (int q = 0; q < s.P; ++q) {  // C_q = W2_q Z
       GPFY_TIMED(TK_GEMM, st);
@@ -1488,22 +1513,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_zonal_bwd<DIMP>(st, zb)));
     }
 
-    if (p.f32s) {
-      GPFY_TIMED(TK_SYRK, st);
-      GPFY_TRY(launch_syrk32(st, p, ws, npts));
-    } else
-    for (int q = 0; q < s.P; ++q) {
-      GPFY_TIMED(TK_SYRK, st);
-      SyrkArgs sa;
-      sa.Z = ws + p.o_Z; sa.ldz = p.nc; sa.Mp = Mp; sa.npts = npts;
-      sa.wq = ws + p.o_wq + (int64_t)q * p.nc; sa.wp = ws + p.o_wp + (int64_t)q * p.nc;
-      sa.Gpart = ws + p.o_Gpart + (int64_t)q * p.split.total() * SYRK_B * SYRK_B;
-      sa.bzpart = ws + p.o_bzpart + (int64_t)q * p.split.bslot(p.nb) * SYRK_B;
-      sa.split = p.split; sa.chunk = npts;   // the splits cover THIS launch's rows (a short slab still uses every CTA)
-      sa.accumulate = 1;
-      GPFY_TRY(device_configure_once(DEV_CFG_SYRK, (const void*)syrk_dmma_kernel, SYRK_SMEM));
-      GPFY_K(syrk_dmma_kernel, p.split.total(), SYRK_THREADS, SYRK_SMEM, st, sa);
-    }
+    if (!syrk_first) GPFY_TRY(launch_syrk(false));
 
     if (!fused && !bwd4) {
       DvhatArgs da;

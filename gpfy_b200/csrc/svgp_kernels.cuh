@@ -3,6 +3,7 @@
 // points contiguous, like the reference's [M, N] arrays); C = W2 Z; dT = cotangent of t = Vhat xhat.
 #pragma once
 #include "common.cuh"
+#include "gemm_i8.cuh"
 #include "gh20.h"
 
 namespace gpfy {
@@ -680,7 +681,30 @@ struct SyrkArgs {
   SyrkSplit split;
   int64_t chunk;      // rows of a full chunk: block type t covers it in split.ks[t] ranges of ceil(chunk / ks[t]) rows (multiple of 16)
   int accumulate;
+  // GPFY_PREC_F64_I8 on the fused path: the diagonal-block CTAs, through whose shared memory every element of the panel passes
+  // exactly once, also cut it into the int8 digit planes of the contraction (gemm_i8.cuh) - the separate slicing pass (a full
+  // read of the float64 panel, HBM-bound) disappears.  Null = no slicing.
+  int8_t* zs_out = nullptr;
+  const double* kscale = nullptr;   // [Mp] 2^48 / s_k
 };
+
+// One k-step (16 points) of the slicing: thread = one point x 16 features of the stage; the six 16-byte digit vectors of 16
+// consecutive points are contiguous in the digit-plane image (256 bytes per plane).
+__device__ __forceinline__ void syrk_slice_step(const double* zs, const double* ksc, int c, int pt, int8_t* dst) {
+  Digits16 d;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint64_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = 16 * c + 4 * w + j;
+      t[j] = gi8_digits(zs[f * (SYRK_BK + 4) + pt], ksc[f]);
+    }
+    gi8_pack4(t, d, w);
+  }
+#pragma unroll
+  for (int s = 0; s < GI8_S; ++s) *reinterpret_cast<uint4*>(dst + s * 4096) = make_uint4(d.w[s][0], d.w[s][1], d.w[s][2], d.w[s][3]);
+}
 
 // Diagonal blocks only need the lower triangle.  In 8 x 8 tensor-core tiles that is tile row r with columns
 // 0..r (78 of 144 tiles); the 12 tile rows are dealt to the 8 warps as 11 | 10 | 9 | 8 | 7+0 | 6+1 | 5+2 | 4+3, i.e.
@@ -714,6 +738,7 @@ __device__ __forceinline__ void syrk_diag_step(const double* zs, const double* w
 __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint64_t bar_full[SYRK_STAGES], bar_empty[SYRK_STAGES];
+  __shared__ double ksc_s[SYRK_B];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;   // off-diagonal: 4 x 2 warps, warp tile 24 x 48
   const int g = lane >> 2, t4 = lane & 3;
@@ -747,6 +772,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
       mbar_init(&bar_empty[s], SYRK_THREADS / 32);
     }
   }
+  if (a.zs_out && diag && tid < SYRK_B) ksc_s[tid] = (bi * SYRK_B + tid) < a.Mp ? a.kscale[bi * SYRK_B + tid] : 0.0;
   __syncthreads();
 
   // producer: 6 chunks of 16 bytes per thread and stage (Zi rows r, r+32, r+64; same for Zj) + weights;
@@ -845,6 +871,14 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     const double* zs = smem + st * SYRK_STAGE_DBL;
     const double* wqs = zs + 2 * SYRK_B * SYRK_ZS;
     produce();
+    if (a.zs_out && warp >= 5) {   // warps 5..7 (the lightest tensor-core loads): 96 (point, 16-feature chunk) items per k-step
+      const int item = (warp - 5) * 32 + lane, pt = item & 15, c = item >> 4;
+      const int64_t n = p0 + (int64_t)kb * SYRK_BK + pt;
+      const int krow = bi * (SYRK_B / 16) + c;                 // 16-feature chunk of the panel
+      if (n < p1 && krow * 16 < a.Mp)
+        syrk_slice_step(zs, ksc_s, c, pt,
+                        a.zs_out + ((n >> 7) * (int64_t)(a.Mp / 32) + (krow >> 1)) * GI8_A_STAGE + (krow & 1) * 2048 + (int)(n & 127) * 16);
+    }
     switch (warp) {
       case 0: syrk_diag_step<11, -1>(zs, wqs, acc, accx, g, t4); break;
       case 1: syrk_diag_step<10, -1>(zs, wqs, acc, accx, g, t4); break;

@@ -110,6 +110,80 @@ __global__ void __launch_bounds__(192, 1) probe(const int8_t* Aimg, const int8_t
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// ---- TS variant: the A planes are copied once per k-block from shared memory into TMEM (tcgen05.cp 128x256b) and the MMAs read A
+// from there, so an MMA's shared-memory traffic is B only (32 N bytes instead of 4096 + 32 N) ----
+__device__ __forceinline__ void cp_128x256b(uint32_t taddr, uint32_t lo, uint32_t hi) {
+  asm volatile("{\n.reg .b64 d;\nmov.b64 d, {%1, %2};\ntcgen05.cp.cta_group::1.128x256b [%0], d;\n}\n" ::"r"(taddr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\n.reg .b64 db;\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n}\n"
+               ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.b32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__global__ void __launch_bounds__(192, 1) probe_ts(const int8_t* Aimg, const int8_t* Bimg, int N, int reps, int32_t* D, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S * 4096;
+  for (int i = tid; i < S * 4096 / 16; i += blockDim.x) ((int4*)sA)[i] = ((const int4*)Aimg)[i];
+  for (int i = tid; i < S * N * 32 / 16; i += blockDim.x) ((int4*)sB)[i] = ((const int4*)Bimg)[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  const uint32_t hiA = desc_hi(128), hiB = desc_hi(128);
+  const uint32_t a0 = desc_lo(smem_u32(sA), M * 16), b0 = desc_lo(smem_u32(sB), N * 16);
+  const uint32_t bstep = (uint32_t)(N * 32) >> 4;
+  const uint32_t ta = tmem + (uint32_t)(S * N);        // A planes: 8 columns each, two buffers of S planes
+  if (warp == 0) {
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one()) {
+        const uint32_t tab = ta + (uint32_t)((r & 1) * S * 8);
+#pragma unroll
+        for (int i = 0; i < S; ++i) cp_128x256b(tab + 8u * i, a0 + 256u * i, hiA);
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+#pragma unroll
+          for (int j = 0; j < S - i; ++j)
+            mma_i8_ts(tmem + (uint32_t)((i + j) * N), tab + 8u * i, b0 + bstep * j, hiB, idesc, (r | i) ? 1u : 0u);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) commit(&bar[0]);
+    __syncwarp();
+    mbar_wait(&bar[0], 0);
+    if (lane == 0) cycles[blockIdx.x * 4] = clock64() - t0;
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp < 4 && D && blockIdx.x == 0) {
+    for (int c0 = 0; c0 < S * N; c0 += 32) {
+      uint32_t v[32];
+      ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      for (int j = 0; j < 32; ++j) D[(size_t)(warp * 32 + lane) * (S * N) + c0 + j] = (int32_t)v[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 static void make_image(const std::vector<int8_t>& T, int R, std::vector<int8_t>& img) {   // T[slice][row][32] -> image
   img.assign((size_t)S * R * 32, 0);
   for (int s = 0; s < S; ++s)
@@ -157,8 +231,50 @@ int main() {
     }
     CK(cudaFree(dA)); CK(cudaFree(dB));
   }
+  // ---- TS variant: correctness (N = 64, one k-block) and rate ----
+  {
+    const int N = 64;
+    std::vector<int8_t> A((size_t)S * M * 32), B((size_t)S * N * 32), Ai, Bi;
+    for (auto& v : A) v = (int8_t)(rand() % 256 - 128);
+    for (auto& v : B) v = (int8_t)(rand() % 256 - 128);
+    make_image(A, M, Ai);
+    make_image(B, N, Bi);
+    int8_t *dA, *dB;
+    CK(cudaMalloc(&dA, Ai.size())); CK(cudaMalloc(&dB, Bi.size()));
+    CK(cudaMemcpy(dA, Ai.data(), Ai.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, Bi.data(), Bi.size(), cudaMemcpyHostToDevice));
+    const int smem = S * 4096 + S * N * 32 + 1024;
+    CK(cudaFuncSetAttribute(probe_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaMemset(dD, 0, 128 * 512 * 4));
+    probe_ts<<<1, 192, smem>>>(dA, dB, N, 1, dD, dC);
+    CK(cudaDeviceSynchronize());
+    std::vector<int32_t> D((size_t)128 * S * N);
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    long bad = 0;
+    for (int g = 0; g < S; ++g)
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+          int32_t ref = 0;
+          for (int i = 0; i <= g; ++i)
+            for (int k = 0; k < 32; ++k) ref += (int32_t)A[((size_t)i * M + m) * 32 + k] * (int32_t)B[((size_t)(g - i) * N + n) * 32 + k];
+          if (ref != D[(size_t)m * (S * N) + g * N + n]) ++bad;
+        }
+    printf("TS (A planes via tcgen05.cp 128x256b into TMEM) N = %d: %ld of %d mismatches\n", N, bad, S * M * N);
+    for (int grid : {1, 148}) {
+      const int reps = 2000;
+      probe_ts<<<grid, 192, smem>>>(dA, dB, N, reps, nullptr, dC);
+      CK(cudaDeviceSynchronize());
+      long long c[148 * 4];
+      CK(cudaMemcpy(c, dC, sizeof(long long) * grid * 4, cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (int b = 0; b < grid; ++b) mx = c[b * 4] > mx ? c[b * 4] : mx;
+      printf("TS N = %d grid %3d: %.1f cycles per MMA incl. 6 copies per 21 MMAs (math floor %d), %.0f MAC/clk/SM\n", N, grid, (double)mx / (21.0 * reps), N / 2,
+             21.0 * reps * 128 * N * 32 / mx);
+    }
+    CK(cudaFree(dA)); CK(cudaFree(dB));
+  }
   // ---- issue-rate timing: all SMs, operands static in shared memory ----
-  for (int N : {32, 48, 64, 80, 128, 256}) {
+  for (int N : {64, 80}) {
     const int G = 512 / N < S ? 512 / N : S;
     std::vector<int8_t> Ai((size_t)S * 4096, 1), Bi((size_t)S * N * 32, 1);
     int8_t *dA, *dB;
