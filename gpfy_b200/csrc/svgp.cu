@@ -1414,7 +1414,11 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
     za.Mp = Mp; za.M = s.M; za.dim = s.dim; za.npts = npts;
     za.Z = ws + p.o_Z; za.ldz = p.nc; za.XH = ws + p.o_XH; za.R = ws + p.o_R; za.mz = ws + p.o_mz; za.P = s.P;
     za.deg = deg; za.rc = rc;
-    if (fuse_lik) { za.Yg = Y + c0; za.s2g = sigma2; za.wq = ws + p.o_wq; za.wp = ws + p.o_wp; za.cq = ws + p.o_cq; }
+    // Gaussian weights need only fmu: the forward kernel writes them (likelihoods.py:210-218).  The fused path uses them throughout;
+    // on the zonal_bwd4 path with the int8 contraction they let the weighted-Gram kernel (and its digit slicing) run before the
+    // contraction - lik_point_kernel recomputes the same weights afterwards together with the value terms.
+    const bool early_w = fuse_lik || (p.i8 && bwd4 && s.P == 1 && desc->likelihood == GPFY_LIK_GAUSSIAN);
+    if (early_w) { za.Yg = Y + c0; za.s2g = sigma2; za.wq = ws + p.o_wq; za.wp = ws + p.o_wp; za.cq = ws + p.o_cq; }
     za.ZPb = bwd4 ? ws + p.o_dT : nullptr;   // the derivative panel takes the place of the legacy path's dT buffer
     if (p.f32) { za.Zh = reinterpret_cast<float*>(ws + p.o_Zf); za.Zl = za.Zh + (int64_t)Mp * p.nc; }
     if (p.f32s) za.Z = nullptr;   // both contractions read the float planes: the fp64 panel is not written
@@ -1445,7 +1449,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       }
       return GPFY_OK;
     };
-    const bool syrk_first = p.i8 && fuse_lik && !debug_option(DBG_NO_SYRK_SLICE);
+    const bool syrk_first = p.i8 && early_w && !debug_option(DBG_NO_SYRK_SLICE);
     if (syrk_first) GPFY_TRY(launch_syrk(true));
 
     if (p.f32) {  // C = W2 Z on tcgen05 in 3 x TF32 (P = 1); psi goes out as one slab
