@@ -714,20 +714,22 @@ __device__ __forceinline__ void syrk_slice_step(const double* zs, const double* 
 template <int RA, int RB>
 __device__ __forceinline__ void syrk_diag_step(const double* zs, const double* wqs, double (&acc)[12][2],
                                                double (&accx)[2][2], int g, int t4) {
-  // one k4 step: rows of tile row RA (and RB < RA) against the weighted columns 0..RA
+  // one k4 step: rows of tile row RA (and RB < RA) against the columns 0..RA.  The weight goes onto the A fragments (one or two
+  // multiplies per step) instead of every B fragment (RA + 1 of them: as many FP64-pipe multiplies as tensor-core tiles)
 #pragma unroll
   for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
     const double w = wqs[k4 * 4 + t4];
     const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
     const double afa = zs[(RA * 8 + g) * SYRK_ZS + k4 * 4 + t4];
-    double afb = 0.0;
-    if constexpr (RB >= 0) afb = zs[(RB * 8 + g) * SYRK_ZS + k4 * 4 + t4];
+    const double afaw = afa * w;
+    double afb = 0.0, afbw = 0.0;
+    if constexpr (RB >= 0) { afb = zs[(RB * 8 + g) * SYRK_ZS + k4 * 4 + t4]; afbw = afb * w; }
 #pragma unroll
     for (int c = 0; c <= RA; ++c) {
-      const double bf = zs[(c * 8 + g) * SYRK_ZS + k4 * 4 + t4] * w;
-      dmma884(acc[c][0], acc[c][1], afa, bf);
+      const double bf = zs[(c * 8 + g) * SYRK_ZS + k4 * 4 + t4];
+      dmma884(acc[c][0], acc[c][1], afaw, bf);
       if constexpr (RB >= 0) {
-        if (c <= RB) dmma884(acc[RA + 1 + c][0], acc[RA + 1 + c][1], afb, bf);
+        if (c <= RB) dmma884(acc[RA + 1 + c][0], acc[RA + 1 + c][1], afbw, bf);
       }
     }
     dmma884(accx[0][0], accx[0][1], afa, bx);
@@ -830,9 +832,9 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
         double af[3], bf[6];
         const double w = wqs[k4 * 4 + t4];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) af[r] = zi[r * 32 * SYRK_ZS + k4 * 4];
+        for (int r = 0; r < 3; ++r) af[r] = zi[r * 32 * SYRK_ZS + k4 * 4] * w;   // the weight on the three A fragments, not the six B
 #pragma unroll
-        for (int c = 0; c < 6; ++c) bf[c] = zj[c * 8 * SYRK_ZS + k4 * 4] * w;
+        for (int c = 0; c < 6; ++c) bf[c] = zj[c * 8 * SYRK_ZS + k4 * 4];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
           if (ract[r]) {
