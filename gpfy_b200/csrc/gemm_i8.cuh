@@ -280,8 +280,12 @@ __device__ __forceinline__ double gi8_epilogue16(const GemmI8Args& a, uint32_t t
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const long long pair = (long long)(int)vh[j] * 256 + (long long)(int)vl[j];
+#if defined(GI8_KO) && (GI8_KO & 16)   // development knock-out: no FP64-pipe instruction in the epilogue (wrong values)
+      c[j] = __longlong_as_double((pr == GI8_S / 2 - 1) ? pair : (__double_as_longlong(c[j]) >> 16) + pair);
+#else
       const double pd = __longlong_as_double(pair + 0x4338000000000000ll) - 6755399441055744.0;   // exact: |pair| < 2^51
       c[j] = (pr == GI8_S / 2 - 1) ? pd : fma(c[j], 1.0 / 65536.0, pd);
+#endif
     }
   }
   const int Mp = a.Mp;
@@ -293,7 +297,11 @@ __device__ __forceinline__ double gi8_epilogue16(const GemmI8Args& a, uint32_t t
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int row = row0 + col0 + j;
+#if defined(GI8_KO) && (GI8_KO & 16)
+    const double cv = __longlong_as_double(__double_as_longlong(c[j]) + __double_as_longlong(rs_s[col0 + j]));
+#else
     const double cv = gi8_mul(c[j], rs_s[col0 + j], nz);
+#endif
     if (store) ctile[row * 32 + (lane ^ ((row & 3) << 2))] = cv;
     if (a.psi) psi = fma(n < a.npts ? a.Z[(int64_t)row * a.ldz + n] : 0.0, cv, psi);
   }
@@ -392,16 +400,20 @@ __global__ void __launch_bounds__(GI8_THREADS, 1) gemm_i8_kernel(const __grid_co
           const uint32_t a_lo = g32_desc_lo(g32_smem_u32(sA + st * GI8_A_STAGE), 2048);
           const uint32_t b_lo = b_lo0 + (uint32_t)(kb * 2 * NB);   // k-block kb = 16-feature chunks 2 kb, 2 kb + 1 (NB * 16 bytes each)
           if (kb == 0 && it > 0) {
-            // first k-block of a tile: digit group by digit group in the order the epilogue drains the previous tile's
-            // accumulators (consecutive MMAs on ONE accumulator run at ~80 cycles each instead of 52, hidden behind the drain)
+            // first k-block of a tile: the accumulators come back from the epilogue in pairs (5, 4), (3, 2), (1, 0) - lowest weights
+            // first; the products of a pair are issued alternately, because consecutive MMAs on ONE accumulator run at ~80 cycles
+            // each instead of 52 (tools/i8_probe.cu, tools/i8_gemm_bench.cu)
 #pragma unroll
-            for (int g = GI8_S - 1; g >= 0; --g) {
-              { GI8_T0; mbar_wait(&d_empty[g], (unsigned)((it - 1) & 1)); GI8_T1(t_d); }
+            for (int pr = GI8_S / 2 - 1; pr >= 0; --pr) {
+              const int g1 = 2 * pr + 1, g0 = 2 * pr;
+              { GI8_T0; mbar_wait(&d_empty[g1], (unsigned)((it - 1) & 1)); mbar_wait(&d_empty[g0], (unsigned)((it - 1) & 1)); GI8_T1(t_d); }
               asm volatile("tcgen05.fence::after_thread_sync;");
               if (gi8_elect_one()) {
 #pragma unroll
-                for (int i = 0; i <= g; ++i)                    // digits i + 1 of Z and g - i + 1 of W2
-                  gi8_mma(tmem + (uint32_t)(g * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)(g - i), hi, idesc, i ? 1u : 0u);
+                for (int i = 0; i <= g1; ++i) {                 // digits i + 1 of Z and g - i + 1 of W2
+                  gi8_mma(tmem + (uint32_t)(g1 * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)(g1 - i), hi, idesc, i ? 1u : 0u);
+                  if (i <= g0) gi8_mma(tmem + (uint32_t)(g0 * NB), a_lo + 256u * i, hi, b_lo + bstep * (uint32_t)(g0 - i), hi, idesc, i ? 1u : 0u);
+                }
               }
               __syncwarp();
             }

@@ -712,18 +712,15 @@ __device__ __forceinline__ void syrk_slice_step(const double* zs, const double* 
 // An off-diagonal block keeps the 4 x 2 grid of 24 x 48 warp tiles (18 tiles per warp).  Diagonal CTAs come first
 // in the grid so that the two CTAs sharing an SM are one of each kind.
 template <int RA, int RB>
-__device__ __forceinline__ void syrk_diag_step(const double* zs, const double* wqs, double (&acc)[12][2],
-                                               double (&accx)[2][2], int g, int t4) {
+__device__ __forceinline__ void syrk_diag_step(const double* zs, const double* wqs, double (&acc)[12][2], int g, int t4) {
   // one k4 step: rows of tile row RA (and RB < RA) against the columns 0..RA.  The weight goes onto the A fragments (one or two
   // multiplies per step) instead of every B fragment (RA + 1 of them: as many FP64-pipe multiplies as tensor-core tiles)
 #pragma unroll
   for (int k4 = 0; k4 < SYRK_BK / 4; ++k4) {
     const double w = wqs[k4 * 4 + t4];
-    const double bx = (g == 0) ? wqs[SYRK_BK + k4 * 4 + t4] : 0.0;
-    const double afa = zs[(RA * 8 + g) * SYRK_ZS + k4 * 4 + t4];
-    const double afaw = afa * w;
-    double afb = 0.0, afbw = 0.0;
-    if constexpr (RB >= 0) { afb = zs[(RB * 8 + g) * SYRK_ZS + k4 * 4 + t4]; afbw = afb * w; }
+    const double afaw = zs[(RA * 8 + g) * SYRK_ZS + k4 * 4 + t4] * w;
+    double afbw = 0.0;
+    if constexpr (RB >= 0) afbw = zs[(RB * 8 + g) * SYRK_ZS + k4 * 4 + t4] * w;
 #pragma unroll
     for (int c = 0; c <= RA; ++c) {
       const double bf = zs[(c * 8 + g) * SYRK_ZS + k4 * 4 + t4];
@@ -732,8 +729,6 @@ __device__ __forceinline__ void syrk_diag_step(const double* zs, const double* w
         if (c <= RB) dmma884(acc[RA + 1 + c][0], acc[RA + 1 + c][1], afbw, bf);
       }
     }
-    dmma884(accx[0][0], accx[0][1], afa, bx);
-    if constexpr (RB >= 0) dmma884(accx[1][0], accx[1][1], afb, bx);
   }
 }
 
@@ -863,10 +858,15 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
 
   // ---- diagonal block ----
   double acc[12][2];
-  double accx[2][2];
 #pragma unroll
   for (int c = 0; c < 12; ++c) acc[c][0] = acc[c][1] = 0.0;
-  accx[0][0] = accx[0][1] = accx[1][0] = accx[1][1] = 0.0;
+  // bz = Z wp on the FP64 vector pipe: thread = one point of the k-step x 6 of the block's 96 rows (16 x 16 threads), summed over the
+  // 16 point lanes once at the end.  As an extra tensor-core column (one m8n8k4 tile per tile row with seven of its eight columns
+  // unused) it cost 12 of a diagonal CTA's 90 tiles per step; here it is 6 fused multiply-adds per thread.
+  double bzacc[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) bzacc[i] = 0.0;
+  const int bz_pt = tid & 15, bz_r0 = (tid >> 4) * 6;
   for (int kb = 0; kb < kt; ++kb) {
     const int st = kb % SYRK_STAGES;
     mbar_wait(&bar_full[st], (kb / SYRK_STAGES) & 1);
@@ -881,15 +881,20 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
         syrk_slice_step(zs, ksc_s, c, pt,
                         a.zs_out + ((n >> 7) * (int64_t)(a.Mp / 32) + (krow >> 1)) * GI8_A_STAGE + (krow & 1) * 2048 + (int)(n & 127) * 16);
     }
+    {
+      const double wpv = wqs[SYRK_BK + bz_pt];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) bzacc[i] = fma(zs[(bz_r0 + i) * SYRK_ZS + bz_pt], wpv, bzacc[i]);
+    }
     switch (warp) {
-      case 0: syrk_diag_step<11, -1>(zs, wqs, acc, accx, g, t4); break;
-      case 1: syrk_diag_step<10, -1>(zs, wqs, acc, accx, g, t4); break;
-      case 2: syrk_diag_step<9, -1>(zs, wqs, acc, accx, g, t4); break;
-      case 3: syrk_diag_step<8, -1>(zs, wqs, acc, accx, g, t4); break;
-      case 4: syrk_diag_step<7, 0>(zs, wqs, acc, accx, g, t4); break;
-      case 5: syrk_diag_step<6, 1>(zs, wqs, acc, accx, g, t4); break;
-      case 6: syrk_diag_step<5, 2>(zs, wqs, acc, accx, g, t4); break;
-      default: syrk_diag_step<4, 3>(zs, wqs, acc, accx, g, t4); break;
+      case 0: syrk_diag_step<11, -1>(zs, wqs, acc, g, t4); break;
+      case 1: syrk_diag_step<10, -1>(zs, wqs, acc, g, t4); break;
+      case 2: syrk_diag_step<9, -1>(zs, wqs, acc, g, t4); break;
+      case 3: syrk_diag_step<8, -1>(zs, wqs, acc, g, t4); break;
+      case 4: syrk_diag_step<7, 0>(zs, wqs, acc, g, t4); break;
+      case 5: syrk_diag_step<6, 1>(zs, wqs, acc, g, t4); break;
+      case 6: syrk_diag_step<5, 2>(zs, wqs, acc, g, t4); break;
+      default: syrk_diag_step<4, 3>(zs, wqs, acc, g, t4); break;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_empty[st]);
@@ -907,12 +912,16 @@ __global__ void __launch_bounds__(SYRK_THREADS, 2) syrk_dmma_kernel(SyrkArgs a) 
     if (a.accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
     *dst = v;
   }
-  if (t4 == 0) {
-    double* d0 = bzp + ra * 8 + g;
-    *d0 = a.accumulate ? *d0 + accx[0][0] : accx[0][0];
-    if (rb >= 0) {
-      double* d1 = bzp + rb * 8 + g;
-      *d1 = a.accumulate ? *d1 + accx[1][0] : accx[1][0];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {   // over the 16 point lanes (a half warp), fixed order
+    double v = bzacc[i];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (bz_pt == 0) {
+      double* d0 = bzp + bz_r0 + i;
+      *d0 = a.accumulate ? *d0 + v : v;
     }
   }
 }
