@@ -1456,7 +1456,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       GPFY_TIMED(TK_GEMM, st);
       GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi));
     } else if (p.i8) {  // C = W2 Z as exact int8 digit products on tcgen05 (P = 1); psi in one slab per out-block
-      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, ws + p.o_C, fuse_lik ? nullptr : ws + p.o_psi, syrk_first));
+      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, ws + p.o_C, nullptr, syrk_first));   // psi, where needed, is formed by lik_point_kernel
     } else
     for (int q = 0; q < s.P; ++q) {  // C_q = W2_q Z
       GPFY_TIMED(TK_GEMM, st);
@@ -1478,6 +1478,7 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
       lp.P = s.P; lp.order = desc->kernel_order; lp.lik_kind = desc->likelihood; lp.npts = npts;
       lp.wq = ws + p.o_wq; lp.wp = ws + p.o_wp; lp.cq = ws + p.o_cq; lp.dr = ws + p.o_dr;
       lp.partials = ws + p.o_partials; lp.npart = p.npart; lp.accumulate = 1;
+      if (p.i8) { lp.Zp = ws + p.o_Z; lp.Cb = ws + p.o_C; lp.Mp = Mp; lp.M = s.M; }
       GPFY_TIMED(TK_LIK, st);
       GPFY_K(lik_point_kernel, (unsigned)((npts_e + 255) / 256), 256, 0, st, lp);
     }

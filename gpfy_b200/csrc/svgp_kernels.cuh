@@ -312,6 +312,12 @@ struct LikPointArgs {
   double* partials;     // [npts / 32][npart]: one row per 32 points (PART_E, PART_DV, PART_DS2 written here)
   int npart;
   int accumulate;
+  // psi_n = z_n . C_n formed HERE from the two panels instead of by the contraction's epilogue (P = 1; used with the int8
+  // contraction, whose epilogue warps pay ~40 cycles per FP64 instruction while the tensor pipe is saturated): Zp [Mp][ldz] and the
+  // blocked, swizzled C (GemmArgs::c_blocked).  Null = read psi_part.
+  const double* Zp = nullptr;
+  const double* Cb = nullptr;
+  int Mp = 0, M = 0;
 };
 
 // One point per thread: psi, fmu, fvar, the likelihood terms and everything the backward pass needs
@@ -339,6 +345,19 @@ __global__ void __launch_bounds__(256) lik_point_kernel(LikPointArgs a) {
     double dr = 0.0;
     for (int p = 0; p < a.P; ++p) {
       double psi = 0.0;
+      if (a.Cb) {   // both reads are coalesced over the warp's 32 points: a Z row and the matching 256-byte row of the C tile
+        const double* zc = a.Zp + n;
+        const double* cc = a.Cb + (n >> 5) * (int64_t)a.Mp * 32;
+        const int ln = (int)(n & 31);
+        double ps[4] = {0.0, 0.0, 0.0, 0.0};
+        int row = 0;
+        for (; row + 4 <= a.M; row += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ps[u] = fma(zc[(int64_t)(row + u) * a.ldz], cc[(row + u) * 32 + (ln ^ (u << 2))], ps[u]);
+        }
+        for (; row < a.M; ++row) ps[0] = fma(zc[(int64_t)row * a.ldz], cc[row * 32 + (ln ^ ((row & 3) << 2))], ps[0]);
+        psi = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      } else
       for (int k = 0; k < a.npsi; ++k) psi += a.psi_part[((int64_t)p * a.npsi + k) * a.ldz + n];
       const double mzp = a.mz[(int64_t)p * a.ldz + n];
       const double fmu = r * mzp;
