@@ -89,6 +89,8 @@ _SIGNATURES = {
     "gpfy_svgp_elbo_finish": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64] + [_P] * 6 + [_P, ctypes.c_size_t]),
     "gpfy_inducing_basis_fwd": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, ctypes.c_int, _P, _P]),
     "gpfy_inducing_basis_vjp": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, ctypes.c_int, _P, _P, _P]),
+    "gpfy_inducing_basis_fwd_ws": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, ctypes.c_int, _P, _P, _P, ctypes.c_size_t]),
+    "gpfy_inducing_basis_vjp_ws": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), _P, _P, ctypes.c_int, _P, _P, _P, _P, ctypes.c_size_t]),
     "gpfy_step_constrain": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyStepLayout), _P, _P, _P, _P]),
     "gpfy_step_grad": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.POINTER(GpfyStepLayout), _P, _P, _P, _P, _P, ctypes.c_double, _P, _P]),
     "gpfy_step_adam": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P, _P, _P] + [ctypes.c_double] * 4 + [ctypes.c_int64]),

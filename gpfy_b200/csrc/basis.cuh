@@ -1,7 +1,8 @@
 // N-independent inducing-basis algebra on the device: under phase truncation the reference
 // re-normalises the fundamental points, rebuilds the per-degree Gram matrices and their Cholesky factors every step
 // (spherical_harmonics.py:194-239, 265-288) and differentiates through all of it.  One CTA per degree; everything
-// for a degree lives in shared memory (m_l <= 64).
+// for a degree lives in shared memory (m_l <= 64); for 64 < m_l <= 256 the four m x m matrices live in caller-provided global scratch
+// (L2-resident; O(m^3) once per step either way).
 //   fwd : Vhat_l = V_l / |V_l| (rows; only in learned mode),  B_l = c_l C_l^alpha(Vhat_l Vhat_l^T) + 1e-16 I,
 //         L_l = chol(B_l)                                      c_l = alpha / (alpha + l)
 //   vjp : (dVhat_l, dL_l) -> dV_l :  dB = sym(L^-T Phi(L^T dL) L^-1)   (Phi: lower triangle, halved diagonal; the
@@ -12,7 +13,7 @@
 
 namespace gpfy {
 
-constexpr int BASIS_MAX_M = 64;
+constexpr int BASIS_MAX_M = 64, BASIS_MAX_M_WS = 256;
 
 struct BasisArgs {
   const double* V;      // [M][dim] raw parameters
@@ -25,9 +26,10 @@ struct BasisArgs {
   double alpha;
   DegreeTable deg;
   RecCoef rc;
+  double* scratch = nullptr;   // [4 * sum m_l^2] or null (all matrices in shared memory)
 };
 
-static inline int basis_smem_bytes(int m, int dim) { return (4 * m * m + 2 * m * dim + 2 * m) * 8; }
+static inline int basis_smem_bytes(int m, int dim, bool scratch = false) { return ((scratch ? 0 : 4 * m * m) + 2 * m * dim + 2 * m) * 8; }
 
 __global__ void __launch_bounds__(256) inducing_basis_kernel(BasisArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -36,11 +38,11 @@ __global__ void __launch_bounds__(256) inducing_basis_kernel(BasisArgs a) {
   int64_t loff = 0;
   for (int k = 0; k < l; ++k) { off += a.deg.m[k]; loff += (int64_t)a.deg.m[k] * a.deg.m[k]; }
   const int m = a.deg.m[l], dim = a.dim;
-  double* G = sm;                 // [m][m] Gram Vhat Vhat^T
+  double* G = a.scratch ? a.scratch + 4 * loff : sm;   // [m][m] Gram Vhat Vhat^T
   double* L = G + m * m;          // [m][m]
   double* T1 = L + m * m;         // [m][m] scratch
   double* T2 = T1 + m * m;        // [m][m] scratch
-  double* vh = T2 + m * m;        // [m][dim]
+  double* vh = a.scratch ? sm : T2 + m * m;        // [m][dim]
   double* dvh = vh + m * dim;     // [m][dim]
   double* nrm = dvh + m * dim;    // [m]
   double* dots = nrm + m;         // [m]

@@ -1599,12 +1599,19 @@ int gpfy_svgp_elbo_valgrad(void* stream, const GpfyDesc* desc, int64_t n, const 
   return gpfy_svgp_elbo_finish(stream, desc, n, w, b, variance, eig, mu, packed, workspace, workspace_bytes);
 }
 
-static int basis_launch(void* stream, const GpfyDesc* desc, BasisArgs& ba) {
+static int basis_launch(void* stream, const GpfyDesc* desc, BasisArgs& ba, void* workspace = nullptr, size_t workspace_bytes = 0) {
   Shape s;
   GPFY_TRY(make_shape(desc, &s));
-  if (s.mmax > BASIS_MAX_M) { set_error("inducing-basis kernels are built for m_l <= %d (got %d): keep this degree's algebra on the host", BASIS_MAX_M, s.mmax); return GPFY_EUNSUPPORTED; }
+  ba.scratch = nullptr;
+  if (s.mmax > BASIS_MAX_M) {
+    if (!workspace) { set_error("inducing-basis kernels keep m_l <= %d in shared memory (got %d): use the _ws entry points", BASIS_MAX_M, s.mmax); return GPFY_EUNSUPPORTED; }
+    if (s.mmax > BASIS_MAX_M_WS) { set_error("inducing-basis kernels are built for m_l <= %d (got %d)", BASIS_MAX_M_WS, s.mmax); return GPFY_EUNSUPPORTED; }
+    const size_t need = (size_t)4 * s.lsize * 8;
+    if (((uintptr_t)workspace & 15) != 0 || workspace_bytes < need) { set_error("inducing basis with m_l > %d needs %zu bytes of 16-byte aligned workspace", BASIS_MAX_M, need); return GPFY_EWORKSPACE; }
+    ba.scratch = (double*)workspace;
+  }
   ba.dim = s.dim; ba.alpha = desc->alpha; ba.deg = degree_table(desc); ba.rc = make_rec_coef(desc->alpha);
-  const int smem = basis_smem_bytes(s.mmax, s.dim);
+  const int smem = basis_smem_bytes(s.mmax, s.dim, ba.scratch != nullptr);
   GPFY_TRY(set_smem(inducing_basis_kernel, smem));
   GPFY_K(inducing_basis_kernel, s.F, 256, smem, (cudaStream_t)stream, ba);
   return GPFY_OK;
@@ -1623,6 +1630,22 @@ int gpfy_inducing_basis_vjp(void* stream, const GpfyDesc* desc, const double* V,
   ba.V = V; ba.vhat = nullptr; ba.lcat = const_cast<double*>(lcat); ba.dvhat = dvhat; ba.dlcat = dlcat; ba.dV = dV;
   ba.normalise = normalise; ba.vjp = 1;
   return basis_launch(stream, desc, ba);
+}
+
+int gpfy_inducing_basis_fwd_ws(void* stream, const GpfyDesc* desc, const double* V, int normalise, double* vhat, double* lcat,
+                               void* workspace, size_t workspace_bytes) {
+  BasisArgs ba;
+  ba.V = V; ba.vhat = vhat; ba.lcat = lcat; ba.dvhat = nullptr; ba.dlcat = nullptr; ba.dV = nullptr;
+  ba.normalise = normalise; ba.vjp = 0;
+  return basis_launch(stream, desc, ba, workspace, workspace_bytes);
+}
+
+int gpfy_inducing_basis_vjp_ws(void* stream, const GpfyDesc* desc, const double* V, const double* lcat, int normalise,
+                               const double* dvhat, const double* dlcat, double* dV, void* workspace, size_t workspace_bytes) {
+  BasisArgs ba;
+  ba.V = V; ba.vhat = nullptr; ba.lcat = const_cast<double*>(lcat); ba.dvhat = dvhat; ba.dlcat = dlcat; ba.dV = dV;
+  ba.normalise = normalise; ba.vjp = 1;
+  return basis_launch(stream, desc, ba, workspace, workspace_bytes);
 }
 
 int gpfy_prior_kl_valgrad(void* stream, const GpfyDesc* desc, const double* mu, const double* sigma, double* out) {

@@ -6,7 +6,7 @@ equivalent around the CUDA hot path: the unconstrained parameters live in ONE fl
 fixed sequence of stream-ordered C-ABI calls (constrain -> inducing basis -> ELBO + gradient -> all-reduce -> KL ->
 basis VJP -> gradient assembly -> Adam) without a single host synchronisation; `fit(..., use_graph=True)` /
 `fit_minibatch(..., use_graph=True)` capture that sequence once in a CUDA graph and replay it.  Supports the TriL variational distribution with Gaussian or Bernoulli likelihood and every kernel of
-gpfy_b200.spherical; m_l <= 64 in learned-basis mode.
+gpfy_b200.spherical; m_l <= 256 in learned-basis mode.
 """
 import ctypes
 
@@ -34,8 +34,8 @@ class DeviceTrainer:
         kname = self.kernel.name
         kp = con.params[kname]
         self.learned = self.sh._learned(con)
-        if self.learned and max(hp.m) > 64:
-            raise _lib.GpfyError("DeviceTrainer needs m_l <= 64 in learned-basis mode")
+        if self.learned and max(hp.m) > hp.BASIS_MAX_M:
+            raise _lib.GpfyError(f"DeviceTrainer needs m_l <= {hp.BASIS_MAX_M} in learned-basis mode")
         self.vnames = sorted(con.params["variational"]["inducing_features"])
         self._check_bijectors(con, kname, lik, q, bool(hp.projection_dim))
         M, P, F, dim = hp.M, hp.P, hp.F, hp.dim
@@ -165,7 +165,8 @@ class DeviceTrainer:
             with torch.cuda.stream(kl_stream):
                 _lib.check(lib.gpfy_prior_kl_valgrad(_stream(hp.device), d, _ptr(self.v_mu), _ptr(self.v_sig), _ptr(self.kl)))
         if self.learned:
-            _lib.check(lib.gpfy_inducing_basis_fwd(st, d, _ptr(self.v_V), 1, _ptr(self.vhat), _ptr(self.lcat)))
+            bws = hp._basis_workspace()
+            _lib.check(lib.gpfy_inducing_basis_fwd_ws(st, d, _ptr(self.v_V), 1, _ptr(self.vhat), _ptr(self.lcat), _ptr(bws), bws.numel() * 8))
             vhat = self.vhat
         else:
             vhat = self.v_V
@@ -181,9 +182,10 @@ class DeviceTrainer:
             _lib.check(lib.gpfy_prior_kl_valgrad(st, d, _ptr(self.v_mu), _ptr(self.v_sig), _ptr(self.kl)))
         E = hp.layout
         if self.learned:
-            _lib.check(lib.gpfy_inducing_basis_vjp(st, d, _ptr(self.v_V), _ptr(self.lcat), 1,
-                                                   ctypes.c_void_p(self.packed.data_ptr() + 8 * E.d_vhat),
-                                                   ctypes.c_void_p(self.packed.data_ptr() + 8 * E.d_lcat), _ptr(self.dV)))
+            bws = hp._basis_workspace()
+            _lib.check(lib.gpfy_inducing_basis_vjp_ws(st, d, _ptr(self.v_V), _ptr(self.lcat), 1,
+                                                      ctypes.c_void_p(self.packed.data_ptr() + 8 * E.d_vhat),
+                                                      ctypes.c_void_p(self.packed.data_ptr() + 8 * E.d_lcat), _ptr(self.dV), _ptr(bws), bws.numel() * 8))
             dV = self.dV
         else:
             dV = self.packed[E.d_vhat:E.d_vhat + hp.M * hp.dim]

@@ -35,7 +35,53 @@ class Likelihood:
         return self.variational_expectations(param, F, zeros)(Y)
 
     def conditional_distribution(self, param: Param, F):
-        raise NotImplementedError("TFP distribution objects are not part of the accelerated path; use log_prob")
+        raise NotImplementedError
+
+
+@dataclasses.dataclass(frozen=True)
+class NormalDistribution:
+    """Host-side stand-in for `tfp.distributions.Normal(loc, scale)` (TFP is not installable here): the members GPfY's
+    callers use on the object `conditional_distribution` returns (likelihoods.py:172-186)."""
+    loc: np.ndarray
+    scale: np.ndarray
+
+    def mean(self):
+        return np.asarray(self.loc, dtype=np.float64)
+
+    def stddev(self):
+        return np.broadcast_to(np.asarray(self.scale, dtype=np.float64), np.shape(self.loc)).copy()
+
+    def variance(self):
+        return self.stddev() ** 2
+
+    def log_prob(self, y):
+        z = (np.asarray(y, dtype=np.float64) - self.mean()) / self.scale
+        return -0.5 * z * z - np.log(self.scale) - 0.5 * np.log(2.0 * np.pi)
+
+    def sample(self, sample_shape=(), seed=0):
+        rng = np.random.default_rng(seed)
+        return self.mean() + self.scale * rng.standard_normal(tuple(np.atleast_1d(sample_shape).astype(int)) + np.shape(self.loc))
+
+
+@dataclasses.dataclass(frozen=True)
+class BernoulliDistribution:
+    """Host-side stand-in for `tfp.distributions.Bernoulli(probs=...)` (likelihoods.py:236-252)."""
+    probs: np.ndarray
+
+    def mean(self):
+        return np.asarray(self.probs, dtype=np.float64)
+
+    def variance(self):
+        p = self.mean()
+        return p * (1.0 - p)
+
+    def log_prob(self, y):
+        y, p = np.asarray(y, dtype=np.float64), self.mean()
+        return y * np.log(p) + (1.0 - y) * np.log1p(-p)
+
+    def sample(self, sample_shape=(), seed=0):
+        rng = np.random.default_rng(seed)
+        return (rng.random(tuple(np.atleast_1d(sample_shape).astype(int)) + np.shape(self.probs)) < self.mean()).astype(np.float64)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -58,11 +104,21 @@ class Gaussian(Likelihood):
     def _sigma2(self, param: Param):
         return param.params["likelihood"][self.name]["variance"]
 
+    def conditional_distribution(self, param: Param, F):
+        """p(Y | F) = N(F, sigma^2) (likelihoods.py:172-186), as a host-side `NormalDistribution`."""
+        F = F.detach().cpu().numpy() if hasattr(F, "detach") else np.asarray(F, dtype=np.float64)
+        return NormalDistribution(loc=F.astype(np.float64), scale=np.sqrt(np.asarray(self._sigma2(param), dtype=np.float64)))
+
 
 @dataclasses.dataclass(frozen=True)
 class Bernoulli(Likelihood):
     name: str = "Bernoulli"
     _kind = "bernoulli"
+
+    def conditional_distribution(self, param: Param, F):
+        """p(Y | F) = Bernoulli(inv_probit(F)) (likelihoods.py:236-252), as a host-side `BernoulliDistribution`."""
+        F = F.detach().cpu().numpy() if hasattr(F, "detach") else np.asarray(F, dtype=np.float64)
+        return BernoulliDistribution(probs=inv_probit(F))
 
 
 def inv_probit(x):

@@ -355,16 +355,28 @@ class HotPath:
         V = self._dev(V)
         vhat = torch.empty((self.M, self.dim), dtype=torch.float64, device=self.device)
         lcat = torch.empty((self.lsize,), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.gpfy_inducing_basis_fwd(_stream(self.device), ctypes.byref(self.desc), _ptr(V), int(bool(normalise)),
-                                                    _ptr(vhat), _ptr(lcat)))
+        ws = self._basis_workspace()
+        _lib.check(self.lib.gpfy_inducing_basis_fwd_ws(_stream(self.device), ctypes.byref(self.desc), _ptr(V), int(bool(normalise)),
+                                                       _ptr(vhat), _ptr(lcat), _ptr(ws), ws.numel() * 8))
         return vhat, lcat
+
+    BASIS_MAX_M = 256   # gpfy_inducing_basis_*_ws: m_l <= 64 in shared memory, up to 256 with global scratch
+
+    def _basis_workspace(self):
+        """Scratch of the inducing-basis kernels for m_l > 64 (32 * sum m_l^2 bytes; one element otherwise), cached."""
+        ws = getattr(self, "_basis_ws", None)
+        if ws is None:
+            n = 4 * self.lsize if max(self.m) > 64 else 2
+            ws = self._basis_ws = torch.empty((n,), dtype=torch.float64, device=self.device)
+        return ws
 
     def inducing_basis_vjp(self, V, lcat, dvhat, dlcat, normalise=True):
         """dV [M, dim] from the cotangents of (vhat, lcat) — the reverse pass of `inducing_basis`."""
         V, lcat, dvhat, dlcat = self._dev(V), self._dev(lcat), self._dev(dvhat), self._dev(dlcat)
         dV = torch.empty((self.M, self.dim), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.gpfy_inducing_basis_vjp(_stream(self.device), ctypes.byref(self.desc), _ptr(V), _ptr(lcat),
-                                                    int(bool(normalise)), _ptr(dvhat), _ptr(dlcat), _ptr(dV)))
+        ws = self._basis_workspace()
+        _lib.check(self.lib.gpfy_inducing_basis_vjp_ws(_stream(self.device), ctypes.byref(self.desc), _ptr(V), _ptr(lcat),
+                                                       int(bool(normalise)), _ptr(dvhat), _ptr(dlcat), _ptr(dV), _ptr(ws), ws.numel() * 8))
         return dV
 
     def prior_kl_valgrad(self, mu, sigma):

@@ -119,11 +119,11 @@ class SphericalHarmonics:
     def _cat(self, param: Param):
         """(vhat [M, dim], lcat [sum m_l^2], m) as the kernels consume them.  In learned mode (phase truncation) the
         normalisation, the Gram matrices and their Cholesky factors are rebuilt on the device every call
-        (`gpfy_inducing_basis_fwd`) when every m_l <= 64; otherwise it is host numpy, as in fixed mode where the
+        (`gpfy_inducing_basis_fwd_ws`) when every m_l <= 256; otherwise it is host numpy, as in fixed mode where the
         factors are constants."""
         raw = [v for _, v in sorted(param.params["variational"]["inducing_features"].items())]
         m = [int(v.shape[0]) for v in raw]
-        if self._learned(param) and max(m) <= 64 and _runtime.cuda_available():
+        if self._learned(param) and max(m) <= 256 and _runtime.cuda_available():
             hp = _runtime.hot_path(raw[0].shape[1] - 1, m)
             vhat, lcat = hp.inducing_basis(np.concatenate(raw, 0), normalise=True)
             return vhat, lcat, m

@@ -187,10 +187,16 @@ GPFY_API int gpfy_svgp_elbo_finish(void* stream, const GpfyDesc* desc, int64_t n
  * pass).  V [M, dim] are the raw `V_l` parameters concatenated over degrees.
  *   fwd: vhat = rows of V normalised (normalise != 0), lcat = chol(alpha/(alpha+l) C_l^alpha(vhat vhat^T) + 1e-16 I)
  *   vjp: dV from the cotangents of (vhat, lcat) as gpfy_svgp_elbo_valgrad returns them (d_vhat, d_lcat).
- * Built for m_l <= 64; GPFY_EUNSUPPORTED otherwise (the host framework keeps that algebra). */
+ * Without scratch everything for a degree lives in shared memory: m_l <= 64, GPFY_EUNSUPPORTED otherwise.  The _ws forms take
+ * 32 * sum_l m_l^2 bytes of 16-byte aligned scratch (the four m_l x m_l matrices of every degree) and serve m_l <= 256
+ * (phase_truncation = 100 of the reference's sweeps included); with m_l <= 64 they ignore it. */
 GPFY_API int gpfy_inducing_basis_fwd(void* stream, const GpfyDesc* desc, const double* V, int normalise, double* vhat, double* lcat);
 GPFY_API int gpfy_inducing_basis_vjp(void* stream, const GpfyDesc* desc, const double* V, const double* lcat, int normalise,
                             const double* dvhat, const double* dlcat, double* dV);
+GPFY_API int gpfy_inducing_basis_fwd_ws(void* stream, const GpfyDesc* desc, const double* V, int normalise, double* vhat, double* lcat,
+                               void* workspace, size_t workspace_bytes);
+GPFY_API int gpfy_inducing_basis_vjp_ws(void* stream, const GpfyDesc* desc, const double* V, const double* lcat, int normalise,
+                               const double* dvhat, const double* dlcat, double* dV, void* workspace, size_t workspace_bytes);
 
 /* KL(q || N(0, I)) and its gradients (replaces variational.py:225-240 with :262-286 / :375-399).
  * out: [1 + M*P + P*M*M] = KL, dKL/dmu, dKL/dSigma.  TriL only reads diag/all of L; full covariance

@@ -158,3 +158,27 @@ def test_inducing_chain_matches_autograd_through_normalise_gram_cholesky(name):
     out = opt._inducing_chain(sh, param, np.concatenate(dvh, 0), np.concatenate([d.ravel() for d in dL]))
     for n in range(F):
         assert rel_err(out[f"V_{n:02d}"], grads[n].numpy()) < 1e-9, n
+
+
+# ---- reference likelihoods.py:172-186, 236-252 ----
+def test_conditional_distribution_objects():
+    """`Likelihood.conditional_distribution` returns p(Y | F): N(F, sigma^2) for Gaussian, Bernoulli(inv_probit(F)) otherwise -
+    host-side stand-ins for the TFP objects (mean / variance / log_prob / sample), checked against the closed forms."""
+    from scipy.stats import norm
+    from gpfy_b200.likelihoods import Bernoulli, Gaussian
+    rng = np.random.default_rng(0)
+    F, Y = rng.standard_normal((7, 2)), rng.standard_normal((7, 2))
+    lik = Gaussian()
+    param = lik.init()
+    param.params["likelihood"]["Gaussian"]["variance"] = np.array(0.37)
+    d = lik.conditional_distribution(param, F)
+    np.testing.assert_allclose(d.mean(), F)
+    np.testing.assert_allclose(d.variance(), np.full(F.shape, 0.37))
+    np.testing.assert_allclose(d.log_prob(Y), norm.logpdf(Y, F, np.sqrt(0.37)), rtol=1e-13)
+    assert d.sample((3,), seed=1).shape == (3, 7, 2)
+    b = Bernoulli().conditional_distribution(Bernoulli().init(), F)
+    p = 0.5 * (1.0 + torch.erf(torch.as_tensor(F) / 2.0 ** 0.5).numpy()) * (1 - 2e-3) + 1e-3
+    np.testing.assert_allclose(b.mean(), p, rtol=1e-13)
+    Yb = (Y > 0).astype(float)
+    np.testing.assert_allclose(b.log_prob(Yb), Yb * np.log(p) + (1 - Yb) * np.log1p(-p), rtol=1e-13)
+    assert set(np.unique(b.sample((5,), seed=2))) <= {0.0, 1.0}

@@ -265,6 +265,29 @@ def test_inducing_basis_on_device_matches_reference_and_autograd(name):
     assert rel_err(dV.cpu().numpy(), np.concatenate([x.numpy() for x in grads], 0)) < 1e-9
 
 
+def test_inducing_basis_on_device_beyond_64_points_per_degree():
+    """m_l = 100 (phase_truncation = 100 of the reference's sweeps, spherical_harmonics.py:119-127): the _ws entry points keep the four
+    m_l x m_l matrices of a degree in global scratch instead of shared memory.  Forward and reverse pass against the oracle
+    (normalise -> Gram -> Gegenbauer -> Cholesky and torch.autograd through it)."""
+    from gpfy_b200.ops import HotPath
+    rng = np.random.default_rng(11)
+    dim, m, alpha = 9, [1, 9, 30, 100, 100, 70], 3.5   # N(9, 2) = 44 harmonics of degree 2: 30 points keep that Gram matrix regular
+    V = [rng.standard_normal((k, dim)) for k in m]
+    hp = HotPath(dim - 1, m)
+    vhat, lcat = hp.inducing_basis(np.concatenate(V, 0), normalise=True)
+    Vt = [O.T(v).requires_grad_(True) for v in V]
+    Vh = O.normalise_V(Vt)
+    Ls = O.orthogonalise_basis(Vh, alpha)
+    assert rel_err(vhat.cpu().numpy(), np.concatenate([v.detach().numpy() for v in Vh], 0)) < 1e-14
+    assert rel_err(lcat.cpu().numpy(), np.concatenate([np.tril(l.detach().numpy()).ravel() for l in Ls])) < 1e-10
+    dvh = [rng.standard_normal(v.shape) for v in V]
+    dL = [np.tril(rng.standard_normal((k, k))) for k in m]
+    s = sum((v * O.T(d)).sum() for v, d in zip(Vh, dvh)) + sum((l * O.T(d)).sum() for l, d in zip(Ls, dL))
+    grads = torch.autograd.grad(s, Vt)
+    dV = hp.inducing_basis_vjp(np.concatenate(V, 0), lcat, np.concatenate(dvh, 0), np.concatenate([d.ravel() for d in dL]), normalise=True)
+    assert rel_err(dV.cpu().numpy(), np.concatenate([x.numpy() for x in grads], 0)) < 1e-9
+
+
 def test_fused_and_general_kernel_paths_agree_on_the_headline_shape():
     """Three independent implementations of the same step: the headline kernels (tensor-core zonal forward + zonal_bwd3,
     P = 1, ambient dim <= 16, Mp <= 288), the general fused backward (zonal_bwd4: C + derivative panel, any Mp / dim) and
