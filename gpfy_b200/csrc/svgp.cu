@@ -526,7 +526,7 @@ struct Plan {
   bool i8;          // GPFY_PREC_F64_I8: C = W2 Z as exact int8 digit products on tcgen05 (gemm_i8.cuh); float64 results
   GemmI8Blocks i8blk;
   int i8nsa;
-  int64_t o_Zi8, o_Wi8, o_rs8, o_ks8, o_bd8;
+  int64_t o_Zi8, o_Wi8, o_rs8, o_ks8, o_bd8, o_ctr;
   int npsi;
 };
 
@@ -574,8 +574,11 @@ static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, int prec = 
     // One uniform split count.  Measured (r02c): splits proportional to the tensor-core tile count of each block type
     // (12 diagonal / 18 off-diagonal / 12 partial) made the SYRK 5 - 10 % SLOWER at Mp = 352 and 256 - the kernel is not
     // bound by its DMMA count alone - so the per-type table stays at one value.
+    // Round 2: the CTAs are persistent and pull (block, point range) units from a counter, heaviest block type first, so the table
+    // only sets the granularity: about four units per resident CTA for a full chunk (a launch with fewer rows uses fewer, see
+    // syrk_ks_eff).
     (void)noff;
-    for (int t = 0; t < 4; ++t) sp.ks[t] = std::max(1, slots / (p->nb * (p->nb + 1) / 2));
+    for (int t = 0; t < 4; ++t) sp.ks[t] = std::max(1, 4 * slots / (p->nb * (p->nb + 1) / 2));
   }
   p->KSV = std::max(p->sms, (8 * p->sms) / (s.Mp / 32));  // dVhat partial slots: >= one per persistent CTA of the fused backward kernel
   p->nblocks_c = p->nc / 32;
@@ -640,6 +643,7 @@ static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, int prec = 
   p->o_rs8 = take(p->i8 ? Mp : 0);
   p->o_ks8 = take(p->i8 ? Mp : 0);
   p->o_bd8 = take(p->i8 ? Mp : 0);
+  p->o_ctr = take(32);   // work-unit counter of the weighted-Gram kernel
   if (p->i8) p->npsi = std::max(p->npsi, p->i8blk.nblk);
   p->total = o;
 }
@@ -1444,8 +1448,16 @@ int gpfy_svgp_elbo_rows(void* stream, const GpfyDesc* desc, int64_t n_capacity, 
         sa.split = p.split; sa.chunk = npts;   // the splits cover THIS launch's rows (a short slab still uses every CTA)
         sa.accumulate = 1;
         if (slice) { sa.zs_out = reinterpret_cast<int8_t*>(ws + p.o_Zi8); sa.kscale = ws + p.o_ks8; }
+        // units of at least 1024 points, never fewer ranges than two resident CTAs per SM can take
+        const int nblocks = p.nb * (p.nb + 1) / 2;
+        const int ks_fix = std::max(1, 2 * p.sms / nblocks);   // one unit per resident CTA
+        const bool fixed = p.nb == 3;   // three block rows (3 diagonal + 3 off-diagonal blocks): the fixed order pairs the two kinds on every SM; measured
+                                         // against the dynamic order: Mp = 288 11.5 vs 12.6 ms, Mp = 256 11.6 vs 11.9 ms per 4 M points; Mp = 352 23.3 vs 21.9, Mp = 576 24.8 vs 22.3
+        sa.ks_eff = fixed ? ks_fix : (int)std::min<int64_t>(p.split.ks[0], std::max<int64_t>(ks_fix, npts / 1024));
+        sa.counter = fixed ? nullptr : reinterpret_cast<int*>(ws + p.o_ctr);
+        if (sa.counter) GPFY_CUDA_OK(cudaMemsetAsync(sa.counter, 0, sizeof(int), st));
         GPFY_TRY(device_configure_once(DEV_CFG_SYRK, (const void*)syrk_dmma_kernel, SYRK_SMEM));
-        GPFY_K(syrk_dmma_kernel, p.split.total(), SYRK_THREADS, SYRK_SMEM, st, sa);
+        GPFY_K(syrk_dmma_kernel, fixed ? nblocks * sa.ks_eff : std::min(nblocks * sa.ks_eff, 2 * p.sms), SYRK_THREADS, SYRK_SMEM, st, sa);
       }
       return GPFY_OK;
     };
