@@ -77,3 +77,15 @@ def test_i8_is_exactly_zero_at_the_prior():
     _, v8 = p["hot"].predict_diag(*pa)
     _, v64 = p64["hot"].predict_diag(*pa)
     assert torch.equal(v8, v64)
+
+
+def test_contraction_path_reports_the_arithmetic_actually_used():
+    """gpfy_contraction_path: the int8 request is honoured where the kernel is built (P = 1, M_p <= 352, one of the fused backward
+    kernels) and falls back to the DMMA contraction elsewhere - same float64 contract either way."""
+    from gpfy_b200.ops import HotPath
+    assert HotPath(8, [1, 9, 30, 30, 30]).contraction_path(100_000) == "f64i8"
+    assert HotPath(8, [1, 9, 30, 30, 30], precision="f64dmma").contraction_path(100_000) == "f64"
+    assert HotPath(8, [1, 9, 30, 30, 30], precision="f32").contraction_path(100_000) == "f32"
+    assert HotPath(8, [1, 9, 30, 30, 30], num_outputs=2).contraction_path(100_000) == "f64"          # P > 1: legacy kernels
+    assert HotPath(8, [1, 9] + [64] * 9).contraction_path(100_000) == "f64"                          # M = 586 > 352
+    assert HotPath(8, [1, 9, 30, 30, 30], weight_mode="projection", projection_dim=3).contraction_path(100_000) == "f64"
