@@ -208,21 +208,24 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(gpfy_ffi_prior_kl_valgrad, PriorKlImpl,
                                                     .Ret<F64>().Ret<ffi::Buffer<ffi::U8>>()));
 
 // ---- Vs / Ls / orthogonalise_basis and their reverse pass  (spherical_harmonics.py:194-239, 265-288) ----
-static ffi::Error BasisFwdImpl(cudaStream_t stream, F64 V, RF64 vhat, RF64 lcat, int32_t normalise, GPFY_STATIC_PARAMS) {
+// scratch: 32 * sum m_l^2 bytes when some m_l > 64 (the per-degree matrices then live in global memory), any size otherwise
+static ffi::Error BasisFwdImpl(cudaStream_t stream, F64 V, RF64 vhat, RF64 lcat, RU8 scratch, int32_t normalise, GPFY_STATIC_PARAMS) {
   GPFY_STATIC_INIT;
-  return status(gpfy_inducing_basis_fwd(stream, &d, V.typed_data(), normalise, vhat->typed_data(), lcat->typed_data()));
+  return status(gpfy_inducing_basis_fwd_ws(stream, &d, V.typed_data(), normalise, vhat->typed_data(), lcat->typed_data(),
+                                           scratch->untyped_data(), scratch->size_bytes()));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(gpfy_ffi_inducing_basis_fwd, BasisFwdImpl,
                               GPFY_STATIC_ATTRS(ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Ret<F64>().Ret<F64>()
-                                                    .Attr<int32_t>("normalise")));
-static ffi::Error BasisVjpImpl(cudaStream_t stream, F64 V, F64 lcat, F64 dvhat, F64 dlcat, RF64 dV, int32_t normalise, GPFY_STATIC_PARAMS) {
+                                                    .Ret<ffi::Buffer<ffi::U8>>().Attr<int32_t>("normalise")));
+static ffi::Error BasisVjpImpl(cudaStream_t stream, F64 V, F64 lcat, F64 dvhat, F64 dlcat, RF64 dV, RU8 scratch, int32_t normalise,
+                               GPFY_STATIC_PARAMS) {
   GPFY_STATIC_INIT;
-  return status(gpfy_inducing_basis_vjp(stream, &d, V.typed_data(), lcat.typed_data(), normalise, dvhat.typed_data(), dlcat.typed_data(),
-                                        dV->typed_data()));
+  return status(gpfy_inducing_basis_vjp_ws(stream, &d, V.typed_data(), lcat.typed_data(), normalise, dvhat.typed_data(), dlcat.typed_data(),
+                                           dV->typed_data(), scratch->untyped_data(), scratch->size_bytes()));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(gpfy_ffi_inducing_basis_vjp, BasisVjpImpl,
                               GPFY_STATIC_ATTRS(ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>().Arg<F64>()
-                                                    .Arg<F64>().Ret<F64>().Attr<int32_t>("normalise")));
+                                                    .Arg<F64>().Ret<F64>().Ret<ffi::Buffer<ffi::U8>>().Attr<int32_t>("normalise")));
 
 // ---- project_variance / the conditional covariance of GP.predict  (variational.py:330-351, 443-464; model.py:231-259) ----
 static ffi::Error ProjectVarianceImpl(cudaStream_t stream, F64 A, F64 sigma, F64 base, RF64 out, RU8 scratch, int32_t subtract_identity,
