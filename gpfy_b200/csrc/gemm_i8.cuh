@@ -127,11 +127,7 @@ __device__ __forceinline__ void gi8_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ bool gi8_elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.b32 %0, 1, 0, px;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
+__device__ __forceinline__ bool gi8_elect_one() { return g32_elect_one(); }
 
 // waits of the warps that are NOT on the critical path back off between polls: nine warps spinning on mbarriers
 // were measured to slow the MMA warp's issue rate (tools/i8_gemm_bench.cu)

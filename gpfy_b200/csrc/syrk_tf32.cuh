@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
   __shared__ __align__(16) float wsm[4][2][32];    // per scale warp: wq / wp of the k-block's points, rounded to fp32
   const int Mp = a.Mp, NC = a.NC;
   const int stage_bytes = s32_stage_bytes(Mp, NC);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (see g32_elect_one)
   const int h = (int)blockIdx.x % a.H, ks = (int)blockIdx.x / a.H;
   const int64_t p0 = (int64_t)ks * a.range;
   int64_t p1 = p0 + a.range;
@@ -87,29 +88,32 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
+    {
       const int rows_box = Mp / a.nbox;
       for (int kb = 0; kb < kt; ++kb) {
         const int st = kb % S32_NS;
         if (kb >= S32_NS) mbar_wait(&empty[st], (unsigned)(((kb / S32_NS) - 1) & 1));
         uint8_t* dst = smem + st * stage_bytes;
-        mbar_expect_tx(&full_a[st], (unsigned)(2 * Mp * S32_RB));
         // planes are tile-contiguous ([n / 32][Mp][32]): the k-block's rows are ONE contiguous slab of HBM per plane
         const int64_t n0 = p0 + S32_KP * (int64_t)kb;
         const int col = (int)(n0 & 31), row0 = (int)((n0 >> 5) * Mp);
-        for (int b = 0; b < a.nbox; ++b) {
-          g32_tma_2d(dst + b * rows_box * S32_RB, &maps.zh, col, row0 + b * rows_box, &full_a[st]);
-          g32_tma_2d(dst + Mp * S32_RB + b * rows_box * S32_RB, &maps.zl, col, row0 + b * rows_box, &full_a[st]);
+        if (g32_elect_one()) {
+          mbar_expect_tx(&full_a[st], (unsigned)(2 * Mp * S32_RB));
+          for (int b = 0; b < a.nbox; ++b) {
+            g32_tma_2d(dst + b * rows_box * S32_RB, &maps.zh, col, row0 + b * rows_box, &full_a[st]);
+            g32_tma_2d(dst + Mp * S32_RB + b * rows_box * S32_RB, &maps.zl, col, row0 + b * rows_box, &full_a[st]);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+    {
       // both operands K-major (the contraction runs over the points), D f32, M = 128, N = NC
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t hiD = g32_desc_hi(S32_SBO, S32_LAYOUT);
@@ -130,20 +134,23 @@ __global__ void __launch_bounds__(S32_THREADS, 1) syrk_tf32x3_kernel(const __gri
         // K-major operands (swizzled rows of S32_RB bytes, 8-row atoms): 8 points = 32 B inside a row (+2 in the descriptor's
         // address field); tile t of the A operand starts r0 rows further down (+toff[t])
         const uint32_t ahl = g32_desc_lo(ah, 16), all = g32_desc_lo(al, 16), bhl = g32_desc_lo(bh, 16), bll = g32_desc_lo(bl, 16);
+        if (g32_elect_one()) {
 #pragma unroll
-        for (int k8 = 0; k8 < S32_KP / 8; ++k8) {
+          for (int k8 = 0; k8 < S32_KP / 8; ++k8) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            if (t < a.ntile) {
-              const uint32_t d = tmem + (uint32_t)(t * NC);
-              g32_mma2(d, all + toff[t] + 2 * k8, hiD, bhl + 2 * k8, hiD, idesc, ((inflush && kb) | k8) ? 1u : 0u);
-              g32_mma2(d, ahl + toff[t] + 2 * k8, hiD, bll + 2 * k8, hiD, idesc, 1u);
-              g32_mma2(d, ahl + toff[t] + 2 * k8, hiD, bhl + 2 * k8, hiD, idesc, 1u);
+            for (int t = 0; t < 4; ++t) {
+              if (t < a.ntile) {
+                const uint32_t d = tmem + (uint32_t)(t * NC);
+                g32_mma2(d, all + toff[t] + 2 * k8, hiD, bhl + 2 * k8, hiD, idesc, ((inflush && kb) | k8) ? 1u : 0u);
+                g32_mma2(d, ahl + toff[t] + 2 * k8, hiD, bll + 2 * k8, hiD, idesc, 1u);
+                g32_mma2(d, ahl + toff[t] + 2 * k8, hiD, bhl + 2 * k8, hiD, idesc, 1u);
+              }
             }
           }
+          g32_commit(&empty[st]);
+          if (inflush == KF - 1 || kb == kt - 1) g32_commit(&d_full);
         }
-        g32_commit(&empty[st]);
-        if (inflush == KF - 1 || kb == kt - 1) g32_commit(&d_full);
+        __syncwarp();
       }
     }
   } else {
