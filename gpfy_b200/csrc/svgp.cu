@@ -1732,7 +1732,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     if (p.f32) {
       GPFY_TRY(launch_gemm32(st, p, ws, 0, npts, nullptr, ws + p.o_psi));   // psi only, 3 x TF32 on tcgen05
     } else if (p.i8) {
-      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, nullptr, ws + p.o_psi));  // psi only, int8 digit products on tcgen05
+      GPFY_TRY(launch_gemm_i8(st, p, ws, npts, ws + p.o_C, nullptr));  // C by int8 digit products on tcgen05; psi = z . C in predict_kernel
     } else
     for (int q = 0; q < s.P; ++q) {
       GemmArgs g;
@@ -1749,6 +1749,7 @@ int gpfy_predict_diag(void* stream, const GpfyDesc* desc, int64_t n, const doubl
     pa.psi_part = ws + p.o_psi; pa.npsi = p.f32 ? 1 : (p.i8 ? p.i8blk.nblk : p.npsi); pa.mz = ws + p.o_mz; pa.ldz = p.nc;
     pa.R = ws + p.o_R; pa.vptr = variance; pa.P = s.P; pa.order = desc->kernel_order; pa.npts = npts;
     pa.fmu = fmu + c0 * s.P; pa.fvar = fvar + c0 * s.P;
+    if (p.i8) { pa.Zp = ws + p.o_Z; pa.Cb = ws + p.o_C; pa.Mp = Mp; pa.M = s.M; }
     GPFY_TRY(launch_predict(st, pa));
   }
   return GPFY_OK;

@@ -577,6 +577,10 @@ struct PredictArgs {
   int64_t npts;
   double* fmu;         // [npts][P]
   double* fvar;
+  // psi_n = z_n . C_n formed here from the two panels (int8 contraction, P = 1; see LikPointArgs): Zp [Mp][ldz], blocked C.  Null = psi_part.
+  const double* Zp = nullptr;
+  const double* Cb = nullptr;
+  int Mp = 0, M = 0;
 };
 
 __global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
@@ -587,6 +591,19 @@ __global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
   for (int k = 0; k < 2 * a.order; ++k) kd *= r;
   for (int p = 0; p < a.P; ++p) {
     double psi = 0.0;
+    if (a.Cb) {
+      const double* zc = a.Zp + n;
+      const double* cc = a.Cb + (n >> 5) * (int64_t)a.Mp * 32;
+      const int ln = (int)(n & 31);
+      double ps[4] = {0.0, 0.0, 0.0, 0.0};
+      int row = 0;
+      for (; row + 4 <= a.M; row += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ps[u] = fma(zc[(int64_t)(row + u) * a.ldz], cc[(row + u) * 32 + (ln ^ (u << 2))], ps[u]);
+      }
+      for (; row < a.M; ++row) ps[0] = fma(zc[(int64_t)row * a.ldz], cc[row * 32 + (ln ^ ((row & 3) << 2))], ps[0]);
+      psi = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    } else
     for (int k = 0; k < a.npsi; ++k) psi += a.psi_part[((int64_t)p * a.npsi + k) * a.ldz + n];
     a.fmu[n * a.P + p] = r * a.mz[(int64_t)p * a.ldz + n];
     a.fvar[n * a.P + p] = kd + r * r * psi;
