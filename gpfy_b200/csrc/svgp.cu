@@ -578,7 +578,8 @@ static void make_plan(const Shape& s, int64_t n, int op_in, Plan* p, int prec = 
     // only sets the granularity: about four units per resident CTA for a full chunk (a launch with fewer rows uses fewer, see
     // syrk_ks_eff).
     (void)noff;
-    for (int t = 0; t < 4; ++t) sp.ks[t] = std::max(1, 4 * slots / (p->nb * (p->nb + 1) / 2));
+    // (three block rows keep one unit per resident CTA, in the fixed order: no need for the finer slots)
+    for (int t = 0; t < 4; ++t) sp.ks[t] = std::max(1, (p->nb == 3 ? 1 : 4) * slots / (p->nb * (p->nb + 1) / 2));
   }
   p->KSV = std::max(p->sms, (8 * p->sms) / (s.Mp / 32));  // dVhat partial slots: >= one per persistent CTA of the fused backward kernel
   p->nblocks_c = p->nc / 32;
