@@ -1230,6 +1230,7 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     za.deg = deg; za.rc = rc;
     fa.mt = make_monic(desc->alpha);
     fa.Linv = ws + p.o_linv; fa.scale = degree_scale; fa.mul_r = mul_r; fa.out = out; fa.ldo = n; fa.r_out = r_out;
+    ft_deal_items(&fa, deg);
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_features2<DIMP>(st, fa)));
     return GPFY_OK;
   }

@@ -259,7 +259,32 @@ struct FeaturesArgs {
   double* out;            // [M][ldo], first column of this launch
   int64_t ldo;
   double* r_out;          // [npts] or null
+  unsigned char item_warp[160];   // phase B: warp of every (degree, 8-row tile) item, dealt on the host by falling cost (255 = round robin)
 };
+
+// host: longest-processing-time deal of the whitening items (cost = k-steps of the lower-triangular row tile) to the 8 warps
+static inline void ft_deal_items(FeaturesArgs* fa, const DegreeTable& deg) {
+  int cost[160], order[160], n = 0;
+  for (int l = 0; l < deg.F; ++l)
+    for (int i = 0; i * 8 < deg.m[l]; ++i) {
+      if (n >= 160) { for (int k = 0; k < 160; ++k) fa->item_warp[k] = 255; return; }
+      const int kend = deg.m[l] < 8 * i + 8 ? deg.m[l] : 8 * i + 8;
+      cost[n] = (kend + 3) / 4 + 2;   // + the store
+      order[n] = n;
+      ++n;
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (cost[order[j]] > cost[order[i]]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 160; ++k) fa->item_warp[k] = 255;
+  for (int i = 0; i < n; ++i) {
+    int best = 0;
+    for (int w = 1; w < 8; ++w) if (load[w] < load[best]) best = w;
+    fa->item_warp[order[i]] = (unsigned char)best;
+    load[best] += cost[order[i]];
+  }
+}
 
 constexpr int FT_LD = 32;
 __device__ __forceinline__ int ft_at(int row, int pt) { return row * FT_LD + (pt ^ ((row & 3) << 2)); }
@@ -395,7 +420,8 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
         const int off = offs[l], ml = offs[l + 1] - off;
         const double sc = scl[l];
         for (int i = 0; i * 8 < ml; ++i, ++item) {
-          if ((item & 7) != warp) continue;
+          const int iw = item < 160 ? (int)args.item_warp[item] : 255;
+          if ((iw == 255 ? (item & 7) : iw) != warp) continue;
           double acc[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) acc[u] = 0.0;
@@ -403,13 +429,24 @@ __global__ void __launch_bounds__(256, 2) features2_kernel(const __grid_constant
           const int kend = min(ml, 8 * i + 8);        // lower triangular: columns 0 .. 8 i + 7
           const bool rok = rloc < ml;
           const double* Lrow = args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off;
-#pragma unroll 4
-          for (int k0 = 0; k0 < kend; k0 += 4) {
-            const int kc = k0 + t4;
-            const double av = (rok && kc < ml) ? __ldg(Lrow + kc) : 0.0;
-            const int zrow = min(off + kc, Mp - 1);
+          // the A fragments (rows of Linv, read through L1) of eight k-steps are fetched ahead of the tensor-core steps that use
+          // them: one exposed load latency per 32 columns instead of one per step (ncu r02a: the DMMAs' long-scoreboard stalls)
+          for (int kb0 = 0; kb0 < kend; kb0 += 32) {
+            double av[8];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(acc[2 * nt], acc[2 * nt + 1], av, zt[ft_at(zrow, 8 * nt + g)]);
+            for (int q = 0; q < 8; ++q) {
+              const int kc = kb0 + 4 * q + t4;
+              av[q] = (rok && kc < ml && kb0 + 4 * q < kend) ? __ldg(Lrow + kc) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int k0 = kb0 + 4 * q;
+              if (k0 < kend) {
+                const int zrow = min(off + k0 + t4, Mp - 1);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(acc[2 * nt], acc[2 * nt + 1], av[q], zt[ft_at(zrow, 8 * nt + g)]);
+              }
+            }
           }
           if (rok) {
             double* orow = args.out + (int64_t)(off + rloc) * args.ldo + p0;
