@@ -42,7 +42,7 @@ struct ZonalBwd4Args {
 
 static inline int zb4_header_ring(int G, int NST) { return (NST + G - 1) / G + 1; }
 static inline int zb4_smem_bytes(int Mp, int dimp, int RG, int NST) {
-  const int hdr = 64 + 32 * dimp;
+  const int hdr = 128 + 32 * dimp;
   const int dbl = Mp * dimp + Mp + NST * 2 * RG * 32 + zb4_header_ring(Mp / RG, NST) * hdr + 2 * dimp * 32 + (1 + dimp) * 32;
   return dbl * 8 + 64;
 }
@@ -61,7 +61,7 @@ static inline bool zb4_plan(int Mp, int dimp, int* RG_out, int* NST_out) {
 template <int DIMP, int SLOTS>
 __global__ void __launch_bounds__(ZB4_THREADS, 1) zonal_bwd4_kernel(const __grid_constant__ ZonalBwd4Args a) {
   constexpr int CT = (DIMP + 7) / 8;
-  constexpr int HDR = 64 + 32 * DIMP;
+  constexpr int HDR = 128 + 32 * DIMP;
   constexpr int NBLK = CT * 4;                               // 8 x 8 output blocks of dxhat [CT * 8, 32]
   constexpr int BSLOTS = (NBLK + ZB4_CW - 1) / ZB4_CW;
   extern __shared__ __align__(16) double smem[];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(ZB4_THREADS, 1) zonal_bwd4_kernel(const __grid
   double* vs = smem;                               // [Mp][DIMP]
   double* mu2s = vs + Mp * DIMP;                   // [Mp]
   double* stg = mu2s + Mp;                         // [NST][ C slab RG x 32 | ZP slab RG x 32 ]
-  double* hdr = stg + NST * 2 * RG * 32;           // [HB][wp(32) | cq(32) | xhat(32 x DIMP)]
+  double* hdr = stg + NST * 2 * RG * 32;           // [HB][wp(32) | cq(32) | r(32) | dr(32) | xhat(32 x DIMP)]
   double* dxs = hdr + HB * HDR;                    // [2][DIMP][32]
   double* lsum = dxs + 2 * DIMP * 32;              // [1 + DIMP][32] per-lane running sums of the tail
 
@@ -110,29 +110,26 @@ __global__ void __launch_bounds__(ZB4_THREADS, 1) zonal_bwd4_kernel(const __grid
       }
       if (g == 0) {
         double* hb = hdr + (t % HB) * HDR;
+        if (lane == 27) tma_bulk_g2s(hb + 64, a.R + p0, 256, &bar_full[buf]);     // r and dr ride along for the tail (round 2: its own
+        if (lane == 28) tma_bulk_g2s(hb + 96, a.dr + p0, 256, &bar_full[buf]);    // global loads kept the compute warps waiting on bar_tail)
         if (lane == 29) tma_bulk_g2s(hb, a.wp + p0, 256, &bar_full[buf]);
         if (lane == 30) tma_bulk_g2s(hb + 32, a.cq + p0, 256, &bar_full[buf]);
-        if (lane == 31) tma_bulk_g2s(hb + 64, a.XH + p0 * DIMP, 32 * DIMP * 8, &bar_full[buf]);
+        if (lane == 31) tma_bulk_g2s(hb + 128, a.XH + p0 * DIMP, 32 * DIMP * 8, &bar_full[buf]);
       }
     };
     auto tail = [&](int t) {
       const int64_t n = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 32 + lane;
       const bool valid = n < a.npts;
       double xh[DIMP], dxh[DIMP];
-      double r = 1.0, drv = 0.0;
-      if (valid) {   // the global loads are issued before the wait
-        r = a.R[n];
-        drv = a.dr[n];
-#pragma unroll
-        for (int c = 0; c < DIMP; c += 2) {
-          const double2 v2 = *reinterpret_cast<const double2*>(a.XH + n * DIMP + c);
-          xh[c] = v2.x; xh[c + 1] = v2.y;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
-      }
       mbar_wait(&bar_tile[t & 1], (unsigned)((t >> 1) & 1));
+      // r, dr and the xhat rows of the tile sit in its header (TMA, with the first row group): no global load in the tail
+      const double* hb = hdr + (t % HB) * HDR;
+      const double r = valid ? hb[64 + lane] : 1.0, drv = valid ? hb[96 + lane] : 0.0;
+#pragma unroll
+      for (int c = 0; c < DIMP; c += 2) {
+        const double2 v2 = *reinterpret_cast<const double2*>(hb + 128 + lane * DIMP + c);
+        xh[c] = valid ? v2.x : 0.0; xh[c + 1] = valid ? v2.y : 0.0;
+      }
       const double* dx = dxs + (t & 1) * DIMP * 32;
 #pragma unroll
       for (int c = 0; c < DIMP; ++c) dxh[c] = dx[c * 32 + lane];
@@ -156,8 +153,10 @@ __global__ void __launch_bounds__(ZB4_THREADS, 1) zonal_bwd4_kernel(const __grid
     while (next_tail < n_my) {
       if (next_issue < n_stage) {
         const int buf = next_issue % NST;
-        const bool free_now = next_issue < NST || mbar_try_wait(&bar_empty[buf], (unsigned)(((next_issue / NST) - 1) & 1));
+        const bool hdr_free = (next_issue % G) != 0 || next_issue / G < HB || next_tail > next_issue / G - HB;   // the tail reads the header too
+        const bool free_now = hdr_free && (next_issue < NST || mbar_try_wait(&bar_empty[buf], (unsigned)(((next_issue / NST) - 1) & 1)));
         if (free_now) { issue(next_issue++); continue; }
+        if (!hdr_free) { tail(next_tail++); continue; }
       }
       if (mbar_try_wait(&bar_tile[next_tail & 1], (unsigned)((next_tail >> 1) & 1))) { tail(next_tail++); continue; }
       if (next_issue >= n_stage) { tail(next_tail++); }   // nothing left to issue: block in the tail's wait
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(ZB4_THREADS, 1) zonal_bwd4_kernel(const __grid
             const double af = cb[zb_at(lr + g8, pt)];
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
-              const double bf = (8 * c + g8 < DIMP && pt < nvalid) ? hb[64 + pt * DIMP + 8 * c + g8] : 0.0;
+              const double bf = (8 * c + g8 < DIMP && pt < nvalid) ? hb[128 + pt * DIMP + 8 * c + g8] : 0.0;
               dmma884(accv[sl][c][0], accv[sl][c][1], af, bf);
             }
           }
