@@ -7,7 +7,7 @@
 //   x         = sum_{i = 1..S} x_i 256^-i + e,   x_i in [-128, 127],  |e| <= 2^-49         (S = 6 digits, |x| <= 0.4902)
 //   C[o, n]   = r_o sum_{g = 2..S+1} 256^-g  sum_{i + j = g} sum_k a_i[n, k] b_j[o, k]     (21 digit products, 6 accumulators)
 //
-// Every digit product is exact (|sum| <= 6 * 352 * 2^14 < 2^26 in int32); the error is the two operands' truncation (2^-49 of the row /
+// Every digit product is exact (|sum| <= 6 * 864 * 2^14 < 2^27 in int32); the error is the two operands' truncation (2^-49 of the row /
 // column maximum each) plus the dropped products i + j >= S + 2 (<= 5 * K * 2^14 * 256^-8 = 2^-39.5 K-worst-case, ~2^-46 typical) -
 // normwise ~1e-14 of max|C| against ~1e-15 for the DMMA kernel and the 1e-10 contract (tests/test_gpu_i8.py).
 //
@@ -32,7 +32,7 @@ constexpr int GI8_S = 6;                       // digits per operand
 constexpr int GI8_BM = 128;                    // points per tile
 constexpr int GI8_THREADS = 704;               // producer warp, MMA warp, 20 epilogue warps (one per TMEM lane quarter and 16 columns)
 constexpr int GI8_A_STAGE = GI8_S * 4096;      // bytes of one k-block (32 features) of a tile, all digits
-constexpr int GI8_MAXBLK = 8;
+constexpr int GI8_MAXBLK = 32;
 constexpr int GI8_MAXNB = 80;
 constexpr int GI8_STATIC_SMEM = 12 * 1024;    // barriers, row scales, psi staging (2 x 5 x 4 x 32 doubles): see gemm_i8_kernel
 #ifndef GI8_SLEEP_NS
@@ -68,44 +68,50 @@ struct GemmI8Args {
   GemmI8Blocks blk;
 };
 
-// out-blocks: ceil(Mp / 80) blocks of whole 16-row units, as equal as possible; SMs in proportion to the MMA time per tile
+// out-blocks: the widest blocks (<= 80 rows, whole 16-row units, as equal as possible) whose resident W2 planes leave room for at
+// least two stages of the Z ring - 80 rows up to Mp = 352, 64 at 384 .. 448, 48 at 576 (T = 64), 32 beyond; SMs in proportion to the
+// MMA time per tile
 static inline bool gi8_plan(int Mp, int sms, GemmI8Blocks* b, int* nsa) {
   if (Mp % 32 || Mp < 32) return false;
   const int units = Mp / 16;
-  const int nblk = (Mp + GI8_MAXNB - 1) / GI8_MAXNB;
-  if (nblk > GI8_MAXBLK || sms < nblk) return false;
-  b->nblk = nblk;
-  int r0 = 0, maxrows = 0;
-  int64_t off = 0;
-  double wsum = 0.0, w[GI8_MAXBLK];
-  for (int i = 0; i < nblk; ++i) {
-    const int u = units / nblk + (i < units % nblk ? 1 : 0);
-    b->row0[i] = r0;
-    b->rows[i] = 16 * u;
-    b->woff[i] = off;
-    r0 += 16 * u;
-    off += (int64_t)GI8_S * 16 * u * Mp;
-    maxrows = 16 * u > maxrows ? 16 * u : maxrows;
-    w[i] = 16 * u / 2.0 > 32.0 + 16 * u / 4.0 ? 16 * u / 2.0 : 32.0 + 16 * u / 4.0;
-    wsum += w[i];
+  for (int nbmax = GI8_MAXNB; nbmax >= 32; nbmax -= 16) {
+    const int nblk = (Mp + nbmax - 1) / nbmax;
+    if (nblk > GI8_MAXBLK || sms < nblk) continue;
+    b->nblk = nblk;
+    int r0 = 0, maxrows = 0;
+    int64_t off = 0;
+    double wsum = 0.0, w[GI8_MAXBLK];
+    for (int i = 0; i < nblk; ++i) {
+      const int u = units / nblk + (i < units % nblk ? 1 : 0);
+      b->row0[i] = r0;
+      b->rows[i] = 16 * u;
+      b->woff[i] = off;
+      r0 += 16 * u;
+      off += (int64_t)GI8_S * 16 * u * Mp;
+      maxrows = 16 * u > maxrows ? 16 * u : maxrows;
+      const double wi = 16 * u / 2.0 > 32.0 + 16 * u / 4.0 ? 16 * u / 2.0 : 32.0 + 16 * u / 4.0;
+      w[i] = wi > 45.0 ? wi : 45.0;   // no kind::i8 MMA issues faster than ~45 cycles (tools/i8_probe.cu)
+      wsum += w[i];
+    }
+    const int avail = 227 * 1024 - 1024 - GI8_STATIC_SMEM - GI8_S * maxrows * Mp;   // alignment slack, static shared memory, resident W2 planes
+    if (avail < 2 * GI8_A_STAGE) continue;
+    *nsa = avail / GI8_A_STAGE > 4 ? 4 : avail / GI8_A_STAGE;
+    int given = 0;
+    for (int i = 0; i < nblk; ++i) {
+      b->cta0[i] = given;
+      int c = (int)(sms * w[i] / wsum);
+      if (c < 1) c = 1;
+      given += c;
+    }
+    b->cta0[nblk] = given;
+    // leftover SMs to the blocks in order (heaviest first: blocks are sorted by size)
+    int left = sms - given;
+    for (int i = 0; left > 0; i = (i + 1) % nblk, --left)
+      for (int j = i + 1; j <= nblk; ++j) b->cta0[j] += 1;
+    if (b->cta0[nblk] > sms) continue;
+    return true;
   }
-  int given = 0;
-  for (int i = 0; i < nblk; ++i) {   // largest remainder
-    b->cta0[i] = given;
-    int c = (int)(sms * w[i] / wsum);
-    if (c < 1) c = 1;
-    given += c;
-  }
-  b->cta0[nblk] = given;
-  // leftover SMs to the blocks in order (heaviest first: blocks are sorted by size)
-  int left = sms - given;
-  for (int i = 0; left > 0; i = (i + 1) % nblk, --left)
-    for (int j = i + 1; j <= nblk; ++j) b->cta0[j] += 1;
-  if (b->cta0[nblk] > sms) return false;
-  const int avail = 227 * 1024 - 1024 - GI8_STATIC_SMEM - GI8_S * maxrows * Mp;   // alignment slack, static shared memory, resident W2 planes
-  *nsa = avail / GI8_A_STAGE;
-  if (*nsa > 4) *nsa = 4;
-  return *nsa >= 2;
+  return false;
 }
 static inline int gi8_smem_bytes(int Mp, const GemmI8Blocks& b, int nsa) {
   int maxrows = 0;

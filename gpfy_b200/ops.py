@@ -55,7 +55,7 @@ def shape_function(fn, alpha, x, device=None):
 
 
 # precision of the dense contraction C = W2 Z (include/gpfy_b200.h GPFY_PREC_*).  "f64" - the default, float64 results to the
-# reference's 1e-10 contract - runs it as exact int8 digit products on tcgen05 where that kernel is built (P = 1, M <= 352, one of
+# reference's 1e-10 contract - runs it as exact int8 digit products on tcgen05 where that kernel is built (P = 1, M <= 864, one of
 # the fused backward kernels; ~1e-14 normwise) and on the FP64 tensor cores elsewhere; "f64dmma" forces the DMMA kernel everywhere.
 PRECISIONS = {"f64": _lib.PREC_F64_I8, "f64i8": _lib.PREC_F64_I8, "f64dmma": _lib.PREC_F64, "f32": _lib.PREC_TF32X3, "tf32x3": _lib.PREC_TF32X3}
 

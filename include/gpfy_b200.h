@@ -61,7 +61,7 @@ enum { GPFY_W_ARD = 0, GPFY_W_SCALAR = 1, GPFY_W_PROJECTION = 2 };
  *   GPFY_PREC_F64_I8 : float64 RESULTS from the int8 tensor cores - an Ozaki-style error-free split of W2 and Z into six signed
  *                      radix-256 digits each, the 21 digit products with i + j <= 7 as tcgen05 kind::i8 MMAs into exact int32
  *                      TMEM accumulators, recombined in float64 (csrc/gemm_i8.cuh).  Normwise error of C ~1e-14 (DMMA: ~1e-15),
- *                      inside the 1e-10 contract of the float64 path; shapes it is not built for (num_outputs > 1, M > 352,
+ *                      inside the 1e-10 contract of the float64 path; shapes it is not built for (num_outputs > 1, M > 864,
  *                      the one-point-per-lane backward kernels) run the DMMA contraction - same results, same contract. */
 enum { GPFY_PREC_F64 = 0, GPFY_PREC_TF32X3 = 1, GPFY_PREC_F64_I8 = 2 };
 

@@ -46,7 +46,8 @@ def test_i8_elbo_gradients_and_predictions_match_goldens_and_dmma(name):
 
 
 @pytest.mark.parametrize("d,F,T,lik,N", [(8, 11, 30, "gaussian", 150_001), (8, 13, 30, "gaussian", 60_000), (32, 5, 64, "bernoulli", 60_000),
-                                          (8, 11, 30, "bernoulli", 40_000), (2, 11, 12, "gaussian", 40_000), (8, 11, 20, "gaussian", 33_333)])
+                                          (8, 11, 30, "bernoulli", 40_000), (2, 11, 12, "gaussian", 40_000), (8, 11, 20, "gaussian", 33_333), (8, 11, 64, "gaussian", 20_000),
+                                          (8, 11, 100, "gaussian", 10_000)])
 def test_i8_matches_dmma_at_the_bench_shapes(d, F, T, lik, N):
     """cfg3 / cfg4 / cfg5 shapes, S^2 and an M = 200 case (four out-blocks of 64 / 48 rows), tail tiles included."""
     from gpfy_b200.synthetic import headline_problem
@@ -87,5 +88,6 @@ def test_contraction_path_reports_the_arithmetic_actually_used():
     assert HotPath(8, [1, 9, 30, 30, 30], precision="f64dmma").contraction_path(100_000) == "f64"
     assert HotPath(8, [1, 9, 30, 30, 30], precision="f32").contraction_path(100_000) == "f32"
     assert HotPath(8, [1, 9, 30, 30, 30], num_outputs=2).contraction_path(100_000) == "f64"          # P > 1: legacy kernels
-    assert HotPath(8, [1, 9] + [64] * 9).contraction_path(100_000) == "f64"                          # M = 586 > 352
+    assert HotPath(8, [1, 9] + [64] * 9).contraction_path(100_000) == "f64i8"                        # M = 586: out-blocks of 48 rows
+    assert HotPath(8, [1, 9] + [100] * 9).contraction_path(100_000) == "f64"                         # M = 910 > 864: the W2 planes no longer fit
     assert HotPath(8, [1, 9, 30, 30, 30], weight_mode="projection", projection_dim=3).contraction_path(100_000) == "f64"
