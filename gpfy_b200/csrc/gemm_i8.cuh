@@ -19,9 +19,11 @@
 // to the out-blocks in proportion to a block's MMA time, max(NB / 2, 32 + NB / 4) cycles per product (measured, tools/i8_probe.cu:
 // below N = 128 an MMA is bound by the 128 B/clk shared-memory read of its operands, 4 KB of A + 32 NB of B).
 // Roles (704 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane; two issuing warps were measured SLOWER: 89 cycles per
-// MMA against 52), warps 2..21 = epilogue, one per TMEM lane quarter and 16 columns of the block (tcgen05.ld, digits -> float64 by Horner, row scale, C stored in the tile-contiguous swizzled
-// layout zonal_bwd3 / zonal_bwd4 read; optional psi = z . C partial sums).  The accumulator of digit group g is handed back to the
-// MMA warp as soon as the epilogue has read it, so the next tile's first k-block overlaps the drain.
+// MMA against 52), warps 2..21 = epilogue, one per TMEM lane quarter and 16 columns of the block (tcgen05.ld, accumulator pairs folded
+// in integer arithmetic, converted and chained in float64, row scale, C stored in the tile-contiguous swizzled layout zonal_bwd3 /
+// zonal_bwd4 read; optional psi = z . C partial sums - the library's callers now form psi in lik_point_kernel / predict_kernel
+// instead, because FP64 instructions of these warps are slow while the tensor pipe is saturated).  The accumulators of a digit-group
+// pair are handed back to the MMA warp as soon as the epilogue has read them, so the next tile's first k-block overlaps the drain.
 #pragma once
 #include "common.cuh"
 #include "gemm_tf32.cuh"
