@@ -4,7 +4,8 @@ import numpy as np, torch
 sys.path.insert(0, ".")
 from gpfy_b200.synthetic import headline_problem
 from gpfy_b200.ops import gegenbauer
-for (N, T, P, lik, d, F) in [(1000, 30, 1, "gaussian", 8, 11), (333, 12, 2, "bernoulli", 5, 5), (65, 30, 1, "gaussian", 8, 11), (257, 8, 1, "gaussian", 2, 6)]:
+for (N, T, P, lik, d, F) in [(1000, 30, 1, "gaussian", 8, 11), (333, 12, 2, "bernoulli", 5, 5), (65, 30, 1, "gaussian", 8, 11), (257, 8, 1, "gaussian", 2, 6),
+                             (700, 30, 1, "gaussian", 8, 13), (515, 64, 1, "bernoulli", 32, 5), (300, 64, 1, "gaussian", 8, 11)]:   # int8 contraction on the zonal_bwd4 paths
     prob = headline_problem(N, d=d, F=F, T=T, P=P, likelihood=lik, device="cuda")
     hp, args = prob["hot"], prob["args"]
     X, Y, w, b, v, eig, vhat, lcat, mu, sg, s2 = args
