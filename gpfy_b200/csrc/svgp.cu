@@ -1116,6 +1116,21 @@ GPFY_API int gpfy_debug_zb_clocks(unsigned long long* out) {
 }
 #endif
 
+// The int8 contraction's work split for Mp rows on `sms` SMs (host arithmetic only; tests/test_i8_plan_cpu.py):
+// out[0] = built (0 / 1), out[1] = out-blocks, out[2] = ring stages, out[3] = shared-memory bytes, then per block (row0, rows, first CTA), then the CTA total.
+GPFY_API int gpfy_debug_i8_plan(int Mp, int sms, int* out, int out_len) {
+  GemmI8Blocks b;
+  int nsa = 0;
+  if (!out || out_len < 5 + 3 * GI8_MAXBLK) return GPFY_EINVAL;
+  const bool ok = gi8_plan(Mp, sms, &b, &nsa);
+  out[0] = ok ? 1 : 0;
+  if (!ok) return GPFY_OK;
+  out[1] = b.nblk; out[2] = nsa; out[3] = gi8_smem_bytes(Mp, b, nsa) + GI8_STATIC_SMEM;
+  for (int i = 0; i < b.nblk; ++i) { out[4 + 3 * i] = b.row0[i]; out[5 + 3 * i] = b.rows[i]; out[6 + 3 * i] = b.cta0[i]; }
+  out[4 + 3 * b.nblk] = b.cta0[b.nblk];
+  return GPFY_OK;
+}
+
 GPFY_API int gpfy_debug_kernel_timing(int enable) {
   g_timer.on = enable != 0;
   for (int k = 0; k < TK_COUNT; ++k) g_timer.used[k] = 0;
