@@ -518,6 +518,25 @@ def run_ours(a):
     extras = {}
     if world == 1 and not a.no_extras:
         extras = side_measurements(a, c, prob, e0, e1)
+        if path == "f64i8":
+            # the same step with the contraction on the FP64 tensor cores (DMMA) only, for comparison inside the same run
+            from gpfy_b200.ops import HotPath
+            hd = HotPath(c["d"], prob["m"], num_outputs=1, kernel_order=1, likelihood=c["lik"], q_kind="tril", weight_mode="ard", device=dev,
+                         precision="f64dmma")
+            pk = torch.empty_like(packed)
+            for _ in range(2):
+                hd.elbo_valgrad_packed(*args, out=pk)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                hd.elbo_valgrad_packed(*args, out=pk)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_d = e0.elapsed_time(e1) / 3
+            extras["f64_dmma"] = {"workload": "the same step with precision f64dmma (contraction on the FP64 tensor cores)", "value": N / (ms_d * 1e-3),
+                                  "unit": UNIT, "ms_per_step": ms_d, "steps": 3,
+                                  "rel_diff_of_packed_result": float(((pk - packed).abs().max() / packed.abs().max()).item())}
+            del hd, pk
 
     line = {
         "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
