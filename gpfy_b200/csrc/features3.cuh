@@ -1,0 +1,193 @@
+// K_F3  fused feature matrix without CTA barriers (spherical_harmonics.py:290-320, :344-362, :385-387):
+//     out[off_l + i, n] = scale_l * (r_n) * sum_k Linv_l[i][k] C_l^alpha(Vhat_l xhat_n)[k]
+// The whitening is block diagonal: the output rows of degree l need the zonal values of degree l only.  So the work unit is
+// (32-point tile, group of whole degrees) and ONE WARP carries a unit from the points' coordinates to the stored rows - zonal forward
+// on the FP64 tensor cores into the warp's private shared-memory tile, __syncwarp, lower-triangular DMMA whitening out of that tile,
+// store.  No warp ever waits for another: `features2_kernel` (one CTA per tile, phase A | barrier | phase B | barrier) spent 19 % of
+// its stall samples at the two barriers and ran its DMMAs at 30 % of the pipe (profiles/ncu_full_r02a_features2_summary.txt).
+// Every warp re-projects its tile's points (8 d bytes per point out of L1/L2, ~5 % of a unit's instructions).  Degrees are grouped on the
+// host (`ft3_groups`) so that tiny degrees (m_0 = 1, m_1 = d + 1) ride with a full one; units go round-robin over all warps of the grid,
+// consecutive units (same tile, next group) to the warps of one CTA.
+// Shapes: every m_l <= 32 (the private tile is 32 rows), padded dimension <= 32; the rest stays on features2_kernel.
+#pragma once
+#include "zonal_fwd2.cuh"
+
+namespace gpfy {
+
+struct Features3Args {
+  FeaturesArgs f;
+  int ngrp;
+  unsigned char grp_lo[GPFY_MAX_DEGREES + 2];   // group gi = degrees grp_lo[gi] .. grp_lo[gi + 1] - 1
+};
+
+// host: consecutive degrees are merged while the group stays within 40 rows (a full 30/32-row degree plus the small leading ones)
+static inline bool ft3_groups(Features3Args* fa, const DegreeTable& deg) {
+  int n = 0, rows = 0;
+  fa->grp_lo[0] = 0;
+  for (int l = 0; l < deg.F; ++l) {
+    if (deg.m[l] > 32) return false;
+    if (rows > 0 && rows + deg.m[l] > 40) { fa->grp_lo[++n] = (unsigned char)l; rows = 0; }
+    rows += deg.m[l];
+  }
+  fa->grp_lo[++n] = (unsigned char)deg.F;
+  fa->ngrp = n;
+  return true;
+}
+
+static inline int ft3_smem_bytes(int Mp, int dimp) {
+  const int dbl = Mp * dimp + 8 * (32 * 32 + 32) + 3 * (GPFY_MAX_DEGREES + 2) + 4;
+  return dbl * 8 + (GPFY_MAX_DEGREES + 1) * 4 + 16;
+}
+
+template <int DIMP>
+__global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant__ Features3Args args3) {
+  static_assert(DIMP <= 32, "the coordinates are staged in the warp's 32 x 32 tile");
+  constexpr int KS = DIMP / 4;
+  const FeaturesArgs& args = args3.f;
+  const ZonalArgs& a = args.z;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint64_t bar;
+  const int Mp = a.Mp;
+  double* vs = smem;                           // [Mp][DIMP]
+  double* ztw = vs + Mp * DIMP;                // [8 warps][32][32] swizzled zonal tile of one degree (first the tile's coordinates)
+  double* rsw = ztw + 8 * 32 * 32;             // [8][32] radii (or 1)
+  double* leads = rsw + 8 * 32;                // [MAX_DEGREES + 2]
+  double* scl = leads + GPFY_MAX_DEGREES + 2;  // [MAX_DEGREES + 2] per-degree output scale
+  double* betas = scl + GPFY_MAX_DEGREES + 2;  // [MAX_DEGREES + 6]
+  int* offs = reinterpret_cast<int*>(betas + GPFY_MAX_DEGREES + 6);  // [F + 1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int F = a.deg.F;
+  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) {
+    leads[i] = args.mt.lead[i];
+    scl[i] = (i < F && args.scale) ? args.scale[i] : 1.0;
+  }
+  for (int i = tid; i < GPFY_MAX_DEGREES + 6; i += 256) betas[i] = i < GPFY_MAX_DEGREES + 2 ? args.mt.beta[i] : 0.0;
+  if (tid == 0) {
+    int o = 0;
+    for (int l = 0; l < F; ++l) { offs[l] = o; o += a.deg.m[l]; }
+    offs[F] = o;
+  }
+  stage_params_tma(vs, a.vhat_p, (unsigned)(Mp * DIMP * 8), &bar);
+  __syncthreads();   // the only CTA barrier: parameters staged
+
+  double* zt = ztw + warp * 32 * 32;
+  double* rw = rsw + warp * 32;
+  const int ngrp = args3.ngrp;
+  const int64_t tiles = (a.npts + 31) / 32;
+  // unit u = tile * ngrp + group, walked with stride gridDim.x * 8 without a division per unit
+  const int stride = (int)gridDim.x * 8;
+  const int sdiv = stride / ngrp, smod = stride - sdiv * ngrp;
+  const bool vec_ok = (args.ldo & 1) == 0;
+  // lane-constant parts of the swizzled tile addresses (ft_at with a row index that is a multiple of 4 plus t4 / 8 j + g)
+  int bidx[4];   // B fragment of k-step k0: zt[k0 * 32 + bidx[nt]] = tile[k0 + t4][8 nt + g]
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) bidx[nt] = ft_at(t4, 8 * nt + g);
+  const int sidx = g * FT_LD;   // C fragment store: row 8 j + g, columns (8 nt + 2 t4) ^ ((g & 3) << 2)
+  const int sswz = (g & 3) << 2;
+
+  const int u0 = (int)blockIdx.x * 8 + warp;
+  int gi = u0 % ngrp;
+  for (int64_t tile = u0 / ngrp; tile < tiles; tile += sdiv) {
+    const int64_t p0 = tile * 32;
+    // ---- the tile's points onto the sphere (lane = point), B fragments of the projection through the private tile ----
+    {
+      const int64_t n = p0 + lane;
+      double xh[DIMP];
+#pragma unroll
+      for (int c = 0; c < DIMP; ++c) xh[c] = 0.0;
+      double r = 1.0;
+      if (n < a.npts) {
+        r = load_point<DIMP>(a.X, a.xcols, a.apply_to_sphere, a.sw, a.sb, a.dim, n, xh, a.proj);
+        if (args.r_out && gi == 0) args.r_out[n] = r;
+      }
+#pragma unroll
+      for (int c = 0; c < DIMP; c += 2) *reinterpret_cast<double2*>(zt + lane * DIMP + c) = make_double2(xh[c], xh[c + 1]);
+      rw[lane] = args.mul_r ? r : 1.0;
+    }
+    __syncwarp();
+    double xb[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) xb[ks][nt] = zt[(8 * nt + g) * DIMP + 4 * ks + t4];
+    __syncwarp();
+
+    for (int l = args3.grp_lo[gi]; l < (int)args3.grp_lo[gi + 1]; ++l) {
+      const int off = offs[l], ml = offs[l + 1] - off;
+      const int ntl = (ml + 7) >> 3;
+      // ---- zonal values of degree l into the private tile (rows past m_l as zeros) ----
+      const double ld = leads[l];
+      for (int j = 0; j < ntl; ++j) {
+        const int rloc = 8 * j + g;
+        const double* vrow = vs + min(off + rloc, Mp - 1) * DIMP + t4;
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const double av = vrow[4 * ks];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(t[2 * nt], t[2 * nt + 1], av, xb[ks][nt]);
+        }
+        double z[8];
+        if (l >= 1) {
+          double p[8], p1[8], p2[8];
+          monic_uniform<8>(betas, l, t, p, p1, p2);
+          const double s = rloc < ml ? ld : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) z[q] = s * p[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) z[q] = rloc < ml ? 1.0 : 0.0;
+        }
+        double* zr = zt + j * (8 * FT_LD) + sidx;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<double2*>(zr + ((8 * nt + 2 * t4) ^ sswz)) = make_double2(z[2 * nt], z[2 * nt + 1]);
+      }
+      __syncwarp();
+      // ---- whitening: row tile i of the degree needs columns 0 .. 8 i + 7 of Linv_l (lower triangular) ----
+      const double sc = scl[l];
+      for (int i = 0; i < ntl; ++i) {
+        const int rloc = 8 * i + g;
+        const bool rok = rloc < ml;
+        const int kend = min(ml, 8 * i + 8);
+        const double* Lrow = args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off + t4;
+        double av[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) av[q] = (rok && 4 * q + t4 < ml && 4 * q < kend) ? __ldg(Lrow + 4 * q) : 0.0;
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (4 * q < kend) {
+            const double* zk = zt + q * (4 * FT_LD);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[2 * nt], acc[2 * nt + 1], av[q], zk[bidx[nt]]);
+          }
+        }
+        if (rok) {
+          double* orow = args.out + (int64_t)(off + rloc) * args.ldo + p0;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int c = 8 * nt + 2 * t4;
+            const double2 rr = *reinterpret_cast<const double2*>(rw + c);
+            const double v0 = sc * rr.x * acc[2 * nt], v1 = sc * rr.y * acc[2 * nt + 1];
+            if (p0 + c + 1 < a.npts && vec_ok) *reinterpret_cast<double2*>(orow + c) = make_double2(v0, v1);
+            else {
+              if (p0 + c < a.npts) orow[c] = v0;
+              if (p0 + c + 1 < a.npts) orow[c + 1] = v1;
+            }
+          }
+        }
+      }
+      __syncwarp();   // the tile is consumed before the next degree (or the next unit's coordinates) overwrites it
+    }
+    gi += smod;
+    if (gi >= ngrp) { gi -= ngrp; ++tile; }
+  }
+}
+
+}  // namespace gpfy

@@ -13,6 +13,7 @@
 #include "zonal_bwd3.cuh"
 #include "zonal_bwd4.cuh"
 #include "zonal_fwd2.cuh"
+#include "features3.cuh"
 #include "basis.cuh"
 #include "features_vjp.cuh"
 #include "syrk_tf32.cuh"
@@ -731,6 +732,23 @@ static int launch_features2(cudaStream_t st, const FeaturesArgs& fa) {
 }
 
 template <int DIMP>
+static int launch_features3(cudaStream_t st, const Features3Args& fa) {
+  if constexpr (DIMP <= 32) {
+    const int smem = ft3_smem_bytes(fa.f.z.Mp, DIMP);
+    const int64_t units = ((fa.f.z.npts + 31) / 32) * fa.ngrp;
+    const unsigned grid = (unsigned)std::min<int64_t>((units + 7) / 8, 2 * device_sms());
+    GPFY_TRY(set_smem(features3_kernel<DIMP>, smem));
+    features3_kernel<DIMP><<<grid, 256, smem, st>>>(fa);
+    GPFY_COUNT_LAUNCH();
+    GPFY_LAUNCH_OK();
+    return GPFY_OK;
+  } else {
+    set_error("features3: padded dim %d > 32", DIMP);
+    return GPFY_EUNSUPPORTED;
+  }
+}
+
+template <int DIMP>
 static int launch_zonal_bwd(cudaStream_t st, const ZonalBwdArgs& a) {
   const int smem = (a.Mp * DIMP + a.P * a.Mp + 8 * DIMP * 32) * 8;
   const unsigned grid = (unsigned)((a.npts + 31) / 32);
@@ -1245,6 +1263,13 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     za.deg = deg; za.rc = rc;
     fa.mt = make_monic(desc->alpha);
     fa.Linv = ws + p.o_linv; fa.scale = degree_scale; fa.mul_r = mul_r; fa.out = out; fa.ldo = n; fa.r_out = r_out;
+    // barrier-free variant (one warp = one (tile, degree group) unit) when every degree fits its 32-row private tile
+    Features3Args f3;
+    if (s.dimp <= 32 && ft3_smem_bytes(Mp, s.dimp) <= 113 * 1024 && !debug_option(DBG_NO_FEATURES3) && ft3_groups(&f3, deg)) {
+      f3.f = fa;
+      GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_features3<DIMP>(st, f3)));
+      return GPFY_OK;
+    }
     ft_deal_items(&fa, deg);
     GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_features2<DIMP>(st, fa)));
     return GPFY_OK;
