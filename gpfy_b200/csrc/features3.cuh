@@ -39,6 +39,23 @@ static inline int ft3_smem_bytes(int Mp, int dimp) {
   return dbl * 8 + (GPFY_MAX_DEGREES + 1) * 4 + 16;
 }
 
+// NQ k-steps of one 8-row tile of the whitening: A fragments (rows of Linv_l through L1, columns past m_l as zeros) fetched ahead of
+// the tensor-core steps, B fragments from the warp's swizzled tile.  lrow = &Linv_l[row][t4]; `lane_row` = row inside the degree.
+template <int NQ>
+__device__ __forceinline__ void ft3_whiten_steps(double (&acc)[8], const double* __restrict__ lrow, bool rok, int ml, const double* zt,
+                                                 const int (&bidx)[4]) {
+  const int t4 = threadIdx.x & 3;
+  double av[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) av[q] = (rok && 4 * q + t4 < ml) ? __ldg(lrow + 4 * q) : 0.0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const double* zk = zt + q * (4 * FT_LD);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) dmma884(acc[2 * nt], acc[2 * nt + 1], av[q], zk[bidx[nt]]);
+  }
+}
+
 template <int DIMP>
 __global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant__ Features3Args args3) {
   static_assert(DIMP <= 32, "the coordinates are staged in the warp's 32 x 32 tile");
@@ -91,6 +108,7 @@ __global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant
   int gi = u0 % ngrp;
   for (int64_t tile = u0 / ngrp; tile < tiles; tile += sdiv) {
     const int64_t p0 = tile * 32;
+    const bool full = vec_ok && p0 + 32 <= a.npts;   // whole tile in range and 16-byte aligned rows: unguarded vector stores
     // ---- the tile's points onto the sphere (lane = point), B fragments of the projection through the private tile ----
     {
       const int64_t n = p0 + lane;
@@ -148,34 +166,43 @@ __global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant
       }
       __syncwarp();
       // ---- whitening: row tile i of the degree needs columns 0 .. 8 i + 7 of Linv_l (lower triangular) ----
-      const double sc = scl[l];
+      double sr[8];   // scale_l * r of this lane's eight points
+      {
+        const double sc = scl[l];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const double2 rr = *reinterpret_cast<const double2*>(rw + 8 * nt + 2 * t4);
+          sr[2 * nt] = sc * rr.x;
+          sr[2 * nt + 1] = sc * rr.y;
+        }
+      }
       for (int i = 0; i < ntl; ++i) {
         const int rloc = 8 * i + g;
         const bool rok = rloc < ml;
         const int kend = min(ml, 8 * i + 8);
         const double* Lrow = args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off + t4;
-        double av[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) av[q] = (rok && 4 * q + t4 < ml && 4 * q < kend) ? __ldg(Lrow + 4 * q) : 0.0;
         double acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (4 * q < kend) {
-            const double* zk = zt + q * (4 * FT_LD);
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(acc[2 * nt], acc[2 * nt + 1], av[q], zk[bidx[nt]]);
-          }
+        // exactly ceil(kend / 4) k-steps through a real branch: as predicated code the skipped DMMAs of the triangle were still issued
+        // (ncu: 1 720 instead of 1 212 DMMAs per tile at the headline shape, on a kernel whose top stall is the FP64 pipe)
+        switch ((kend + 3) >> 2) {
+          case 1: ft3_whiten_steps<1>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 2: ft3_whiten_steps<2>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 3: ft3_whiten_steps<3>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 4: ft3_whiten_steps<4>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 5: ft3_whiten_steps<5>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 6: ft3_whiten_steps<6>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 7: ft3_whiten_steps<7>(acc, Lrow, rok, ml, zt, bidx); break;
+          default: ft3_whiten_steps<8>(acc, Lrow, rok, ml, zt, bidx); break;
         }
         if (rok) {
           double* orow = args.out + (int64_t)(off + rloc) * args.ldo + p0;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             const int c = 8 * nt + 2 * t4;
-            const double2 rr = *reinterpret_cast<const double2*>(rw + c);
-            const double v0 = sc * rr.x * acc[2 * nt], v1 = sc * rr.y * acc[2 * nt + 1];
-            if (p0 + c + 1 < a.npts && vec_ok) *reinterpret_cast<double2*>(orow + c) = make_double2(v0, v1);
+            const double v0 = sr[2 * nt] * acc[2 * nt], v1 = sr[2 * nt + 1] * acc[2 * nt + 1];
+            if (full) *reinterpret_cast<double2*>(orow + c) = make_double2(v0, v1);
             else {
               if (p0 + c < a.npts) orow[c] = v0;
               if (p0 + c + 1 < a.npts) orow[c + 1] = v1;
