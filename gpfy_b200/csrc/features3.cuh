@@ -8,6 +8,9 @@
 // Every warp re-projects its tile's points (8 d bytes per point out of L1/L2, ~5 % of a unit's instructions).  Degrees are grouped on the
 // host (`ft3_groups`) so that tiny degrees (m_0 = 1, m_1 = d + 1) ride with a full one; units go round-robin over all warps of the grid,
 // consecutive units (same tile, next group) to the warps of one CTA.
+// One CTA of 16 warps per SM.  When it fits next to the 16 private tiles, the lower triangles of all Linv_l are staged once per CTA in
+// shared memory, row tile i of a degree as [8][8 i + 12] (8 i + 8 columns + 4 of padding: conflict-free A-fragment reads) - through L1 the
+// whitening's A fragments hit only every second time (ncu r02x: L1 hit rate 60 % with the coordinates included, long-scoreboard stalls).
 // Shapes: every m_l <= 32 (the private tile is 32 rows), padded dimension <= 32; the rest stays on features2_kernel.
 #pragma once
 #include "zonal_fwd2.cuh"
@@ -17,6 +20,7 @@ namespace gpfy {
 struct Features3Args {
   FeaturesArgs f;
   int ngrp;
+  int linv_doubles;   // ft3_linv_doubles: size of the staged triangles
   unsigned char grp_lo[GPFY_MAX_DEGREES + 2];   // group gi = degrees grp_lo[gi] .. grp_lo[gi + 1] - 1
 };
 
@@ -34,20 +38,31 @@ static inline bool ft3_groups(Features3Args* fa, const DegreeTable& deg) {
   return true;
 }
 
-static inline int ft3_smem_bytes(int Mp, int dimp) {
-  const int dbl = Mp * dimp + 8 * (32 * 32 + 32) + 3 * (GPFY_MAX_DEGREES + 2) + 4;
-  return dbl * 8 + (GPFY_MAX_DEGREES + 1) * 4 + 16;
+constexpr int FT3_WARPS = 16;
+// packed lower triangle of one degree with nt row tiles: tile i starts at 32 i^2 + 64 i, rows of 8 i + 12 doubles
+static inline int ft3_tri_doubles(int nt) { return 32 * nt * nt + 64 * nt; }
+static inline int ft3_linv_doubles(const DegreeTable& deg) {
+  int n = 0;
+  for (int l = 0; l < deg.F; ++l) n += ft3_tri_doubles((deg.m[l] + 7) / 8);
+  return n;
+}
+static inline int ft3_smem_bytes(int Mp, int dimp, int linv_doubles) {
+  const int dbl = Mp * dimp + FT3_WARPS * (32 * 32 + 32) + linv_doubles + 3 * (GPFY_MAX_DEGREES + 2) + 4;
+  return dbl * 8 + 2 * (GPFY_MAX_DEGREES + 1) * 4 + 16;
 }
 
 // NQ k-steps of one 8-row tile of the whitening: A fragments (rows of Linv_l through L1, columns past m_l as zeros) fetched ahead of
 // the tensor-core steps, B fragments from the warp's swizzled tile.  lrow = &Linv_l[row][t4]; `lane_row` = row inside the degree.
-template <int NQ>
+template <int NQ, bool LSM>
 __device__ __forceinline__ void ft3_whiten_steps(double (&acc)[8], const double* __restrict__ lrow, bool rok, int ml, const double* zt,
                                                  const int (&bidx)[4]) {
   const int t4 = threadIdx.x & 3;
   double av[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) av[q] = (rok && 4 * q + t4 < ml) ? __ldg(lrow + 4 * q) : 0.0;
+  for (int q = 0; q < NQ; ++q) {
+    if constexpr (LSM) av[q] = lrow[4 * q];   // staged copy: rows / columns past m_l are stored as zeros
+    else av[q] = (rok && 4 * q + t4 < ml) ? __ldg(lrow + 4 * q) : 0.0;
+  }
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const double* zk = zt + q * (4 * FT_LD);
@@ -56,8 +71,8 @@ __device__ __forceinline__ void ft3_whiten_steps(double (&acc)[8], const double*
   }
 }
 
-template <int DIMP>
-__global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant__ Features3Args args3) {
+template <int DIMP, bool LSM>
+__global__ void __launch_bounds__(32 * FT3_WARPS, 1) features3_kernel(const __grid_constant__ Features3Args args3) {
   static_assert(DIMP <= 32, "the coordinates are staged in the warp's 32 x 32 tile");
   constexpr int KS = DIMP / 4;
   const FeaturesArgs& args = args3.f;
@@ -66,35 +81,59 @@ __global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant
   __shared__ uint64_t bar;
   const int Mp = a.Mp;
   double* vs = smem;                           // [Mp][DIMP]
-  double* ztw = vs + Mp * DIMP;                // [8 warps][32][32] swizzled zonal tile of one degree (first the tile's coordinates)
-  double* rsw = ztw + 8 * 32 * 32;             // [8][32] radii (or 1)
-  double* leads = rsw + 8 * 32;                // [MAX_DEGREES + 2]
+  double* ztw = vs + Mp * DIMP;                // [16 warps][32][32] swizzled zonal tile of one degree (first the tile's coordinates)
+  double* rsw = ztw + FT3_WARPS * 32 * 32;     // [16][32] radii (or 1)
+  double* lts = rsw + FT3_WARPS * 32;          // packed lower triangles of Linv_l (LSM)
+  double* leads = lts + (LSM ? args3.linv_doubles : 0);   // [MAX_DEGREES + 2]
   double* scl = leads + GPFY_MAX_DEGREES + 2;  // [MAX_DEGREES + 2] per-degree output scale
   double* betas = scl + GPFY_MAX_DEGREES + 2;  // [MAX_DEGREES + 6]
   int* offs = reinterpret_cast<int*>(betas + GPFY_MAX_DEGREES + 6);  // [F + 1]
+  int* lbase = offs + GPFY_MAX_DEGREES + 1;    // [F] start of degree l in lts
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int F = a.deg.F;
-  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += 256) {
+  constexpr int NTHR = 32 * FT3_WARPS;
+  for (int i = tid; i < GPFY_MAX_DEGREES + 2; i += NTHR) {
     leads[i] = args.mt.lead[i];
     scl[i] = (i < F && args.scale) ? args.scale[i] : 1.0;
   }
-  for (int i = tid; i < GPFY_MAX_DEGREES + 6; i += 256) betas[i] = i < GPFY_MAX_DEGREES + 2 ? args.mt.beta[i] : 0.0;
+  for (int i = tid; i < GPFY_MAX_DEGREES + 6; i += NTHR) betas[i] = i < GPFY_MAX_DEGREES + 2 ? args.mt.beta[i] : 0.0;
   if (tid == 0) {
-    int o = 0;
-    for (int l = 0; l < F; ++l) { offs[l] = o; o += a.deg.m[l]; }
+    int o = 0, lb = 0;
+    for (int l = 0; l < F; ++l) {
+      offs[l] = o;
+      lbase[l] = lb;
+      o += a.deg.m[l];
+      const int nt = (a.deg.m[l] + 7) >> 3;
+      lb += 32 * nt * nt + 64 * nt;
+    }
     offs[F] = o;
   }
-  stage_params_tma(vs, a.vhat_p, (unsigned)(Mp * DIMP * 8), &bar);
-  __syncthreads();   // the only CTA barrier: parameters staged
+  if constexpr (LSM) {
+    for (int i = tid; i < args3.linv_doubles; i += NTHR) lts[i] = 0.0;
+  }
+  stage_params_tma(vs, a.vhat_p, (unsigned)(Mp * DIMP * 8), &bar);   // includes a CTA barrier before the copy is issued
+  __syncthreads();
+  if constexpr (LSM) {   // one warp per row: its columns 0 .. min(8 i + 8, m_l) - 1
+    for (int R = warp; R < a.M; R += FT3_WARPS) {
+      int l = 0;
+      while (R >= offs[l + 1]) ++l;
+      const int off = offs[l], ml = offs[l + 1] - off, r = R - off, i = r >> 3;
+      const int ncol = min(8 * i + 8, ml);
+      double* dst = lts + lbase[l] + 32 * i * i + 64 * i + (r & 7) * (8 * i + 12);
+      for (int k = lane; k < ncol; k += 32) dst[k] = args.Linv[(int64_t)R * Mp + off + k];
+    }
+    __syncthreads();
+  }
+  // from here on no CTA barrier
 
   double* zt = ztw + warp * 32 * 32;
   double* rw = rsw + warp * 32;
   const int ngrp = args3.ngrp;
   const int64_t tiles = (a.npts + 31) / 32;
   // unit u = tile * ngrp + group, walked with stride gridDim.x * 8 without a division per unit
-  const int stride = (int)gridDim.x * 8;
+  const int stride = (int)gridDim.x * FT3_WARPS;
   const int sdiv = stride / ngrp, smod = stride - sdiv * ngrp;
   const bool vec_ok = (args.ldo & 1) == 0;
   // lane-constant parts of the swizzled tile addresses (ft_at with a row index that is a multiple of 4 plus t4 / 8 j + g)
@@ -104,7 +143,7 @@ __global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant
   const int sidx = g * FT_LD;   // C fragment store: row 8 j + g, columns (8 nt + 2 t4) ^ ((g & 3) << 2)
   const int sswz = (g & 3) << 2;
 
-  const int u0 = (int)blockIdx.x * 8 + warp;
+  const int u0 = (int)blockIdx.x * FT3_WARPS + warp;
   int gi = u0 % ngrp;
   for (int64_t tile = u0 / ngrp; tile < tiles; tile += sdiv) {
     const int64_t p0 = tile * 32;
@@ -180,21 +219,22 @@ __global__ void __launch_bounds__(256, 2) features3_kernel(const __grid_constant
         const int rloc = 8 * i + g;
         const bool rok = rloc < ml;
         const int kend = min(ml, 8 * i + 8);
-        const double* Lrow = args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off + t4;
+        const double* Lrow = LSM ? lts + lbase[l] + 32 * i * i + 64 * i + g * (8 * i + 12) + t4
+                                 : args.Linv + (int64_t)(off + (rok ? rloc : 0)) * Mp + off + t4;
         double acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.0;
         // exactly ceil(kend / 4) k-steps through a real branch: as predicated code the skipped DMMAs of the triangle were still issued
         // (ncu: 1 720 instead of 1 212 DMMAs per tile at the headline shape, on a kernel whose top stall is the FP64 pipe)
         switch ((kend + 3) >> 2) {
-          case 1: ft3_whiten_steps<1>(acc, Lrow, rok, ml, zt, bidx); break;
-          case 2: ft3_whiten_steps<2>(acc, Lrow, rok, ml, zt, bidx); break;
-          case 3: ft3_whiten_steps<3>(acc, Lrow, rok, ml, zt, bidx); break;
-          case 4: ft3_whiten_steps<4>(acc, Lrow, rok, ml, zt, bidx); break;
-          case 5: ft3_whiten_steps<5>(acc, Lrow, rok, ml, zt, bidx); break;
-          case 6: ft3_whiten_steps<6>(acc, Lrow, rok, ml, zt, bidx); break;
-          case 7: ft3_whiten_steps<7>(acc, Lrow, rok, ml, zt, bidx); break;
-          default: ft3_whiten_steps<8>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 1: ft3_whiten_steps<1, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 2: ft3_whiten_steps<2, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 3: ft3_whiten_steps<3, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 4: ft3_whiten_steps<4, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 5: ft3_whiten_steps<5, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 6: ft3_whiten_steps<6, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          case 7: ft3_whiten_steps<7, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
+          default: ft3_whiten_steps<8, LSM>(acc, Lrow, rok, ml, zt, bidx); break;
         }
         if (rok) {
           double* orow = args.out + (int64_t)(off + rloc) * args.ldo + p0;

@@ -734,11 +734,17 @@ static int launch_features2(cudaStream_t st, const FeaturesArgs& fa) {
 template <int DIMP>
 static int launch_features3(cudaStream_t st, const Features3Args& fa) {
   if constexpr (DIMP <= 32) {
-    const int smem = ft3_smem_bytes(fa.f.z.Mp, DIMP);
     const int64_t units = ((fa.f.z.npts + 31) / 32) * fa.ngrp;
-    const unsigned grid = (unsigned)std::min<int64_t>((units + 7) / 8, 2 * device_sms());
-    GPFY_TRY(set_smem(features3_kernel<DIMP>, smem));
-    features3_kernel<DIMP><<<grid, 256, smem, st>>>(fa);
+    const unsigned grid = (unsigned)std::min<int64_t>((units + FT3_WARPS - 1) / FT3_WARPS, device_sms());
+    const int smem_l = ft3_smem_bytes(fa.f.z.Mp, DIMP, fa.linv_doubles);
+    if (smem_l <= 227 * 1024 - 64) {   // the triangles of Linv fit next to the private tiles
+      GPFY_TRY(set_smem((features3_kernel<DIMP, true>), smem_l));
+      features3_kernel<DIMP, true><<<grid, 32 * FT3_WARPS, smem_l, st>>>(fa);
+    } else {
+      const int smem = ft3_smem_bytes(fa.f.z.Mp, DIMP, 0);
+      GPFY_TRY(set_smem((features3_kernel<DIMP, false>), smem));
+      features3_kernel<DIMP, false><<<grid, 32 * FT3_WARPS, smem, st>>>(fa);
+    }
     GPFY_COUNT_LAUNCH();
     GPFY_LAUNCH_OK();
     return GPFY_OK;
@@ -1251,8 +1257,12 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
   GPFY_TRY(run_prologue(st, desc, p, ws, apply_to_sphere ? w : vhat, apply_to_sphere ? b : vhat, nullptr, nullptr, vhat, lcat,
                         nullptr, nullptr, false));
   RecCoef rc = make_rec_coef(desc->alpha);
-  if (ft_smem_bytes(Mp, s.dimp) <= 113 * 1024 && !debug_option(DBG_OLD_FEATURES)) {
-    // one fused kernel (two CTAs per SM): the zonal values stay in shared memory
+  Features3Args f3;
+  // barrier-free fused kernel (one warp = one (tile, degree group) unit) when every degree fits its 32-row private tile
+  const bool use_f3 = !debug_option(DBG_OLD_FEATURES) && !debug_option(DBG_NO_FEATURES3) && s.dimp <= 32 &&
+                      ft3_smem_bytes(Mp, s.dimp, 0) <= 227 * 1024 - 64 && ft3_groups(&f3, deg);
+  if (use_f3 || (ft_smem_bytes(Mp, s.dimp) <= 113 * 1024 && !debug_option(DBG_OLD_FEATURES))) {
+    // one fused kernel: the zonal values stay in shared memory
     FeaturesArgs fa;
     ZonalArgs& za = fa.z;
     za.Yg = nullptr; za.ZPb = nullptr; za.Zh = za.Zl = nullptr; za.s2g = nullptr; za.wq = za.wp = za.cq = nullptr; za.proj = apply_to_sphere ? s.proj : 0;
@@ -1263,10 +1273,9 @@ int gpfy_sh_features_fwd(void* stream, const GpfyDesc* desc, int64_t n, const do
     za.deg = deg; za.rc = rc;
     fa.mt = make_monic(desc->alpha);
     fa.Linv = ws + p.o_linv; fa.scale = degree_scale; fa.mul_r = mul_r; fa.out = out; fa.ldo = n; fa.r_out = r_out;
-    // barrier-free variant (one warp = one (tile, degree group) unit) when every degree fits its 32-row private tile
-    Features3Args f3;
-    if (s.dimp <= 32 && ft3_smem_bytes(Mp, s.dimp) <= 113 * 1024 && !debug_option(DBG_NO_FEATURES3) && ft3_groups(&f3, deg)) {
+    if (use_f3) {
       f3.f = fa;
+      f3.linv_doubles = ft3_linv_doubles(deg);
       GPFY_DISPATCH_DIMP(s.dimp, GPFY_TRY(launch_features3<DIMP>(st, f3)));
       return GPFY_OK;
     }
