@@ -13,6 +13,7 @@
 // whitening's A fragments hit only every second time (ncu r02x: L1 hit rate 60 % with the coordinates included, long-scoreboard stalls).
 // Shapes: every m_l <= 32 (the private tile is 32 rows), padded dimension <= 32; the rest stays on features2_kernel.
 #pragma once
+#include <algorithm>
 #include "zonal_fwd2.cuh"
 
 namespace gpfy {
@@ -24,14 +25,21 @@ struct Features3Args {
   unsigned char grp_lo[GPFY_MAX_DEGREES + 2];   // group gi = degrees grp_lo[gi] .. grp_lo[gi + 1] - 1
 };
 
-// host: consecutive degrees are merged while the group stays within 40 rows (a full 30/32-row degree plus the small leading ones)
+// host: consecutive degrees are merged into ~96-row groups of about equal size (three full 30-row degrees): a unit then pays for its
+// tile's coordinates (a load from HBM / L2 nothing hides, ncu r02x: 12 % of the stall samples) once per ~3 k FP64 instructions
 static inline bool ft3_groups(Features3Args* fa, const DegreeTable& deg) {
-  int n = 0, rows = 0;
-  fa->grp_lo[0] = 0;
+  int total = 0;
   for (int l = 0; l < deg.F; ++l) {
     if (deg.m[l] > 32) return false;
-    if (rows > 0 && rows + deg.m[l] > 40) { fa->grp_lo[++n] = (unsigned char)l; rows = 0; }
-    rows += deg.m[l];
+    total += deg.m[l];
+  }
+  const int G = std::max(1, (total + 48) / 96);
+  int n = 0, cum = 0;
+  fa->grp_lo[0] = 0;
+  for (int l = 0; l < deg.F; ++l) {
+    cum += deg.m[l];
+    // close the group at the degree whose end is nearest to the next multiple of total / G
+    if (n + 1 < G && l + 1 < deg.F && 2 * cum * G >= (2 * (n + 1)) * total - deg.m[l + 1] * G) fa->grp_lo[++n] = (unsigned char)(l + 1);
   }
   fa->grp_lo[++n] = (unsigned char)deg.F;
   fa->ngrp = n;
@@ -132,9 +140,16 @@ __global__ void __launch_bounds__(32 * FT3_WARPS, 1) features3_kernel(const __gr
   double* rw = rsw + warp * 32;
   const int ngrp = args3.ngrp;
   const int64_t tiles = (a.npts + 31) / 32;
-  // unit u = tile * ngrp + group, walked with stride gridDim.x * 8 without a division per unit
+  // unit u = tile * ngrp + group.  Round k of the grid covers units [k * stride, (k + 1) * stride); in it warp w takes position
+  // (w + k * skew) mod stride, the skew chosen so that a warp's group index walks through ALL groups (they differ in size) even
+  // when ngrp divides the stride; neighbouring warps keep neighbouring units (same tile: its coordinates come out of L1 / L2).
   const int stride = (int)gridDim.x * FT3_WARPS;
-  const int sdiv = stride / ngrp, smod = stride - sdiv * ngrp;
+  int skew = 0;
+  {
+    auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+    while (gcd((stride + skew) % ngrp, ngrp) != 1 && skew < ngrp) ++skew;   // ngrp = 1: gcd(0, 1) = 1
+  }
+  const int64_t units = tiles * ngrp;
   const bool vec_ok = (args.ldo & 1) == 0;
   // lane-constant parts of the swizzled tile addresses (ft_at with a row index that is a multiple of 4 plus t4 / 8 j + g)
   int bidx[4];   // B fragment of k-step k0: zt[k0 * 32 + bidx[nt]] = tile[k0 + t4][8 nt + g]
@@ -143,9 +158,14 @@ __global__ void __launch_bounds__(32 * FT3_WARPS, 1) features3_kernel(const __gr
   const int sidx = g * FT_LD;   // C fragment store: row 8 j + g, columns (8 nt + 2 t4) ^ ((g & 3) << 2)
   const int sswz = (g & 3) << 2;
 
-  const int u0 = (int)blockIdx.x * FT3_WARPS + warp;
-  int gi = u0 % ngrp;
-  for (int64_t tile = u0 / ngrp; tile < tiles; tile += sdiv) {
+  int pos = (int)blockIdx.x * FT3_WARPS + warp;
+  for (int64_t ubase = 0; ubase < units; ubase += stride) {
+    const int64_t u = ubase + pos;
+    pos += skew;
+    if (pos >= stride) pos -= stride;
+    if (u >= units) continue;   // only in the last round
+    const int64_t tile = u / ngrp;
+    const int gi = (int)(u - tile * ngrp);
     const int64_t p0 = tile * 32;
     const bool full = vec_ok && p0 + 32 <= a.npts;   // whole tile in range and 16-byte aligned rows: unguarded vector stores
     // ---- the tile's points onto the sphere (lane = point), B fragments of the projection through the private tile ----
@@ -252,8 +272,6 @@ __global__ void __launch_bounds__(32 * FT3_WARPS, 1) features3_kernel(const __gr
       }
       __syncwarp();   // the tile is consumed before the next degree (or the next unit's coordinates) overwrites it
     }
-    gi += smod;
-    if (gi >= ngrp) { gi -= ngrp; ++tile; }
   }
 }
 
