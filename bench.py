@@ -473,7 +473,7 @@ def run_ours(a):
     roofline["contraction_path"] = path
     roofline["kernels"] = {k: {kk: v[kk] for kk in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "kernel_share_of_step")}
                            for k, v in classes.items()}
-    roofline["kernels"]["zonal"] = {"kernel": "zonal_fwd2 + zonal_bwd3/4 (+ lik_point, dvhat)", "bound": "fp64",
+    roofline["kernels"]["zonal"] = {"kernel": "zonal_fwd3/2 + zonal_bwd3/4 (+ lik_point, dvhat)", "bound": "fp64",
                                     "achieved": (prob["alg_flops_per_point"] - 3.0 * M * M) * n_local / (z_ms * 1e-3 / a.steps) * 1e-12 if z_ms > 0 else None,
                                     "peak": fp64_peak, "unit": "TFLOP/s", "kernel_share_of_step": z_ms / (ms * a.steps)}
     roofline["step"] = {"alg_flops_per_point": prob["alg_flops_per_point"], "achieved_tflops_per_gpu": step_tflops,

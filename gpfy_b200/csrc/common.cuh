@@ -52,7 +52,7 @@ int device_sms();                                             // SM count of the
 int device_configure_once(unsigned bit, const void* kernel, int smem_bytes);  // cudaFuncSetAttribute once per device
 
 // Development switches (gpfy_debug_set_option; never read from the environment, default 0 = production path).
-enum { DBG_CHUNK_MULT = 0, DBG_OLD_FWD = 1, DBG_NO_FUSED_BWD = 2, DBG_OLD_FEATURES = 3, DBG_NO_BWD4 = 4, DBG_NO_SYRK32 = 5, DBG_SYRK32_KF = 6, DBG_NO_I8 = 7, DBG_NO_SYRK_SLICE = 8, DBG_NO_FEATURES3 = 9, DBG_COUNT = 10 };
+enum { DBG_CHUNK_MULT = 0, DBG_OLD_FWD = 1, DBG_NO_FUSED_BWD = 2, DBG_OLD_FEATURES = 3, DBG_NO_BWD4 = 4, DBG_NO_SYRK32 = 5, DBG_SYRK32_KF = 6, DBG_NO_I8 = 7, DBG_NO_SYRK_SLICE = 8, DBG_NO_FEATURES3 = 9, DBG_NO_FWD3 = 10, DBG_COUNT = 12 };
 int debug_option(int which);
 
 // ------------------------------------------------------------------------------------------------

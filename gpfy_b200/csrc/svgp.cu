@@ -14,6 +14,7 @@
 #include "zonal_bwd4.cuh"
 #include "zonal_fwd2.cuh"
 #include "features3.cuh"
+#include "zonal_fwd3.cuh"
 #include "basis.cuh"
 #include "features_vjp.cuh"
 #include "syrk_tf32.cuh"
@@ -691,6 +692,24 @@ static int launch_zonal(cudaStream_t st, const ZonalArgs& a) {
     fa.dbg = 0;
 #endif
     const int pmax = a.P == 1 ? 1 : (a.P == 2 ? 2 : 4);
+    // barrier-free variant (one warp = one 32-point tile through all row tiles) when its per-warp tiles fit twice per SM
+    const int smem3 = zf3_smem_bytes(a.Mp, DIMP, a.P, a.mz != nullptr, pmax);
+    // (and when there are enough tiles to give every resident warp one: a small batch spreads better over zonal_fwd2_kernel's
+    // seven warps per tile)
+    if (smem3 <= 113 * 1024 && grid >= (unsigned)(2 * ZF3_WARPS * device_sms()) && !debug_option(DBG_NO_FWD3)) {
+      const unsigned grid3 = (unsigned)std::min<int64_t>((grid + ZF3_WARPS - 1) / ZF3_WARPS, 2 * device_sms());
+#define GPFY_ZF3(PM, ZP)                                                            \
+  {                                                                                 \
+    GPFY_TRY(set_smem((zonal_fwd3_kernel<DIMP, PM, ZP>), smem3));                   \
+    zonal_fwd3_kernel<DIMP, PM, ZP><<<grid3, 32 * ZF3_WARPS, smem3, st>>>(fa);      \
+  }
+      if (a.ZPb) { if (pmax != 1) { set_error("the derivative panel is built for P = 1"); return GPFY_EINVAL; } GPFY_ZF3(1, true) }
+      else if (pmax == 1) GPFY_ZF3(1, false) else if (pmax == 2) GPFY_ZF3(2, false) else GPFY_ZF3(4, false)
+#undef GPFY_ZF3
+      GPFY_COUNT_LAUNCH();
+      GPFY_LAUNCH_OK();
+      return GPFY_OK;
+    }
     const int smem = zf2_smem_bytes(a.Mp, DIMP, a.P, a.mz != nullptr, pmax);
     const unsigned pgrid = std::min(grid, (unsigned)(2 * device_sms()));  // persistent: two CTAs per SM
 #define GPFY_ZF(PM, ZP)                                                \

@@ -394,7 +394,7 @@ class HotPath:
         return out[0], out[1:1 + M * P].view(M, P), out[1 + M * P:].view(P, M, M)
 
 
-DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4, "no_syrk32": 5, "syrk32_kf": 6, "no_i8": 7, "no_syrk_slice": 8, "no_features3": 9}
+DEBUG_OPTIONS = {"chunk_mult": 0, "old_fwd": 1, "no_fused_bwd": 2, "old_features": 3, "no_bwd4": 4, "no_syrk32": 5, "syrk32_kf": 6, "no_i8": 7, "no_syrk_slice": 8, "no_features3": 9, "no_fwd3": 10}
 
 
 def debug_option(name, value):
