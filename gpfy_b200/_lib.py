@@ -100,6 +100,7 @@ _SIGNATURES = {
     "gpfy_allreduce_packed": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),
     "gpfy_debug_kernel_timing": (ctypes.c_int, [ctypes.c_int]),
     "gpfy_debug_i8_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "gpfy_debug_features3_plan": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "gpfy_debug_set_option": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "gpfy_debug_kernel_time": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "gpfy_to_sphere": (ctypes.c_int, [_P, ctypes.POINTER(GpfyDesc), ctypes.c_int64, _P, _P, _P, _P, _P]),

@@ -1174,6 +1174,24 @@ GPFY_API int gpfy_debug_i8_plan(int Mp, int sms, int* out, int out_len) {
   return GPFY_OK;
 }
 
+// The barrier-free feature kernel's degree groups for degrees of m[0..F) rows (host arithmetic only; tests/test_features3_plan_cpu.py):
+// out[0] = taken (0 / 1: every m_l <= 32), out[1] = groups, out[2] = doubles of the staged Linv triangles, out[3] / out[4] = shared-memory
+// bytes with / without the staged triangles, then the first degree of every group and F.
+GPFY_API int gpfy_debug_features3_plan(const int* m, int F, int Mp, int dimp, int* out, int out_len) {
+  if (!m || !out || F < 1 || F > GPFY_MAX_DEGREES || out_len < 6 + GPFY_MAX_DEGREES + 1) return GPFY_EINVAL;
+  DegreeTable deg;
+  deg.F = F;
+  for (int l = 0; l < F; ++l) deg.m[l] = m[l];
+  Features3Args f3;
+  const bool ok = ft3_groups(&f3, deg);
+  out[0] = ok ? 1 : 0;
+  if (!ok) return GPFY_OK;
+  out[1] = f3.ngrp; out[2] = ft3_linv_doubles(deg);
+  out[3] = ft3_smem_bytes(Mp, dimp, out[2]); out[4] = ft3_smem_bytes(Mp, dimp, 0);
+  for (int g = 0; g <= f3.ngrp; ++g) out[5 + g] = f3.grp_lo[g];
+  return GPFY_OK;
+}
+
 GPFY_API int gpfy_debug_kernel_timing(int enable) {
   g_timer.on = enable != 0;
   for (int k = 0; k < TK_COUNT; ++k) g_timer.used[k] = 0;
